@@ -1,0 +1,1013 @@
+/*
+ * inflate.c -- oracle (test infrastructure): CPU restatement of the reference decoder,
+ * inflate/inflate.ts + inftrees.ts + inffast.ts + inflate/constants.ts, including the deflate64
+ * (windowBits -16) variant.  Resumable at every bit like the reference, same return codes and
+ * messages.  Not part of the product path.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "zs_oracle.h"
+
+/* InflateMode, common/types.ts:165-198 (only the relative order matters) */
+enum {
+    M_HEAD = 16180, M_FLAGS, M_TIME, M_OS, M_EXLEN, M_EXTRA, M_NAME, M_COMMENT, M_HCRC, M_DICTID,
+    M_DICT, M_TYPE, M_TYPEDO, M_STORED, M_COPY_, M_COPY, M_TABLE, M_LENLENS, M_CODELENS, M_LEN_,
+    M_LEN, M_LENEXT, M_DIST, M_DISTEXT, M_MATCH, M_LIT, M_CHECK, M_LENGTH, M_DONE, M_BAD, M_MEM,
+    M_SYNC
+};
+
+#define ENOUGH_LENS 852
+#define ENOUGH_DISTS 592
+#define ENOUGH_DISTS_9 594
+#define MAXBITS 15
+
+#define E_OP(e) ((e) >> 24)
+#define E_BITS(e) (((e) >> 16) & 0xffu)
+#define E_VAL(e) ((e) & 0xffffu)
+#define PACK(op, bits, val) (((uint32_t)(op) << 24) | ((uint32_t)(bits) << 16) | (uint32_t)(val))
+
+struct zo_inflate_stream {
+    /* Stream, common/types.ts:1-15 */
+    const uint8_t* next_in;
+    size_t avail_in;
+    uint64_t total_in;
+    uint8_t* next_out;
+    size_t avail_out;
+    uint64_t total_out;
+    const char* msg;
+    uint32_t adler;
+    int data_type;
+    int inited;
+    /* InflateState, inflate/utils.ts:11-50 */
+    int mode, last, wrap, havedict, flags;
+    unsigned dmax;
+    uint32_t check;
+    uint64_t total;
+    unsigned w_bits, w_size, w_have, w_next;
+    uint8_t* window;
+    size_t window_alloc;
+    uint32_t hold;
+    unsigned bits;
+    unsigned length, offset, extra;
+    const uint32_t* lencode;
+    const uint32_t* distcode;
+    unsigned lenbits, distbits;
+    unsigned ncode, nlen, ndist, have;
+    uint16_t lens[320];
+    uint16_t work[288];
+    uint32_t codes[ENOUGH_LENS + ENOUGH_DISTS_9];
+    int sane, back;
+    unsigned was;
+    int deflate64;
+};
+
+/* ---- decode base/extra tables, inflate/constants.ts:8-45 (RFC 1951 3.2.5 + deflate64) -------- */
+static uint16_t LBASE[31], LEXT[31], DBASE[32], DEXT[32];
+static uint16_t LBASE_9[31], LEXT_9[31], DBASE_9[32], DEXT_9[32];
+static int base_ready = 0;
+
+__attribute__((constructor)) static void base_tables_build(void) {
+    /* length codes 257..284: extra bits 0 x8, then 1..5 x4 each; bases start at 3 */
+    unsigned len = 3, i;
+    for (i = 0; i < 28; i++) {
+        unsigned eb = i < 8 ? 0 : (i - 4) / 4;
+        LBASE[i] = LBASE_9[i] = (uint16_t)len;
+        LEXT[i] = (uint16_t)(16 + eb);
+        LEXT_9[i] = (uint16_t)(128 + eb);
+        len += 1u << eb;
+    }
+    /* code 285: 258 / 0 extra bits in deflate; base 3 / 16 extra bits in deflate64.  286, 287
+     * carry invalid-code markers (op has the 64 bit set). */
+    LBASE[28] = 258; LEXT[28] = 16;  LBASE[29] = 0; LEXT[29] = 73; LBASE[30] = 0; LEXT[30] = 200;
+    LBASE_9[28] = 3; LEXT_9[28] = 144; LBASE_9[29] = 0; LEXT_9[29] = 72; LBASE_9[30] = 0; LEXT_9[30] = 78;
+    /* distance codes 0..29: extra bits 0 x4 then 1..13 x2 each; bases start at 1 */
+    unsigned dist = 1;
+    for (i = 0; i < 30; i++) {
+        unsigned eb = i < 4 ? 0 : (i - 2) / 2;
+        DBASE[i] = DBASE_9[i] = (uint16_t)dist;
+        DEXT[i] = (uint16_t)(16 + eb);
+        DEXT_9[i] = (uint16_t)(128 + eb);
+        dist += 1u << eb;
+    }
+    DBASE[30] = DBASE[31] = 0; DEXT[30] = DEXT[31] = 64;
+    DBASE_9[30] = 32769; DBASE_9[31] = 49153; DEXT_9[30] = DEXT_9[31] = 142;
+    base_ready = 1;
+}
+
+/* createTableEntry, inftrees.ts:279-307 */
+static uint32_t table_entry(const uint16_t* work, unsigned sym, unsigned len, unsigned drop, int type,
+                            const uint16_t* base, const uint16_t* extra, int match, int deflate64) {
+    int w = (int)work[sym];
+    if (deflate64 ? (w < match) : (w + 1 < match)) return PACK(0, len - drop, w);
+    if (deflate64 ? (w > match) : (w >= match)) {
+        int idx;
+        if (deflate64 && type == 1) idx = w - 257;
+        else idx = deflate64 ? w : w - match;
+        return PACK(extra[idx], len - drop, base[idx]);
+    }
+    return PACK(32 + 64, len - drop, 0);
+}
+
+/* inflate_table, inftrees.ts:62-277 */
+int zo_inflate_table(int type, const uint16_t* lens, unsigned codes, uint32_t* table, unsigned* bits,
+                     uint16_t* work, unsigned* index, int deflate64) {
+    unsigned len, sym, min, max, root, curr, drop, used, huff, incr, fill, mask, next_index;
+    int left, low;
+    uint16_t count[MAXBITS + 1], offs[MAXBITS + 1];
+    const uint16_t *base, *extra;
+    int match;
+    if (!base_ready) base_tables_build();
+    const unsigned enough_d = deflate64 ? ENOUGH_DISTS_9 : ENOUGH_DISTS;
+
+    for (len = 0; len <= MAXBITS; len++) count[len] = 0;
+    for (sym = 0; sym < codes; sym++) count[lens[sym]]++;
+
+    root = *bits;
+    for (max = MAXBITS; max >= 1; max--)
+        if (count[max] != 0) break;
+    if (root > max) root = max;
+    if (max == 0) {
+        if (!deflate64) { /* PARAMS._createTableWhenNoCodes, inftrees.ts:45,58,113-123 */
+            table[0] = PACK(64, 1, 0);
+            table[1] = PACK(64, 1, 0);
+            *bits = 1;
+            return 0;
+        }
+        return -1;
+    }
+    for (min = 1; min < max; min++)
+        if (count[min] != 0) break;
+    if (root < min) root = min;
+
+    left = 1;
+    for (len = 1; len <= MAXBITS; len++) {
+        left <<= 1;
+        left -= count[len];
+        if (left < 0) return -1;
+    }
+    if (left > 0 && (type == 0 || max != 1)) return -1;
+
+    offs[1] = 0;
+    for (len = 1; len < MAXBITS; len++) offs[len + 1] = (uint16_t)(offs[len] + count[len]);
+    for (sym = 0; sym < codes; sym++)
+        if (lens[sym] != 0) work[offs[lens[sym]]++] = (uint16_t)sym;
+
+    switch (type) {
+        case 0: base = extra = work; match = deflate64 ? 19 : 20; break;
+        case 1:
+            base = deflate64 ? LBASE_9 : LBASE; extra = deflate64 ? LEXT_9 : LEXT;
+            match = deflate64 ? 256 : 257; break;
+        default:
+            base = deflate64 ? DBASE_9 : DBASE; extra = deflate64 ? DEXT_9 : DEXT;
+            match = deflate64 ? -1 : 0;
+    }
+
+    huff = 0; sym = 0; len = min; next_index = *index; curr = root; drop = 0; low = -1;
+    used = 1u << root;
+    mask = used - 1;
+
+#define TOO_BIG() ((type == 1 && (deflate64 ? used >= ENOUGH_LENS : used > ENOUGH_LENS)) || \
+                   (type == 2 && (deflate64 ? used >= enough_d : used > enough_d)))
+    if (TOO_BIG()) return 1;
+
+    for (;;) {
+        uint32_t here = table_entry(work, sym, len, drop, type, base, extra, match, deflate64);
+        incr = 1u << (len - drop);
+        fill = 1u << curr;
+        do {
+            fill -= incr;
+            table[next_index + (huff >> drop) + fill] = here;
+        } while (fill != 0);
+
+        incr = 1u << (len - 1);
+        while (huff & incr) incr >>= 1;
+        if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
+
+        sym++;
+        if (--count[len] == 0) {
+            if (len == max) break;
+            len = lens[work[sym]];
+        }
+
+        if (len > root && (int)(huff & mask) != low) {
+            if (drop == 0) drop = root;
+            next_index += 1u << curr;
+            curr = len - drop;
+            left = 1 << curr;
+            while (curr + drop < max) {
+                left -= count[curr + drop];
+                if (left <= 0) break;
+                curr++;
+                left <<= 1;
+            }
+            used += 1u << curr;
+            if (TOO_BIG()) return 1;
+            low = (int)(huff & mask);
+            table[*index + (unsigned)low] = PACK(curr, root, next_index - *index);
+        }
+    }
+
+    if (huff != 0) {
+        uint32_t here = PACK(64, len - drop, 0);
+        while (huff != 0) {
+            if (drop != 0 && (int)(huff & mask) != low) {
+                drop = 0; len = root; next_index = *index; curr = root;
+                here = PACK(64, len, 0);
+            }
+            table[next_index + (huff >> drop)] = here;
+            incr = 1u << (len - 1);
+            while (huff & incr) incr >>= 1;
+            if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
+        }
+    }
+    *index += used;
+    *bits = root;
+    return 0;
+#undef TOO_BIG
+}
+
+/* ---- stream object -------------------------------------------------------------------------- */
+
+zo_inflate_stream* zo_inflate_new(void) {
+    zo_inflate_stream* s = (zo_inflate_stream*)calloc(1, sizeof(*s));
+    if (s) { s->msg = ""; s->mode = M_HEAD; s->inited = 1; }
+    return s;
+}
+
+void zo_inflate_free(zo_inflate_stream* s) {
+    if (!s) return;
+    free(s->window);
+    free(s);
+}
+
+/* inflateStateCheck, inflate.ts:78-93 */
+static int state_check(const zo_inflate_stream* s) {
+    if (!s || !s->inited) return 1;
+    if (s->deflate64 && (s->mode < M_TYPE || s->mode > M_BAD)) return 1;
+    if (!s->deflate64 && (s->mode < M_HEAD || s->mode > M_SYNC)) return 1;
+    return 0;
+}
+
+/* inflateResetKeep, inflate.ts:95-122 */
+static int reset_keep(zo_inflate_stream* s) {
+    if (state_check(s)) return ZO_STREAM_ERROR;
+    s->total_in = s->total_out = s->total = 0;
+    s->msg = "";
+    if (s->wrap) s->adler = (uint32_t)(s->wrap & 1);
+    s->mode = s->deflate64 ? M_TYPE : M_HEAD;
+    s->last = 0;
+    s->havedict = 0;
+    s->flags = -1;
+    s->dmax = s->deflate64 ? 65536u : 32768u;
+    s->hold = 0;
+    s->bits = 0;
+    s->lencode = s->distcode = s->codes;
+    s->sane = 1;
+    s->back = -1;
+    return ZO_OK;
+}
+
+/* inflateReset, inflate.ts:124-136 */
+int zo_inflate_reset(zo_inflate_stream* s) {
+    if (state_check(s)) return ZO_STREAM_ERROR;
+    s->w_size = 0; s->w_have = 0; s->w_next = 0;
+    return reset_keep(s);
+}
+
+/* inflateReset2, inflate.ts:138-172 */
+static int reset2(zo_inflate_stream* s, int window_bits) {
+    int wrap;
+    if (state_check(s)) return ZO_STREAM_ERROR;
+    if (window_bits < 0) {
+        if (window_bits < -16) return ZO_STREAM_ERROR;
+        wrap = 0;
+        s->deflate64 = window_bits == -16;
+        window_bits = -window_bits;
+    } else {
+        wrap = (window_bits >> 4) + 5;
+        s->deflate64 = 0;
+        if (window_bits < 48) window_bits &= 15;
+    }
+    int max_wb = s->deflate64 ? 16 : 15;
+    if (window_bits && (window_bits < 8 || window_bits > max_wb)) return ZO_STREAM_ERROR;
+    if (s->window && s->w_bits != (unsigned)window_bits) {
+        free(s->window);
+        s->window = NULL;
+        s->window_alloc = 0;
+    }
+    s->wrap = wrap;
+    s->w_bits = (unsigned)window_bits;
+    return zo_inflate_reset(s);
+}
+
+/* inflateInit2_, inflate.ts:174-192 */
+int zo_inflate_init2(zo_inflate_stream* s, int window_bits) {
+    if (!s) return ZO_STREAM_ERROR;
+    s->msg = "";
+    int d64 = window_bits == -16;
+    free(s->window);
+    const uint8_t* ni = s->next_in; size_t ai = s->avail_in;
+    uint8_t* no = s->next_out; size_t ao = s->avail_out;
+    memset(s, 0, sizeof(*s));
+    s->next_in = ni; s->avail_in = ai; s->next_out = no; s->avail_out = ao;
+    s->inited = 1;
+    s->msg = "";
+    s->deflate64 = d64;
+    s->mode = d64 ? M_TYPE : M_HEAD;
+    return reset2(s, window_bits);
+}
+
+int zo_inflate_end(zo_inflate_stream* s) { return state_check(s) ? ZO_STREAM_ERROR : ZO_OK; }
+
+void zo_inflate_set_input(zo_inflate_stream* s, const uint8_t* p, size_t n) { s->next_in = p; s->avail_in = n; }
+void zo_inflate_set_output(zo_inflate_stream* s, uint8_t* p, size_t n) { s->next_out = p; s->avail_out = n; }
+size_t zo_inflate_avail_in(const zo_inflate_stream* s) { return s->avail_in; }
+size_t zo_inflate_avail_out(const zo_inflate_stream* s) { return s->avail_out; }
+uint64_t zo_inflate_total_in(const zo_inflate_stream* s) { return s->total_in; }
+uint64_t zo_inflate_total_out(const zo_inflate_stream* s) { return s->total_out; }
+uint32_t zo_inflate_adler(const zo_inflate_stream* s) { return s->adler; }
+const char* zo_inflate_msg(const zo_inflate_stream* s) { return s->msg; }
+int zo_inflate_mode(const zo_inflate_stream* s) { return s->mode; }
+
+/* fixedtables, inflate.ts:218-280 -- separate caches for deflate and deflate64 */
+static uint32_t fixed_tab[2][ENOUGH_LENS + ENOUGH_DISTS_9];
+static unsigned fixed_dist_at[2];
+static int fixed_ready[2] = {0, 0};
+
+static void fixed_build(int k) {
+    uint16_t lens[288], work[288];
+    unsigned sym = 0, bits, idx = 0;
+    while (sym < 144) lens[sym++] = 8;
+    while (sym < 256) lens[sym++] = 9;
+    while (sym < 280) lens[sym++] = 7;
+    while (sym < 288) lens[sym++] = 8;
+    bits = 9;
+    zo_inflate_table(1, lens, 288, fixed_tab[k], &bits, work, &idx, k);
+    fixed_dist_at[k] = idx;
+    for (sym = 0; sym < 32; sym++) lens[sym] = 5;
+    bits = 5;
+    zo_inflate_table(2, lens, 32, fixed_tab[k], &bits, work, &idx, k);
+    fixed_ready[k] = 1;
+}
+
+/* built once at load so that concurrent streams (bench_driver.c) never race on the cache */
+__attribute__((constructor)) static void fixed_build_all(void) { fixed_build(0); fixed_build(1); }
+
+static void fixedtables(zo_inflate_stream* s) {
+    int k = s->deflate64 ? 1 : 0;
+    if (!fixed_ready[k]) fixed_build(k);
+    s->lencode = fixed_tab[k];
+    s->lenbits = 9;
+    s->distcode = fixed_tab[k] + fixed_dist_at[k];
+    s->distbits = 5;
+}
+
+/* updatewindow, inflate.ts:282-324: `end` points one past the last byte written */
+static int updatewindow(zo_inflate_stream* s, const uint8_t* end, size_t copy) {
+    if (!s->window) {
+        s->window_alloc = (size_t)1 << s->w_bits;
+        s->window = (uint8_t*)malloc(s->window_alloc ? s->window_alloc : 1);
+        if (!s->window) return 1;
+    }
+    if (s->w_size == 0) {
+        s->w_size = 1u << s->w_bits;
+        s->w_next = 0;
+        s->w_have = 0;
+    }
+    if (copy >= s->w_size) {
+        memcpy(s->window, end - s->w_size, s->w_size);
+        s->w_next = 0;
+        s->w_have = s->w_size;
+    } else {
+        size_t dist = s->w_size - s->w_next;
+        if (dist > copy) dist = copy;
+        memcpy(s->window + s->w_next, end - copy, dist);
+        copy -= dist;
+        if (copy) {
+            memcpy(s->window, end - copy, copy);
+            s->w_next = (unsigned)copy;
+            s->w_have = s->w_size;
+        } else {
+            s->w_next += (unsigned)dist;
+            if (s->w_next == s->w_size) s->w_next = 0;
+            if (s->w_have < s->w_size) s->w_have += (unsigned)dist;
+        }
+    }
+    return 0;
+}
+
+/* inflateSetDictionary, inflate.ts:1220-1249 */
+int zo_inflate_set_dictionary(zo_inflate_stream* s, const uint8_t* dict, size_t n) {
+    if (state_check(s)) return ZO_STREAM_ERROR;
+    if (s->wrap != 0 && s->mode != M_DICT) return ZO_STREAM_ERROR;
+    if (s->mode == M_DICT) {
+        uint32_t id = zo_adler32(1u, dict, n);
+        if (id != s->check) return ZO_DATA_ERROR;
+    }
+    if (updatewindow(s, dict + n, n)) { s->mode = M_MEM; return ZO_MEM_ERROR; }
+    s->havedict = 1;
+    return ZO_OK;
+}
+
+/* inflate_fast, inffast.ts:5-228.  Entered with avail_in >= 6 and avail_out >= 258. */
+static void inflate_fast(zo_inflate_stream* s, size_t start) {
+    const uint8_t* in = s->next_in;
+    const uint8_t* in_end = s->next_in + s->avail_in;     /* input.length guard, inffast.ts:36 */
+    const uint8_t* last = in + (s->avail_in - 5);
+    uint8_t* out = s->next_out;
+    uint8_t* beg = out - (start - s->avail_out);
+    uint8_t* end = out + (s->avail_out - 257);
+    const uint8_t* window = s->window;
+    uint32_t hold = s->hold;
+    unsigned bits = s->bits;
+    const uint32_t* lcode = s->lencode;
+    const uint32_t* dcode = s->distcode;
+    const unsigned lmask = (1u << s->lenbits) - 1, dmask = (1u << s->distbits) - 1;
+    const unsigned w_size = s->w_size, w_have = s->w_have, w_next = s->w_next;
+    uint32_t here;
+    unsigned op, len, dist;
+
+    do {
+        while (bits < 15) {
+            if (in < in_end) { hold += (uint32_t)(*in++) << bits; bits += 8; }
+            else goto leave;
+        }
+        here = lcode[hold & lmask];
+    dolen:
+        op = E_BITS(here);
+        hold >>= op; bits -= op;
+        op = E_OP(here);
+        if (op == 0) {
+            *out++ = (uint8_t)E_VAL(here);
+        } else if (op & 16) {
+            len = E_VAL(here);
+            op &= 15;
+            if (op) {
+                while (bits < op) {
+                    if (in < in_end) { hold += (uint32_t)(*in++) << bits; bits += 8; }
+                    else { s->mode = M_LEN; goto leave; }
+                }
+                len += hold & ((1u << op) - 1);
+                hold >>= op; bits -= op;
+            }
+            while (bits < 15) {
+                if (in < in_end) { hold += (uint32_t)(*in++) << bits; bits += 8; }
+                else { s->mode = M_LEN; goto leave; }
+            }
+            here = dcode[hold & dmask];
+        dodist:
+            op = E_BITS(here);
+            hold >>= op; bits -= op;
+            op = E_OP(here);
+            if (op & 16) {
+                dist = E_VAL(here);
+                op &= 15;
+                if (op) {
+                    while (bits < op) {
+                        if (in < in_end) { hold += (uint32_t)(*in++) << bits; bits += 8; }
+                        else { s->mode = M_LEN; goto leave; }
+                    }
+                    dist += hold & ((1u << op) - 1);
+                    hold >>= op; bits -= op;
+                }
+                size_t have_out = (size_t)(out - beg);
+                if (dist > have_out) {
+                    unsigned op2 = dist - (unsigned)have_out;
+                    if (op2 > w_have && s->sane) {
+                        s->msg = "invalid distance too far back";
+                        s->mode = M_BAD;
+                        goto leave;
+                    }
+                    /* copy from the ring window, then from the output (inffast.ts:113-163) */
+                    unsigned from = (w_next == 0) ? w_size - op2
+                                    : (w_next < op2 ? w_size + w_next - op2 : w_next - op2);
+                    while (op2 && len) {
+                        *out++ = window[from++];
+                        if (from == w_size) from = 0;
+                        op2--; len--;
+                    }
+                }
+                {
+                    const uint8_t* from = out - dist;
+                    while (len--) *out++ = *from++;
+                }
+            } else if ((op & 64) == 0) {
+                here = dcode[E_VAL(here) + (hold & ((1u << op) - 1))];
+                goto dodist;
+            } else {
+                s->msg = "invalid distance code";
+                s->mode = M_BAD;
+                goto leave;
+            }
+        } else if ((op & 64) == 0) {
+            here = lcode[E_VAL(here) + (hold & ((1u << op) - 1))];
+            goto dolen;
+        } else if (op & 32) {
+            s->mode = M_TYPE;
+            goto leave;
+        } else {
+            s->msg = "invalid literal/length code";
+            s->mode = M_BAD;
+            goto leave;
+        }
+    } while (in < last && out < end);
+
+leave:
+    /* return unused whole bytes, inffast.ts:217-227 */
+    len = bits >> 3;
+    in -= len;
+    bits -= len << 3;
+    hold &= (1u << bits) - 1;
+    s->next_in = in;
+    s->next_out = out;
+    s->avail_in = (size_t)(in < last ? 5 + (last - in) : 5 - (in - last));
+    s->avail_out = (size_t)(out < end ? 257 + (end - out) : 257 - (out - end));
+    s->hold = hold;
+    s->bits = bits;
+}
+
+static uint32_t zswap32(uint32_t v) {
+    return ((v & 0xffu) << 24) | ((v & 0xff00u) << 8) | ((v >> 8) & 0xff00u) | (v >> 24);
+}
+
+static uint32_t update_check(zo_inflate_stream* s, uint32_t check, const uint8_t* buf, size_t n) {
+    return s->flags ? zo_crc32(check, buf, n) : zo_adler32(check, buf, n);
+}
+
+static uint32_t crc_word(uint32_t check, uint32_t word, int nbytes) {
+    uint8_t b[4] = {(uint8_t)word, (uint8_t)(word >> 8), (uint8_t)(word >> 16), (uint8_t)(word >> 24)};
+    return zo_crc32(check, b, (size_t)nbytes);
+}
+
+static const uint8_t BL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+/* inflate, inflate.ts:332-1185 */
+int zo_inflate(zo_inflate_stream* s, int flush) {
+    const uint8_t* next;
+    uint8_t* put;
+    size_t have, left, in0, out0, copy;
+    uint32_t hold, here, last;
+    unsigned bits, len;
+    int ret;
+
+    if (state_check(s) || !s->next_out || (!s->next_in && s->avail_in != 0)) return ZO_STREAM_ERROR;
+    if (s->mode == M_TYPE) s->mode = M_TYPEDO;
+
+#define LOAD() do { put = s->next_out; left = s->avail_out; next = s->next_in; have = s->avail_in; \
+                    hold = s->hold; bits = s->bits; } while (0)
+#define RESTORE() do { s->next_out = put; s->avail_out = left; s->next_in = next; s->avail_in = have; \
+                       s->hold = hold; s->bits = bits; } while (0)
+#define INITBITS() do { hold = 0; bits = 0; } while (0)
+#define PULLBYTE() do { if (have == 0) goto inf_leave; have--; hold += (uint32_t)(*next++) << bits; \
+                        bits += 8; } while (0)
+#define NEEDBITS(n) do { while (bits < (unsigned)(n)) PULLBYTE(); } while (0)
+#define BITS(n) (hold & ((1u << (n)) - 1))
+#define DROPBITS(n) do { hold >>= (n); bits -= (unsigned)(n); } while (0)
+#define BYTEBITS() do { hold >>= bits & 7; bits -= bits & 7; } while (0)
+#define HCRC_ON() ((s->flags & 0x0200) && (s->wrap & 4))
+
+    LOAD();
+    in0 = have;
+    out0 = left;
+    ret = ZO_OK;
+    for (;;) switch (s->mode) {
+        case M_HEAD:
+            if (s->wrap == 0) { s->mode = M_TYPEDO; break; }
+            NEEDBITS(16);
+            if ((s->wrap & 2) && hold == 0x8b1f) {
+                if (s->w_bits == 0) s->w_bits = 15;
+                s->check = crc_word(0, hold, 2);
+                INITBITS();
+                s->mode = M_FLAGS;
+                break;
+            }
+            if (!(s->wrap & 1) || ((BITS(8) << 8) + (hold >> 8)) % 31) {
+                s->msg = "incorrect header check"; s->mode = M_BAD; break;
+            }
+            if (BITS(4) != 8) { s->msg = "unknown compression method"; s->mode = M_BAD; break; }
+            DROPBITS(4);
+            len = BITS(4) + 8;
+            if (s->w_bits == 0) s->w_bits = len;
+            if (len > 15 || len > s->w_bits) { s->msg = "invalid window size"; s->mode = M_BAD; break; }
+            s->dmax = 1u << len;
+            s->flags = 0;
+            s->adler = s->check = 1u;
+            s->mode = (hold & 0x200) ? M_DICTID : M_TYPE;
+            INITBITS();
+            break;
+        case M_FLAGS:
+            NEEDBITS(16);
+            s->flags = (int)hold;
+            if ((s->flags & 0xff) != 8) { s->msg = "unknown compression method"; s->mode = M_BAD; break; }
+            if (s->flags & 0xe000) { s->msg = "unknown header flags set"; s->mode = M_BAD; break; }
+            if (HCRC_ON()) s->check = crc_word(s->check, hold, 2);
+            INITBITS();
+            s->mode = M_TIME;
+            /* fallthrough */
+        case M_TIME:
+            NEEDBITS(32);
+            if (HCRC_ON()) s->check = crc_word(s->check, hold, 4);
+            INITBITS();
+            s->mode = M_OS;
+            /* fallthrough */
+        case M_OS:
+            NEEDBITS(16);
+            if (HCRC_ON()) s->check = crc_word(s->check, hold, 2);
+            INITBITS();
+            s->mode = M_EXLEN;
+            /* fallthrough */
+        case M_EXLEN:
+            if (s->flags & 0x0400) {
+                NEEDBITS(16);
+                s->length = hold;
+                if (HCRC_ON()) s->check = crc_word(s->check, hold, 2);
+                INITBITS();
+            }
+            s->mode = M_EXTRA;
+            /* fallthrough */
+        case M_EXTRA:
+            if (s->flags & 0x0400) {
+                copy = s->length;
+                if (copy > have) copy = have;
+                if (copy) {
+                    if (HCRC_ON()) s->check = zo_crc32(s->check, next, copy);
+                    have -= copy; next += copy; s->length -= (unsigned)copy;
+                }
+                if (s->length) goto inf_leave;
+            }
+            s->length = 0;
+            s->mode = M_NAME;
+            /* fallthrough */
+        case M_NAME:
+            if (s->flags & 0x0800) {
+                if (have == 0) goto inf_leave;
+                copy = 0;
+                do { len = next[copy++]; } while (len && copy < have);
+                if (HCRC_ON()) s->check = zo_crc32(s->check, next, copy);
+                have -= copy; next += copy;
+                if (len) goto inf_leave;
+            }
+            s->length = 0;
+            s->mode = M_COMMENT;
+            /* fallthrough */
+        case M_COMMENT:
+            if (s->flags & 0x1000) {
+                if (have == 0) goto inf_leave;
+                copy = 0;
+                do { len = next[copy++]; } while (len && copy < have);
+                if (HCRC_ON()) s->check = zo_crc32(s->check, next, copy);
+                have -= copy; next += copy;
+                if (len) goto inf_leave;
+            }
+            s->mode = M_HCRC;
+            /* fallthrough */
+        case M_HCRC:
+            if (s->flags & 0x0200) {
+                NEEDBITS(16);
+                if ((s->wrap & 4) && hold != (s->check & 0xffffu)) {
+                    s->msg = "header crc mismatch"; s->mode = M_BAD; break;
+                }
+                INITBITS();
+            }
+            s->adler = s->check = 0u;
+            s->mode = M_TYPE;
+            break;
+        case M_DICTID:
+            NEEDBITS(32);
+            s->adler = s->check = zswap32(hold);
+            INITBITS();
+            s->mode = M_DICT;
+            /* fallthrough */
+        case M_DICT:
+            if (!s->havedict) { RESTORE(); return ZO_NEED_DICT; }
+            s->adler = s->check = 1u;
+            s->mode = M_TYPE;
+            /* fallthrough */
+        case M_TYPE:
+            if (flush == ZO_BLOCK || flush == ZO_TREES) goto inf_leave;
+            /* fallthrough */
+        case M_TYPEDO:
+            if (s->last) { BYTEBITS(); s->mode = M_CHECK; break; }
+            NEEDBITS(3);
+            s->last = (int)BITS(1);
+            DROPBITS(1);
+            switch (BITS(2)) {
+                case 0: s->mode = M_STORED; break;
+                case 1:
+                    fixedtables(s);
+                    s->mode = M_LEN_;
+                    if (flush == ZO_TREES) { DROPBITS(2); goto inf_leave; }
+                    break;
+                case 2: s->mode = M_TABLE; break;
+                case 3: s->msg = "invalid block type"; s->mode = M_BAD;
+            }
+            DROPBITS(2);
+            break;
+        case M_STORED:
+            BYTEBITS();
+            NEEDBITS(32);
+            if ((hold & 0xffffu) != ((hold >> 16) ^ 0xffffu)) {
+                s->msg = "invalid stored block lengths"; s->mode = M_BAD; break;
+            }
+            s->length = hold & 0xffffu;
+            INITBITS();
+            s->mode = M_COPY_;
+            if (flush == ZO_TREES) goto inf_leave;
+            /* fallthrough */
+        case M_COPY_:
+            s->mode = M_COPY;
+            /* fallthrough */
+        case M_COPY:
+            copy = s->length;
+            if (copy) {
+                if (copy > have) copy = have;
+                if (copy > left) copy = left;
+                if (copy == 0) goto inf_leave;
+                memcpy(put, next, copy);
+                have -= copy; next += copy; left -= copy; put += copy;
+                s->length -= (unsigned)copy;
+                break;
+            }
+            s->mode = M_TYPE;
+            break;
+        case M_TABLE:
+            NEEDBITS(14);
+            s->nlen = BITS(5) + 257; DROPBITS(5);
+            s->ndist = BITS(5) + 1;  DROPBITS(5);
+            s->ncode = BITS(4) + 4;  DROPBITS(4);
+            if (s->nlen > 286 || (!s->deflate64 && s->ndist > 30)) {
+                s->msg = s->deflate64 ? "too many length" : "too many length or distance symbols";
+                s->mode = M_BAD;
+                break;
+            }
+            s->have = 0;
+            s->mode = M_LENLENS;
+            /* fallthrough */
+        case M_LENLENS: {
+            while (s->have < s->ncode) {
+                NEEDBITS(3);
+                s->lens[BL_ORDER[s->have++]] = (uint16_t)BITS(3);
+                DROPBITS(3);
+            }
+            while (s->have < 19) s->lens[BL_ORDER[s->have++]] = 0;
+            s->lencode = s->distcode = s->codes;
+            s->lenbits = 7;
+            unsigned idx = 0;
+            if (zo_inflate_table(0, s->lens, 19, s->codes, &s->lenbits, s->work, &idx, s->deflate64)) {
+                s->msg = "invalid code lengths set"; s->mode = M_BAD; break;
+            }
+            s->have = 0;
+            s->mode = M_CODELENS;
+        }
+            /* fallthrough */
+        case M_CODELENS: {
+            while (s->have < s->nlen + s->ndist) {
+                for (;;) {
+                    here = s->lencode[BITS(s->lenbits)];
+                    if (E_BITS(here) <= bits) break;
+                    PULLBYTE();
+                }
+                if (E_VAL(here) < 16) {
+                    DROPBITS(E_BITS(here));
+                    s->lens[s->have++] = (uint16_t)E_VAL(here);
+                } else {
+                    unsigned rep_len, rep;
+                    if (E_VAL(here) == 16) {
+                        NEEDBITS(E_BITS(here) + 2);
+                        DROPBITS(E_BITS(here));
+                        if (s->have == 0) { s->msg = "invalid bit length repeat"; s->mode = M_BAD; break; }
+                        rep_len = s->lens[s->have - 1];
+                        rep = 3 + BITS(2);
+                        DROPBITS(2);
+                    } else if (E_VAL(here) == 17) {
+                        NEEDBITS(E_BITS(here) + 3);
+                        DROPBITS(E_BITS(here));
+                        rep_len = 0;
+                        rep = 3 + BITS(3);
+                        DROPBITS(3);
+                    } else {
+                        NEEDBITS(E_BITS(here) + 7);
+                        DROPBITS(E_BITS(here));
+                        rep_len = 0;
+                        rep = 11 + BITS(7);
+                        DROPBITS(7);
+                    }
+                    if (s->have + rep > s->nlen + s->ndist) {
+                        s->msg = "invalid bit length repeat"; s->mode = M_BAD; break;
+                    }
+                    while (rep--) s->lens[s->have++] = (uint16_t)rep_len;
+                }
+            }
+            if (s->mode == M_BAD) break;
+            if (s->lens[256] == 0) {
+                s->msg = "invalid code -- missing end-of-block"; s->mode = M_BAD; break;
+            }
+            unsigned idx = 0;
+            s->lenbits = 9;
+            s->lencode = s->codes;
+            if (zo_inflate_table(1, s->lens, s->nlen, s->codes, &s->lenbits, s->work, &idx, s->deflate64)) {
+                s->msg = "invalid literal/lengths set"; s->mode = M_BAD; break;
+            }
+            s->distbits = 6;
+            s->distcode = s->codes + idx;
+            if (zo_inflate_table(2, s->lens + s->nlen, s->ndist, s->codes, &s->distbits, s->work, &idx,
+                                 s->deflate64)) {
+                s->msg = "invalid distances set"; s->mode = M_BAD; break;
+            }
+            s->mode = M_LEN_;
+            if (flush == ZO_TREES) goto inf_leave;
+        }
+            /* fallthrough */
+        case M_LEN_:
+            s->mode = M_LEN;
+            /* fallthrough */
+        case M_LEN:
+            if (!s->deflate64 && have >= 6 && left >= 258) {
+                RESTORE();
+                inflate_fast(s, out0);
+                LOAD();
+                if (s->mode == M_TYPE) s->back = -1;
+                break;
+            }
+            s->back = 0;
+            for (;;) {
+                here = s->lencode[BITS(s->lenbits)];
+                if (E_BITS(here) <= bits) break;
+                PULLBYTE();
+            }
+            if (E_OP(here) && (E_OP(here) & 0xf0) == 0) {
+                last = here;
+                for (;;) {
+                    here = s->lencode[E_VAL(last) + (BITS(E_BITS(last) + E_OP(last)) >> E_BITS(last))];
+                    if (E_BITS(last) + E_BITS(here) <= bits) break;
+                    PULLBYTE();
+                }
+                DROPBITS(E_BITS(last));
+                s->back += (int)E_BITS(last);
+            }
+            DROPBITS(E_BITS(here));
+            s->back += (int)E_BITS(here);
+            s->length = E_VAL(here);
+            if (E_OP(here) == 0) { s->mode = M_LIT; break; }
+            if (E_OP(here) & 32) { s->back = -1; s->mode = M_TYPE; break; }
+            if (E_OP(here) & 64) { s->msg = "invalid literal/length code"; s->mode = M_BAD; break; }
+            s->extra = E_OP(here) & (s->deflate64 ? 31u : 15u);
+            s->mode = M_LENEXT;
+            /* fallthrough */
+        case M_LENEXT:
+            if (s->extra) {
+                NEEDBITS(s->extra);
+                s->length += BITS(s->extra);
+                DROPBITS(s->extra);
+                s->back += (int)s->extra;
+            }
+            s->was = s->length;
+            s->mode = M_DIST;
+            /* fallthrough */
+        case M_DIST:
+            for (;;) {
+                here = s->distcode[BITS(s->distbits)];
+                if (E_BITS(here) <= bits) break;
+                PULLBYTE();
+            }
+            if ((E_OP(here) & 0xf0) == 0) {
+                last = here;
+                for (;;) {
+                    here = s->distcode[E_VAL(last) + (BITS(E_BITS(last) + E_OP(last)) >> E_BITS(last))];
+                    if (E_BITS(last) + E_BITS(here) <= bits) break;
+                    PULLBYTE();
+                }
+                DROPBITS(E_BITS(last));
+                s->back += (int)E_BITS(last);
+            }
+            DROPBITS(E_BITS(here));
+            s->back += (int)E_BITS(here);
+            if (E_OP(here) & 64) { s->msg = "invalid distance code"; s->mode = M_BAD; break; }
+            s->offset = E_VAL(here);
+            s->extra = E_OP(here) & 15u;
+            s->mode = M_DISTEXT;
+            /* fallthrough */
+        case M_DISTEXT:
+            if (s->extra) {
+                NEEDBITS(s->extra);
+                s->offset += BITS(s->extra);
+                DROPBITS(s->extra);
+                s->back += (int)s->extra;
+            }
+            s->mode = M_MATCH;
+            /* fallthrough */
+        case M_MATCH:
+            if (left == 0) goto inf_leave;
+            copy = out0 - left;
+            if (s->offset > copy) {
+                unsigned from;
+                copy = s->offset - copy;
+                if (copy > s->w_have && s->sane) {
+                    s->msg = "invalid distance too far back"; s->mode = M_BAD; break;
+                }
+                if (copy > s->w_next) { copy -= s->w_next; from = s->w_size - (unsigned)copy; }
+                else from = s->w_next - (unsigned)copy;
+                if (copy > s->length) copy = s->length;
+                if (copy > left) copy = left;
+                for (size_t i = 0; i < copy; i++) *put++ = s->window[from++];
+            } else {
+                const uint8_t* from = put - s->offset;
+                copy = s->length;
+                if (copy > left) copy = left;
+                for (size_t i = 0; i < copy; i++) *put++ = *from++;
+            }
+            left -= copy;
+            s->length -= (unsigned)copy;
+            if (s->length == 0) s->mode = M_LEN;
+            break;
+        case M_LIT:
+            if (left == 0) goto inf_leave;
+            *put++ = (uint8_t)s->length;
+            left--;
+            s->mode = M_LEN;
+            break;
+        case M_CHECK:
+            if (s->wrap) {
+                NEEDBITS(32);
+                out0 -= left;
+                s->total_out += out0;
+                s->total += out0;
+                if ((s->wrap & 4) && out0) s->adler = s->check = update_check(s, s->check, put - out0, out0);
+                out0 = left;
+                if ((s->wrap & 4) && (s->flags ? hold : zswap32(hold)) != s->check) {
+                    s->msg = "incorrect data check"; s->mode = M_BAD; break;
+                }
+                INITBITS();
+            }
+            s->mode = M_LENGTH;
+            /* fallthrough */
+        case M_LENGTH:
+            if (s->wrap && s->flags) {
+                NEEDBITS(32);
+                /* inflate.ts:1029 compares against a signed int32; identical below 2 GiB members,
+                 * which is all the tests use (SURVEY 8a note) -- the unsigned form is restated. */
+                if ((s->wrap & 4) && hold != (uint32_t)(s->total & 0xffffffffu)) {
+                    s->msg = "incorrect length check"; s->mode = M_BAD; break;
+                }
+                INITBITS();
+            }
+            s->mode = M_DONE;
+            /* fallthrough */
+        case M_DONE:
+            ret = ZO_STREAM_END;
+            goto inf_leave;
+        case M_BAD:
+            ret = ZO_DATA_ERROR;
+            goto inf_leave;
+        case M_MEM:
+            return ZO_MEM_ERROR;
+        default:
+            return ZO_STREAM_ERROR;
+    }
+
+inf_leave: /* inflate.ts:1059-1100 */
+    RESTORE();
+    if (s->w_size ||
+        (out0 != s->avail_out && s->mode < M_BAD && (s->deflate64 ? s->mode < M_DONE : s->mode < M_CHECK)) ||
+        flush != ZO_FINISH) {
+        size_t written = out0 - s->avail_out;
+        if (updatewindow(s, s->next_out, written)) { s->mode = M_MEM; return ZO_MEM_ERROR; }
+    }
+    in0 -= s->avail_in;
+    out0 -= s->avail_out;
+    s->total_in += in0;
+    s->total_out += out0;
+    s->total += out0;
+    if ((s->wrap & 4) && out0) s->adler = s->check = update_check(s, s->check, s->next_out - out0, out0);
+    s->data_type = (int)s->bits + (s->last ? 64 : 0) + (s->mode == M_TYPE ? 128 : 0) +
+                   ((s->mode == M_LEN_ || s->mode == M_COPY_) ? 256 : 0);
+    if (((in0 == 0 && out0 == 0) || flush == ZO_FINISH) && ret == ZO_OK) ret = ZO_BUF_ERROR;
+    return ret;
+}
+
+int zo_inflate_oneshot(const uint8_t* in, size_t in_len, int window_bits, const uint8_t* dict,
+                       size_t dict_len, uint8_t* out, size_t out_cap, size_t* out_len, size_t* in_used,
+                       uint32_t* check) {
+    zo_inflate_stream* s = zo_inflate_new();
+    if (!s) return ZO_MEM_ERROR;
+    int ret = zo_inflate_init2(s, window_bits);
+    uint8_t dummy = 0;
+    if (ret == ZO_OK) {
+        if (dict && dict_len && window_bits < 0) ret = zo_inflate_set_dictionary(s, dict, dict_len);
+    }
+    if (ret == ZO_OK) {
+        zo_inflate_set_input(s, in, in_len);
+        zo_inflate_set_output(s, out ? out : &dummy, out ? out_cap : 0);
+        ret = zo_inflate(s, ZO_FINISH);
+        if (ret == ZO_NEED_DICT && dict && dict_len) {
+            ret = zo_inflate_set_dictionary(s, dict, dict_len);
+            if (ret == ZO_OK) ret = zo_inflate(s, ZO_FINISH);
+        }
+    }
+    if (out_len) *out_len = (size_t)s->total_out;
+    if (in_used) *in_used = (size_t)s->total_in;
+    if (check) *check = s->adler;
+    zo_inflate_free(s);
+    return ret;
+}
