@@ -1,0 +1,203 @@
+/*
+ * zsgpu.h -- C ABI of libzsgpu, the B200-native (sm_100a) deflate / inflate / checksum engine that
+ * sits behind the zlib-streams-ts API.
+ *
+ * The reference (zlib-streams-ts, pure TypeScript) has no FFI seam; this header IS the seam a
+ * maintainer binds from a Node-API addon.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree).  Plain C types only:
+ * no CUDA or torch types appear in the signatures (a CUDA stream is passed as void*).
+ *
+ * There is no CPU fallback: every data-path call runs CUDA kernels and fails with ZS_E_CUDA if no
+ * device is usable.
+ *
+ * Conventions
+ *  - "_dev" entry points take DEVICE pointers, enqueue work on the context's stream and do not
+ *    synchronise; results (offsets, lengths, statuses) are device arrays.
+ *  - the un-suffixed batch entry points take HOST pointers, copy in, run the same kernels, copy
+ *    out and synchronise.
+ *  - status codes are the reference's Z_* values (src/mod/common/constants.ts:21-29).
+ */
+#ifndef ZSGPU_H
+#define ZSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return / status codes: src/mod/common/constants.ts:21-29 ---- */
+#define ZS_OK 0
+#define ZS_STREAM_END 1
+#define ZS_NEED_DICT 2
+#define ZS_ERRNO (-1)
+#define ZS_STREAM_ERROR (-2)
+#define ZS_DATA_ERROR (-3)
+#define ZS_MEM_ERROR (-4)
+#define ZS_BUF_ERROR (-5)
+#define ZS_VERSION_ERROR (-6)
+#define ZS_E_CUDA (-100) /* not a zlib code: CUDA runtime failure, see zs_last_error() */
+
+/* ---- flush values: src/mod/common/constants.ts:13-19 ---- */
+#define ZS_NO_FLUSH 0
+#define ZS_PARTIAL_FLUSH 1
+#define ZS_SYNC_FLUSH 2
+#define ZS_FULL_FLUSH 3
+#define ZS_FINISH 4
+#define ZS_BLOCK 5
+
+/* ---- wrappers: the formats of src/mod/streams.ts:220,233 ---- */
+#define ZS_WRAP_RAW 0  /* "deflate-raw"  windowBits -15 */
+#define ZS_WRAP_ZLIB 1 /* "deflate"      windowBits  15 */
+#define ZS_WRAP_GZIP 2 /* "gzip"         windowBits  31 */
+
+/* ---- deflate batch modes ---- */
+#define ZS_MODE_INDEPENDENT 0 /* every chunk becomes a complete stream with the wrapper */
+#define ZS_MODE_STITCHED 1    /* one stream: chunk bit-streams concatenated at bit granularity */
+
+/* ---- deflate batch flags ---- */
+#define ZS_FLAG_PRIME 1u     /* INDEPENDENT: prime each chunk with the <=32 KiB that precede it in the
+                                input (deflateSetDictionary, deflate.ts:367); raw wrapper only */
+#define ZS_FLAG_NOT_FIRST 2u /* STITCHED: this call is not the first part (no wrapper header) */
+#define ZS_FLAG_NOT_LAST 4u  /* STITCHED: not the last part (no BFINAL, no trailer, not padded) */
+#define ZS_FLAG_SYNC 8u      /* STITCHED: end every chunk with an empty stored block (Z_SYNC_FLUSH
+                                marker, deflate.ts:945-946) so chunks start byte aligned */
+
+typedef struct zs_ctx zs_ctx;
+
+#if defined(__GNUC__)
+#define ZS_API __attribute__((visibility("default")))
+#else
+#define ZS_API
+#endif
+
+ZS_API const char* zs_version(void);
+
+/* Create / destroy an engine context bound to CUDA device `device`.  `cuda_stream` is a
+ * cudaStream_t (or NULL for a stream owned by the context). */
+ZS_API int zs_ctx_create(int device, void* cuda_stream, zs_ctx** out);
+ZS_API void zs_ctx_destroy(zs_ctx* ctx);
+ZS_API const char* zs_last_error(const zs_ctx* ctx);
+ZS_API int zs_ctx_synchronize(zs_ctx* ctx);
+/* number of kernel launches issued through this context so far */
+ZS_API uint64_t zs_ctx_launch_count(const zs_ctx* ctx);
+
+/* deflateBound, src/mod/deflate/deflate.ts:615-674 (windowBits 15, memLevel 8) */
+ZS_API uint64_t zs_deflate_bound(uint64_t source_len, int wrap);
+/* Capacity the batch calls need for `n_chunks` chunks of at most `max_chunk` bytes. */
+ZS_API uint64_t zs_deflate_batch_bound(uint64_t total_len, uint32_t n_chunks, uint32_t max_chunk, int wrap, int mode);
+
+/* ---- checksums: src/mod/common/adler32.ts:4, src/mod/common/crc32.ts:26 ---- */
+/* kind 0 = adler32, 1 = crc32.  Host-side scalar combine (C zlib semantics; the reference has none). */
+ZS_API uint32_t zs_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+ZS_API uint32_t zs_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
+/* Per-segment checksums of n segments [off[i], off[i+1]) of a device buffer; d_out[i] receives the
+ * checksum of segment i started from the reference's initial value (adler 1 / crc 0). */
+ZS_API int zs_checksum_batch_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, const uint64_t* d_off, uint32_t n,
+                          uint32_t* d_out);
+/* Checksum of one device buffer, continuing from `init`; the result is returned to the host. */
+ZS_API int zs_checksum_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, uint32_t init, uint32_t* result);
+/* Host buffer variant: adler32(adler, buf, len) / crc32(crc, buf, len). */
+ZS_API int zs_checksum(zs_ctx* ctx, int kind, const uint8_t* buf, uint64_t len, uint32_t init, uint32_t* result);
+
+/* ---- deflate: replaces deflate_fast/deflate_slow/longest_match (deflate.ts:1053-1448), _tr_tally*
+ *      (deflate/utils.ts:55-81), build_tree/gen_bitlen/gen_codes/compress_block/_tr_flush_block
+ *      (trees.ts) and the header/trailer emission of deflate() (deflate.ts:750-832,964-988) ---- */
+typedef struct zs_deflate_result {
+    uint64_t total_out_bytes; /* bytes valid in `out` */
+    uint64_t total_out_bits;  /* STITCHED: exact bit length (NOT_LAST parts end mid-byte) */
+    uint32_t check;           /* adler32 (zlib) / crc32 (gzip, raw) of this call's whole input */
+    uint32_t n_blocks;        /* deflate blocks emitted */
+} zs_deflate_result;
+
+/*
+ * Chunk i is d_in[d_in_off[i] .. d_in_off[i+1]).  If d_in_off is NULL the input is cut into
+ * `chunk_size`-byte chunks (the last one short) and n_chunks must equal ceil(in_len/chunk_size)
+ * (or 1 when in_len == 0).  `history` bytes before d_in[0] are readable and may be matched against
+ * (STITCHED continuation parts / PRIME).  level 1..9 (-1 = 6), CONFIGURATION_TABLE deflate.ts:86.
+ * Outputs (device): d_out, d_out_off[n_chunks+1] = byte offsets of the streams (INDEPENDENT) or
+ * bit offsets of the chunk bit-streams (STITCHED); d_out_bits[n_chunks] = compressed bit length of
+ * each chunk; d_checks[n_chunks] (may be NULL) = per-chunk adler32/crc32; d_result = summary.
+ */
+ZS_API int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, const uint64_t* d_in_off,
+                         uint32_t n_chunks, uint32_t chunk_size, uint32_t max_chunk, uint32_t history,
+                         int level, int wrap, int mode, uint32_t flags, uint8_t* d_out, uint64_t out_cap,
+                         uint64_t* d_out_off, uint64_t* d_out_bits, uint32_t* d_checks,
+                         zs_deflate_result* d_result);
+
+/* Host-buffer variant (what the Node-API addon binds for deflateBatch).  in_off may be NULL as
+ * above; out_off / out_bits / checks may be NULL.  Returns ZS_OK, ZS_BUF_ERROR (out_cap too
+ * small), ZS_STREAM_ERROR (bad arguments) or ZS_E_CUDA. */
+ZS_API int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
+                     uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out,
+                     uint64_t out_cap, uint64_t* out_off, uint64_t* out_bits, uint32_t* checks,
+                     zs_deflate_result* result);
+
+/* Bit-granular stitch (no reference analogue; deflatePrime, deflate.ts:528, is the reference's
+ * "insert bits at a bit offset" primitive): OR `n_bits` bits of d_src into d_dst starting at bit
+ * `dst_bit_off`.  The destination bits must be zero beforehand. */
+ZS_API int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits);
+
+/* ---- inflate: replaces inflate_fast (inffast.ts:5), inflate_table (inftrees.ts:62) and the
+ *      block/header/trailer modes of inflate() (inflate.ts:332-1100) for whole streams ---- */
+/*
+ * Stream i is d_in[d_in_off[i] .. d_in_off[i+1]); its output goes to d_out[d_out_off[i] ..
+ * d_out_off[i+1]) (capacity).  window_bits as inflateInit2_ (inflate.ts:174): 15 zlib, -15 raw,
+ * 31 gzip, 47 auto-detect zlib/gzip, -16 raw deflate64.  Optional per-stream preset dictionary
+ * (raw streams, inflateSetDictionary inflate.ts:1220): stream i uses d_dict[d_dict_rng[2i] ..
+ * d_dict_rng[2i+1]).  Per stream: d_out_len = bytes produced, d_in_used = bytes consumed
+ * (total_in), d_checks = adler32/crc32 of the output, d_status = what inflate(strm, Z_FINISH)
+ * returns (Z_STREAM_END, Z_DATA_ERROR, Z_BUF_ERROR, Z_NEED_DICT).  d_in_used / d_checks may be NULL.
+ */
+ZS_API int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, int window_bits,
+                         uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint64_t* d_in_used,
+                         uint32_t* d_checks, int32_t* d_status, const uint8_t* d_dict,
+                         const uint64_t* d_dict_rng);
+
+/* Host-buffer variant (what the addon binds for inflateBatch). `in_total` = in_off[n],
+ * out capacity = out_off[n].  dict / dict_rng may be NULL. */
+ZS_API int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits,
+                     uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks,
+                     int32_t* status, const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total);
+
+/* Message the reference would leave in strm.msg for a (status, detail) pair; detail codes are
+ * returned in the high bits of nothing -- see zs_inflate_detail_dev. */
+ZS_API const char* zs_inflate_message(int detail);
+/* Optional: per-stream detail code (index into the reference's message strings) of the last
+ * zs_inflate_batch[_dev] call on this context, copied to the host array `detail[n]`. */
+ZS_API int zs_inflate_last_details(zs_ctx* ctx, int32_t* detail, uint32_t n);
+
+/* ---- streaming shim: the z_stream protocol of deflate()/inflate() over the batch engine ----
+ * Mirrors createDeflateStream/deflateInit2_/deflate/deflateEnd (deflate.ts:80,253,716,991),
+ * deflateSetDictionary (:367) and createInflateStream/inflateInit2_/inflate/inflateEnd/
+ * inflateSetDictionary/inflateReset (inflate.ts:68,174,332,1187,1220,124).  The counters are the
+ * Stream fields of src/mod/common/types.ts:1-15. */
+typedef struct zs_stream {
+    const uint8_t* next_in;
+    uint64_t avail_in;
+    uint64_t total_in;
+    uint8_t* next_out;
+    uint64_t avail_out;
+    uint64_t total_out;
+    const char* msg;
+    uint32_t adler;
+    int32_t data_type;
+    void* state; /* opaque */
+} zs_stream;
+
+ZS_API int zs_stream_deflate_init(zs_ctx* ctx, zs_stream* strm, int level, int method, int window_bits, int mem_level,
+                           int strategy);
+ZS_API int zs_stream_deflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len);
+ZS_API int zs_stream_deflate(zs_stream* strm, int flush);
+ZS_API int zs_stream_deflate_end(zs_stream* strm);
+ZS_API int zs_stream_inflate_init(zs_ctx* ctx, zs_stream* strm, int window_bits);
+ZS_API int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len);
+ZS_API int zs_stream_inflate(zs_stream* strm, int flush);
+ZS_API int zs_stream_inflate_reset(zs_stream* strm);
+ZS_API int zs_stream_inflate_end(zs_stream* strm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSGPU_H */

@@ -129,8 +129,13 @@ int zo_inflate_table(int type, const uint16_t* lens, unsigned codes, uint32_t* t
     if (root > max) root = max;
     if (max == 0) {
         if (!deflate64) { /* PARAMS._createTableWhenNoCodes, inftrees.ts:45,58,113-123 */
-            table[0] = PACK(64, 1, 0);
-            table[1] = PACK(64, 1, 0);
+            /* The reference writes the two invalid-code markers at table[0..1] of a table whose
+             * length part has already been copied out (inflate.ts:797,826), so the live length
+             * table is untouched and the distance table is "no valid code".  Writing them at the
+             * current index gives exactly that decode behaviour for a table shared in place. */
+            table[*index] = PACK(64, 1, 0);
+            table[*index + 1] = PACK(64, 1, 0);
+            *index += 2;
             *bits = 1;
             return 0;
         }

@@ -1,0 +1,215 @@
+"""CPU suite: the oracle restatement against the reference's own known-answer vectors, the
+deflate64 fixtures and C zlib 1.3 (the cross-oracle of the reference's tests)."""
+import random
+import zlib
+
+import pytest
+
+from conftest import make_mixed, make_text, rand_bytes
+
+
+def test_checksum_kats(oracle, kat):
+    for v in kat["crc32"]:
+        assert oracle.crc32(bytes.fromhex(v["data_hex"]), v["init"]) == v["expect"], v["ref"]
+    for v in kat["adler32"]:
+        assert oracle.adler32(bytes.fromhex(v["data_hex"]), v["init"]) == v["expect"], v["ref"]
+    assert oracle.adler32(None) == 1          # adler32(0) with no buffer, coverage-adler32.spec.ts:5-8
+    assert oracle.crc32(None) == 0            # coverage-crc32.spec.ts:5-7
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 15, 16, 17, 1999, 2000, 2001, 5552, 65536, 300001])
+def test_checksums_match_zlib(oracle, n):
+    d = rand_bytes(n, n)
+    assert oracle.crc32(d) == zlib.crc32(d)
+    assert oracle.adler32(d) == zlib.adler32(d)
+    cut = n // 3
+    a, b = d[:cut], d[cut:]
+    assert oracle.crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(d)
+    assert oracle.adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(d)
+    assert oracle.crc32(b, oracle.crc32(a)) == zlib.crc32(d)       # continuation from a passed value
+    assert oracle.adler32(b, oracle.adler32(a)) == zlib.adler32(d)
+
+
+def test_inflate_kats(oracle, kat):
+    for v in kat["inflate"]:
+        ret, out, used, _ = oracle.inflate(bytes.fromhex(v["in_hex"]), v["window_bits"], 1 << 17)
+        if "ret" in v:
+            assert ret == v["ret"], v["ref"]
+        if "ret_le" in v:
+            assert ret <= v["ret_le"], v["ref"]
+        if "ret_not" in v:
+            assert ret not in v["ret_not"], v["ref"]
+        if "out_hex" in v:
+            assert out == bytes.fromhex(v["out_hex"]), v["ref"]
+        if "out_len" in v:
+            assert out == bytes([v["out_byte"]]) * v["out_len"], v["ref"]
+
+
+def test_inflate_kat_one_byte_at_a_time(oracle):
+    # test-length-extra-slow-path.spec.ts:19-45: the 285 code fed byte by byte
+    s = oracle.InflateStream(-15)
+    out = b""
+    ret = 0
+    for b in bytes.fromhex("4b1c0500"):
+        ret, o, used = s.step(bytes([b]), 1024, oracle.Z_NO_FLUSH)
+        out += o
+        assert used == 1
+    assert ret == oracle.Z_STREAM_END and out == b"a" * 259
+
+
+def test_deflate64_fixtures(oracle, fixtures64):
+    for f in fixtures64:
+        ret, out, used, _ = oracle.inflate(f["data"], -16, f["out_len"] + 64)
+        assert ret == oracle.Z_STREAM_END and used == f["length"], f["name"]
+        assert len(out) == f["out_len"] and zlib.crc32(out) == f["crc32"] and zlib.adler32(out) == f["adler32"], f["name"]
+    # SURVEY 4.3 digests (independent decoder) for two of them
+    by = {f["name"]: f for f in fixtures64}
+    assert by["100k_lines.deflate64"]["crc32"] == 0xDC47C238 and by["100k_lines.deflate64"]["out_len"] == 2188890
+    assert by["zeros_100k.deflate64"]["adler32"] == 0x86AF0001
+
+
+def test_deflate64_fixture_chunked_equals_oneshot(oracle, fixtures64):
+    # test-inflate9-chunked.spec.ts / test-inflate9-small-output-window.spec.ts
+    f = next(x for x in fixtures64 if x["name"] == "10k_lines.deflate64")
+    _, want, _, _ = oracle.inflate(f["data"], -16, f["out_len"] + 64)
+    s = oracle.InflateStream(-16)
+    got = b""
+    data = f["data"]
+    pos = 0
+    ret = 0
+    while ret != oracle.Z_STREAM_END:
+        piece = data[pos: pos + 3]
+        ret, o, used = s.step(piece, 8, oracle.Z_NO_FLUSH)
+        got += o
+        pos += used
+        assert ret in (oracle.Z_OK, oracle.Z_STREAM_END, oracle.Z_BUF_ERROR)
+        assert pos <= len(data)
+    assert got == want
+    # first 64 bytes with Z_FINISH -> Z_BUF_ERROR (test-inflate9-finish-buferror.spec.ts:8-34)
+    s2 = oracle.InflateStream(-16)
+    ret, _, _ = s2.step(data[:64], 1 << 20, oracle.Z_FINISH)
+    assert ret == oracle.Z_BUF_ERROR
+
+
+def test_too_many_symbols(oracle):
+    # coverage-too-many-len.spec.ts:28-46 -- dynamic header with ndist = 31 / nlen = 287
+    def hdr(nlen, ndist):
+        v = 0b101 | ((nlen - 257) << 3) | ((ndist - 1) << 8) | (0 << 13)  # BFINAL=1, BTYPE=2
+        return v.to_bytes(3, "little") + bytes(8)
+    ret, _, _, _ = oracle.inflate(hdr(257, 31), -15, 64)
+    assert ret == oracle.Z_DATA_ERROR
+    s = oracle.InflateStream(-16)
+    ret, _, _ = s.step(hdr(257, 31), 64, oracle.Z_NO_FLUSH)
+    assert s.msg != "too many length"      # deflate64 accepts 31/32 distance codes
+    ret, _, _, _ = oracle.inflate(hdr(287, 1), -15, 64)
+    assert ret == oracle.Z_DATA_ERROR
+    s = oracle.InflateStream(-16)
+    ret, _, _ = s.step(hdr(287, 1), 64, oracle.Z_NO_FLUSH)
+    assert ret == oracle.Z_DATA_ERROR and s.msg == "too many length"
+
+
+@pytest.mark.parametrize("wbits", [15, -15, 31])
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_inflate_of_zlib_streams(oracle, wbits, level):
+    for data in (make_text(200000, level), make_mixed(150000, level), rand_bytes(70000, level), b"", b"a", bytes(100000)):
+        co = zlib.compressobj(level, 8, wbits)
+        z = co.compress(data) + co.flush()
+        ret, out, used, check = oracle.inflate(z, wbits, len(data) + 64)
+        assert ret == oracle.Z_STREAM_END and out == data and used == len(z)
+        if wbits == 15:
+            assert check == zlib.adler32(data)
+        if wbits == 31:
+            assert check == zlib.crc32(data)
+
+
+def test_inflate_corrupt_and_truncated(oracle):
+    data = make_text(50000, 5)
+    z = zlib.compress(data, 6)
+    ret, out, _, _ = oracle.inflate(z[:-5], 15, len(data) + 64)
+    assert ret == oracle.Z_BUF_ERROR and out == data          # body complete, trailer missing
+    bad = bytearray(z)
+    bad[-1] ^= 0xFF
+    ret, _, _, _ = oracle.inflate(bytes(bad), 15, len(data) + 64)
+    assert ret == oracle.Z_DATA_ERROR                          # incorrect data check
+    ret, out, _, _ = oracle.inflate(z, 15, 1000)
+    assert ret == oracle.Z_BUF_ERROR and out == data[:1000]    # output full
+    rnd = random.Random(9)
+    for _ in range(200):
+        junk = bytearray(z[:400])
+        junk[rnd.randrange(2, 400)] ^= 1 << rnd.randrange(8)
+        ret, out, _, _ = oracle.inflate(bytes(junk), 15, len(data) + 64)
+        zr = zlib.decompressobj(15)
+        try:
+            zo = zr.decompress(bytes(junk))
+            assert out[: len(zo)] == zo[: len(out)]
+            assert ret in (oracle.Z_BUF_ERROR, oracle.Z_DATA_ERROR)
+        except zlib.error:
+            assert ret == oracle.Z_DATA_ERROR
+
+
+def test_multi_member_gzip_reset(oracle):
+    # test/inflate/test-multistream.ts:16-79
+    a, b = make_text(30000, 1), make_text(20000, 2)
+    za = zlib.compressobj(6, 8, 31)
+    zb = zlib.compressobj(9, 8, 31)
+    blob = za.compress(a) + za.flush() + zb.compress(b) + zb.flush()
+    s = oracle.InflateStream(31)
+    ret, o1, used = s.step(blob, 1 << 20, oracle.Z_NO_FLUSH)
+    assert ret == oracle.Z_STREAM_END and o1 == a and 0 < used < len(blob)
+    assert s.reset() == oracle.Z_OK
+    ret, o2, used2 = s.step(blob[used:], 1 << 20, oracle.Z_NO_FLUSH)
+    assert ret == oracle.Z_STREAM_END and o2 == b and used + used2 == len(blob)
+
+
+@pytest.mark.parametrize("level", list(range(1, 10)))
+def test_deflate_byte_exact_with_zlib(oracle, level):
+    cases = [b"", b"a", b"abc", bytes(200000), bytes(j % 251 for j in range(1 << 18)), rand_bytes(150000, 7),
+             make_text(400000, level), make_mixed(300000, level)]
+    rnd = random.Random(level)
+    for _ in range(6):
+        cases.append(bytes(rnd.getrandbits(8) & rnd.choice((0xFF, 0x0F, 0x03)) for _ in range(rnd.randrange(1, 33000))))
+    for d in cases:
+        for wrap, wb in ((0, -15), (1, 15), (2, 31)):
+            co = zlib.compressobj(level, 8, wb)
+            z = co.compress(d) + co.flush()
+            if wrap == 2:
+                z = z[:9] + b"\xff" + z[10:]   # the reference writes OS = 255 (deflate/constants.ts:30)
+            assert oracle.deflate(d, level, wrap) == z
+
+
+def test_deflate_headers(oracle, kat):
+    for lvl in ("1", "6", "9"):
+        assert oracle.deflate(b"x", int(lvl), 1)[:2].hex() == kat["headers"]["zlib"][lvl]
+    assert oracle.deflate(b"", 6, 0) == bytes([3, 0])          # test-streams-empty-input.ts:32-35
+    g = oracle.deflate(b"x", 9, 2)
+    assert g[:4] == b"\x1f\x8b\x08\x00" and g[8] == 2 and g[9] == kat["headers"]["gzip_os_byte"]
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_deflate_dictionary_and_sync_flush(oracle, level):
+    d = make_text(300000, 5)
+    dic, body = d[:40000], d[40000:140000]
+    co = zlib.compressobj(level, 8, -15, 8, 0, dic[-32768:])
+    z = co.compress(body) + co.flush(zlib.Z_SYNC_FLUSH)
+    assert oracle.deflate(body, level, 0, dic, oracle.Z_SYNC_FLUSH) == z
+    co = zlib.compressobj(level, 8, 15, 8, 0, dic)
+    z = co.compress(body) + co.flush()
+    o = oracle.deflate(body, level, 1, dic)
+    assert o == z
+    ret, out, _, _ = oracle.inflate(o, 15, len(body) + 64, dic)
+    assert ret == oracle.Z_STREAM_END and out == body
+
+
+def test_build_tree_matches_stream(oracle):
+    import ctypes as C
+    import numpy as np
+    rnd = np.random.default_rng(3)
+    freq = rnd.integers(0, 50, size=286).astype(np.uint16)
+    freq[256] = 1
+    lens = np.zeros(286, np.uint16)
+    codes = np.zeros(286, np.uint16)
+    ol, sl = C.c_uint32(0), C.c_uint32(0)
+    f = freq.copy()
+    mc = oracle.lib().zo_build_tree(0, f.ctypes.data, lens.ctypes.data, codes.ctypes.data, C.byref(ol), C.byref(sl))
+    assert mc >= 256 and lens.max() <= 15
+    assert sum(2.0 ** -int(l) for l in lens if l) == 1.0      # complete prefix code

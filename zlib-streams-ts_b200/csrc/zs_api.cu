@@ -1,0 +1,401 @@
+// zs_api.cu -- the C ABI of include/zsgpu.h: context, batch deflate / inflate / checksum entry points
+// (device-pointer and host-buffer variants).  The streaming shim lives in zs_stream.cu.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "zs_common.cuh"
+
+// ---- scratch slots ---------------------------------------------------------------------------------
+enum {
+    SCR_CK_OFF = 0, SCR_CK_PART = 1, SCR_SMALL = 2,
+    SCR_D_SYM = 3, SCR_D_NBLK = 4, SCR_D_DESC = 5, SCR_D_FREQ = 6, SCR_D_CODE = 7, SCR_D_HDR = 8, SCR_D_BITS = 9,
+    SCR_D_PR = 10, SCR_D_OFF = 11, SCR_D_CHECKS = 12,
+    SCR_I_MISC = 13,
+    SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
+    SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22,
+};
+
+void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
+    zs_scratch& s = ctx->scr[slot];
+    if (bytes == 0) bytes = 16;
+    if (s.cap >= bytes) return s.p;
+    if (s.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+    }
+    size_t want = bytes + (bytes >> 3) + 256;  // a little head-room so that growing inputs do not realloc every call
+    want = (want + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&s.p, want);
+    if (e != cudaSuccess) {
+        want = (bytes + 255) & ~(size_t)255;
+        e = cudaMalloc(&s.p, want);
+    }
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        s.p = nullptr;
+        return nullptr;
+    }
+    s.cap = want;
+    return s.p;
+}
+
+int zs_set_cuda_error(zs_ctx* ctx, cudaError_t e, const char* where) {
+    snprintf(ctx->err, sizeof(ctx->err), "CUDA error at %s: %s", where, cudaGetErrorString(e));
+    return ZS_E_CUDA;
+}
+
+namespace {
+
+__global__ void make_chunk_offsets_kernel(uint64_t* off, uint64_t len, uint64_t chunk, uint32_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) {
+        uint64_t v = i * chunk;
+        off[i] = (v < len && i < n) ? v : len;
+    }
+}
+
+int bad_arg(zs_ctx* ctx, const char* msg) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return ZS_STREAM_ERROR;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* zs_version(void) { return "zsgpu 0.1.0 (sm_100a)"; }
+
+int zs_ctx_create(int device, void* cuda_stream, zs_ctx** out) {
+    if (!out) return ZS_STREAM_ERROR;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ZS_E_CUDA;  // no CPU fallback: without a usable CUDA device there is no engine
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return ZS_E_CUDA;
+    zs_ctx* ctx = new zs_ctx();
+    ctx->device = device;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return ZS_E_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return ZS_OK;
+}
+
+void zs_ctx_destroy(zs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->scr)
+        if (s.p) cudaFree(s.p);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* zs_last_error(const zs_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+uint64_t zs_ctx_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zs_ctx_synchronize(zs_ctx* ctx) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+uint64_t zs_deflate_bound(uint64_t n, int wrap) {
+    uint64_t wraplen = wrap == ZS_WRAP_RAW ? 0 : wrap == ZS_WRAP_ZLIB ? 6 : 18;
+    return n + (n >> 12) + (n >> 14) + (n >> 25) + 13 - 6 + wraplen;
+}
+
+uint64_t zs_deflate_batch_bound(uint64_t total_len, uint32_t n_chunks, uint32_t max_chunk, int wrap, int mode) {
+    // every block is at worst stored: 5 bytes (+1 alignment) per <= 16 K symbols, plus per-chunk
+    // framing (wrapper or sync marker) and slack for the word-granular encoder
+    uint64_t blocks = (uint64_t)n_chunks * ((uint64_t)max_chunk / 16351u + 2u);
+    (void)mode;
+    return total_len + 6 * blocks + (uint64_t)n_chunks * (18 + 8) + 64;
+}
+
+uint32_t zs_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) { return zs_host_crc32_combine(c1, c2, len2); }
+uint32_t zs_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return zs_host_adler32_combine(a1, a2, len2); }
+
+// ---- checksums ---------------------------------------------------------------------------------------
+int zs_checksum_batch_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, const uint64_t* d_off, uint32_t n,
+                          uint32_t* d_out) {
+    if (!ctx || (kind != 0 && kind != 1) || (n && (!d_buf || !d_off || !d_out))) return bad_arg(ctx, "checksum: bad arguments");
+    return zs_launch_checksum_segments(ctx, kind, d_buf, d_off, nullptr, n, d_out);
+}
+
+int zs_checksum_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, uint32_t init, uint32_t* result) {
+    if (!ctx || (kind != 0 && kind != 1) || !result || (len && !d_buf)) return bad_arg(ctx, "checksum: bad arguments");
+    uint32_t* d_res = (uint32_t*)zs_scratch_get(ctx, SCR_SMALL, 256);
+    if (!d_res) return ZS_MEM_ERROR;
+    int rc = zs_launch_checksum_whole(ctx, kind, d_buf, len, init, d_res);
+    if (rc != ZS_OK) return rc;
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(result, d_res, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+int zs_checksum(zs_ctx* ctx, int kind, const uint8_t* buf, uint64_t len, uint32_t init, uint32_t* result) {
+    if (!ctx || !result || (len && !buf)) return bad_arg(ctx, "checksum: bad arguments");
+    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, len + 64);
+    if (!d_in) return ZS_MEM_ERROR;
+    if (len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, buf, len, cudaMemcpyHostToDevice, ctx->stream));
+    return zs_checksum_dev(ctx, kind, d_in, len, init, result);
+}
+
+// ---- deflate ------------------------------------------------------------------------------------------
+int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, const uint64_t* d_in_off,
+                         uint32_t n_chunks, uint32_t chunk_size, uint32_t max_chunk, uint32_t history, int level,
+                         int wrap, int mode, uint32_t flags, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
+                         uint64_t* d_out_bits, uint32_t* d_checks, zs_deflate_result* d_result) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (level == -1) level = 6;
+    // argument rules of deflateInit2_ (deflate.ts:263-297) that apply to the batch form
+    if (level < 1 || level > 9) return bad_arg(ctx, "deflate: level must be 1..9 (level 0 / stored is out of scope)");
+    if (wrap < 0 || wrap > 2 || (mode != ZS_MODE_INDEPENDENT && mode != ZS_MODE_STITCHED))
+        return bad_arg(ctx, "deflate: bad wrap or mode");
+    if (!d_out || !d_result || (in_len && !d_in) || n_chunks == 0) return bad_arg(ctx, "deflate: null buffer or zero chunks");
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15u) != 0) return bad_arg(ctx, "deflate: d_out must be 16-byte aligned");
+    if ((flags & ZS_FLAG_PRIME) && (mode != ZS_MODE_INDEPENDENT || wrap != ZS_WRAP_RAW))
+        return bad_arg(ctx, "deflate: ZS_FLAG_PRIME needs INDEPENDENT mode and the raw wrapper (deflate.ts:373)");
+    if (history > 32768) history = 32768;
+    if (mode == ZS_MODE_INDEPENDENT && !(flags & ZS_FLAG_PRIME)) history = 0;
+    if (!d_in_off) {
+        if (chunk_size == 0) return bad_arg(ctx, "deflate: chunk_size is zero");
+        uint64_t want = in_len ? (in_len + chunk_size - 1) / chunk_size : 1;
+        if (want != n_chunks) return bad_arg(ctx, "deflate: n_chunks does not match in_len / chunk_size");
+        max_chunk = chunk_size;
+    }
+    if (max_chunk == 0) max_chunk = 1;
+    if (in_len > 0xffffffff00ull) return bad_arg(ctx, "deflate: input too large for one call");
+
+    zs_deflate_plan p;
+    memset(&p, 0, sizeof(p));
+    p.d_in = d_in; p.in_len = in_len; p.history = history; p.n_chunks = n_chunks; p.max_chunk = max_chunk;
+    p.max_bpc = max_chunk / 16351u + 2u;
+    p.level = level; p.wrap = wrap; p.mode = mode; p.flags = flags;
+    const size_t slots = (size_t)n_chunks * p.max_bpc;
+
+    uint64_t* off = (uint64_t*)zs_scratch_get(ctx, SCR_D_OFF, (size_t)(n_chunks + 1) * 8);
+    p.d_sym = (uint32_t*)zs_scratch_get(ctx, SCR_D_SYM, (size_t)in_len * 4 + 64);
+    p.d_chunk_nblk = (uint32_t*)zs_scratch_get(ctx, SCR_D_NBLK, (size_t)n_chunks * 4);
+    p.d_blk_desc = (uint32_t*)zs_scratch_get(ctx, SCR_D_DESC, slots * 16);
+    p.d_blk_freq = (uint32_t*)zs_scratch_get(ctx, SCR_D_FREQ, slots * 320 * 4);
+    p.d_blk_code = (uint32_t*)zs_scratch_get(ctx, SCR_D_CODE, slots * 320 * 4);
+    p.d_blk_hdr = (uint32_t*)zs_scratch_get(ctx, SCR_D_HDR, slots * 160 * 4);
+    p.d_blk_bits = (uint64_t*)zs_scratch_get(ctx, SCR_D_BITS, slots * 8);
+    p.d_chunk_pr = (uint64_t*)zs_scratch_get(ctx, SCR_D_PR, (size_t)n_chunks * 16);
+    uint32_t* small = (uint32_t*)zs_scratch_get(ctx, SCR_SMALL, 256);
+    uint32_t* checks_scr = (uint32_t*)zs_scratch_get(ctx, SCR_D_CHECKS, (size_t)n_chunks * 4);
+    uint64_t* outoff_scr = (uint64_t*)zs_scratch_get(ctx, SCR_D_OUTOFF, (size_t)(n_chunks + 1) * 8);
+    uint64_t* outbits_scr = (uint64_t*)zs_scratch_get(ctx, SCR_D_OUTBITS, (size_t)n_chunks * 8);
+    if (!off || !p.d_sym || !p.d_chunk_nblk || !p.d_blk_desc || !p.d_blk_freq || !p.d_blk_code || !p.d_blk_hdr ||
+        !p.d_blk_bits || !p.d_chunk_pr || !small || !checks_scr || !outoff_scr || !outbits_scr)
+        return ZS_MEM_ERROR;
+    p.d_seg_counter = small + 8;
+    p.d_check_total = small + 9;
+    p.d_error = (int32_t*)(small + 10);
+    ZS_CUDA_TRY(ctx, cudaMemsetAsync(small + 8, 0, 3 * sizeof(uint32_t), ctx->stream));
+
+    if (d_in_off) {
+        p.d_in_off = d_in_off;
+    } else {
+        make_chunk_offsets_kernel<<<(n_chunks + 1 + 255) / 256, 256, 0, ctx->stream>>>(off, in_len, chunk_size, n_chunks);
+        ZS_LAUNCH_CHECK(ctx, "make_chunk_offsets_kernel");
+        p.d_in_off = off;
+    }
+    p.d_out = d_out; p.out_cap = out_cap;
+    p.d_out_off = d_out_off ? d_out_off : outoff_scr;
+    p.d_out_bits = d_out_bits ? d_out_bits : outbits_scr;
+    p.d_result = d_result;
+
+    // checksums of the uncompressed data (read_buf, deflate.ts:155-159): adler32 for the zlib
+    // wrapper, crc32 for gzip; for raw streams only when the caller asks for per-chunk values
+    const bool need_check = wrap != ZS_WRAP_RAW || d_checks != nullptr;
+    p.d_checks = nullptr;
+    if (need_check) {
+        const int kind = wrap == ZS_WRAP_ZLIB ? 0 : 1;
+        p.d_checks = d_checks ? d_checks : checks_scr;
+        int rc = zs_launch_checksum_segments(ctx, kind, d_in, p.d_in_off, nullptr, n_chunks, p.d_checks);
+        if (rc != ZS_OK) return rc;
+        rc = zs_launch_checksum_fold(ctx, kind, p.d_checks, p.d_in_off, n_chunks, kind ? 0u : 1u, p.d_check_total);
+        if (rc != ZS_OK) return rc;
+    }
+    int rc = zs_launch_lz77(ctx, p);
+    if (rc != ZS_OK) return rc;
+    return zs_launch_huffman(ctx, p);
+}
+
+int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
+                     uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out, uint64_t out_cap,
+                     uint64_t* out_off, uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (!out || !result || (in_len && !in) || n_chunks == 0) return bad_arg(ctx, "deflate: null buffer or zero chunks");
+    uint32_t max_chunk = chunk_size;
+    if (in_off) {
+        max_chunk = 1;
+        if (in_off[0] != 0 || in_off[n_chunks] != in_len) return bad_arg(ctx, "deflate: in_off must span [0, in_len]");
+        for (uint32_t i = 0; i < n_chunks; i++) {
+            if (in_off[i + 1] < in_off[i]) return bad_arg(ctx, "deflate: in_off must be non-decreasing");
+            uint64_t l = in_off[i + 1] - in_off[i];
+            if (l > 0xffffffffull) return bad_arg(ctx, "deflate: chunk too large");
+            if (l > max_chunk) max_chunk = (uint32_t)l;
+        }
+    }
+    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_len + 64);
+    uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, out_cap + 64);
+    uint64_t* d_off = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)(n_chunks + 1) * 8);
+    uint64_t* d_ooff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF2, (size_t)(2 * (size_t)n_chunks + 1) * 8);
+    uint8_t* d_res = (uint8_t*)zs_scratch_get(ctx, SCR_H_RES, sizeof(zs_deflate_result) + (size_t)n_chunks * 4 + 64);
+    if (!d_in || !d_out || !d_off || !d_ooff || !d_res) return ZS_MEM_ERROR;
+    zs_deflate_result* d_result = (zs_deflate_result*)d_res;
+    uint32_t* d_checks = checks ? (uint32_t*)(d_res + 64) : nullptr;
+    if (in_len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream));
+    if (in_off)
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, in_off, (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = zs_deflate_batch_dev(ctx, d_in, in_len, in_off ? d_off : nullptr, n_chunks, chunk_size, max_chunk, 0, level,
+                                  wrap, mode, flags, d_out, out_cap, d_ooff, d_ooff + n_chunks + 1, d_checks, d_result);
+    if (rc != ZS_OK) return rc;
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(result, d_result, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (result->total_out_bytes > out_cap) {
+        snprintf(ctx->err, sizeof(ctx->err), "deflate: output needs %llu bytes, capacity %llu",
+                 (unsigned long long)result->total_out_bytes, (unsigned long long)out_cap);
+        return ZS_BUF_ERROR;
+    }
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, result->total_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_off)
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_off, d_ooff, (size_t)(n_chunks + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_bits)
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_bits, d_ooff + n_chunks + 1, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (checks)
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits) {
+    if (!ctx || !d_dst || (n_bits && !d_src)) return bad_arg(ctx, "bit_concat: bad arguments");
+    return zs_launch_bit_concat(ctx, d_dst, dst_bit_off, d_src, n_bits);
+}
+
+// ---- inflate ------------------------------------------------------------------------------------------
+int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, int window_bits,
+                         uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint64_t* d_in_used,
+                         uint32_t* d_checks, int32_t* d_status, const uint8_t* d_dict, const uint64_t* d_dict_rng) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (n == 0) return ZS_OK;
+    if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return bad_arg(ctx, "inflate: null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 7u) != 0) return bad_arg(ctx, "inflate: d_in must be 8-byte aligned");
+    // inflateReset2, inflate.ts:138-172
+    int wrap, d64 = 0;
+    if (window_bits < 0) {
+        if (window_bits < -16) return bad_arg(ctx, "inflate: windowBits out of range");
+        wrap = 0;
+        d64 = window_bits == -16;
+        window_bits = -window_bits;
+    } else {
+        wrap = ((window_bits >> 4) + 5) & 3;  // bit0 zlib, bit1 gzip
+        if (window_bits < 48) window_bits &= 15;
+    }
+    if (window_bits && (window_bits < 8 || window_bits > (d64 ? 16 : 15))) return bad_arg(ctx, "inflate: windowBits out of range");
+
+    // misc scratch: detail[n] trailer[2n] flags[n] adler[n] crc[n]
+    uint32_t* misc = (uint32_t*)zs_scratch_get(ctx, SCR_I_MISC, (size_t)n * 6 * 4);
+    if (!misc) return ZS_MEM_ERROR;
+    zs_inflate_args a;
+    a.d_in = d_in; a.d_in_off = d_in_off; a.n = n; a.wrap = wrap; a.deflate64 = d64;
+    a.d_out = d_out; a.d_out_off = d_out_off; a.d_out_len = d_out_len; a.d_in_used = d_in_used;
+    a.d_status = d_status;
+    a.d_detail = (int32_t*)misc;
+    a.d_trailer = misc + n;
+    a.d_flags = misc + 3 * (size_t)n;
+    a.d_dict = d_dict; a.d_dict_rng = d_dict_rng;
+    uint32_t* d_adler = misc + 4 * (size_t)n;
+    uint32_t* d_crc = misc + 5 * (size_t)n;
+    int rc = zs_launch_inflate(ctx, a);
+    if (rc != ZS_OK) return rc;
+    ctx->d_last_detail = a.d_detail;
+    ctx->last_detail_n = n;
+    // checksum of what was produced (inf_leave / CHECK, inflate.ts:1012-1015,1079-1085)
+    const bool want_adler = (wrap & 1) != 0;
+    const bool want_crc = (wrap & 2) != 0 || (wrap == 0 && d_checks != nullptr);
+    if (want_adler) {
+        rc = zs_launch_checksum_segments(ctx, 0, d_out, d_out_off, d_out_len, n, d_adler);
+        if (rc != ZS_OK) return rc;
+    }
+    if (want_crc) {
+        rc = zs_launch_checksum_segments(ctx, 1, d_out, d_out_off, d_out_len, n, d_crc);
+        if (rc != ZS_OK) return rc;
+    }
+    return zs_launch_inflate_verify(ctx, n, want_adler ? d_adler : nullptr, want_crc ? d_crc : nullptr, a.d_trailer,
+                                    a.d_flags, d_out_len, d_checks, d_status, a.d_detail);
+}
+
+int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits, uint8_t* out,
+                     const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks, int32_t* status,
+                     const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (n == 0) return ZS_OK;
+    if (!in_off || !out_off || !out_len || !status) return bad_arg(ctx, "inflate: null buffer");
+    const uint64_t in_total = in_off[n], out_total = out_off[n];
+    if ((in_total && !in) || (out_total && !out)) return bad_arg(ctx, "inflate: null buffer");
+    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_total + 64);
+    uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, out_total + 64);
+    uint64_t* d_ioff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)(n + 1) * 8);
+    uint64_t* d_ooff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF2, (size_t)(n + 1) * 8);
+    // results: out_len[n] in_used[n] (u64) | checks[n] status[n] (u32)
+    uint8_t* d_res = (uint8_t*)zs_scratch_get(ctx, SCR_H_RES, (size_t)n * 24 + 64);
+    if (!d_in || !d_out || !d_ioff || !d_ooff || !d_res) return ZS_MEM_ERROR;
+    uint64_t* d_olen = (uint64_t*)d_res;
+    uint64_t* d_used = d_olen + n;
+    uint32_t* d_checks = (uint32_t*)(d_used + n);
+    int32_t* d_status = (int32_t*)(d_checks + n);
+    uint8_t* d_dict = nullptr;
+    uint64_t* d_rng = nullptr;
+    if (dict && dict_rng && dict_total) {
+        d_dict = (uint8_t*)zs_scratch_get(ctx, SCR_H_DICT, dict_total + 64);
+        d_rng = (uint64_t*)zs_scratch_get(ctx, SCR_H_RNG, (size_t)n * 16);
+        if (!d_dict || !d_rng) return ZS_MEM_ERROR;
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_dict, dict, dict_total, cudaMemcpyHostToDevice, ctx->stream));
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_rng, dict_rng, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (in_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_total, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ioff, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ooff, out_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = zs_inflate_batch_dev(ctx, d_in, d_ioff, n, window_bits, d_out, d_ooff, d_olen, d_used, d_checks, d_status,
+                                  d_dict, d_rng);
+    if (rc != ZS_OK) return rc;
+    if (out_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_olen, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (in_used) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(in_used, d_used, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (checks) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+int zs_inflate_last_details(zs_ctx* ctx, int32_t* detail, uint32_t n) {
+    if (!ctx || !detail) return ZS_STREAM_ERROR;
+    if (!ctx->d_last_detail || n > ctx->last_detail_n) return bad_arg(ctx, "inflate: no details available");
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(detail, ctx->d_last_detail, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,769 @@
+// zs_huff.cu -- K4/K5/K9: length-limited Huffman construction, block-type choice, bit-offset layout,
+// bit-packing encode, wrapper framing and the bit-granular stitch.
+//
+// Replaces the reference's trees.ts for whole blocks: build_tree / pqdownheap / gen_bitlen / gen_codes
+// (src/mod/deflate/trees.ts:54-76,167-316), scan_tree / send_tree / build_bl_tree / send_all_trees
+// (:318-447), compress_block / send_bits (:476-520,78-88), _tr_stored_block (:449-464), the
+// stored/static/dynamic choice of _tr_flush_block (:544-590), and the header / trailer bytes that
+// deflate() emits (src/mod/deflate/deflate.ts:750-832,964-988).
+//
+//  * huff_build_kernel: one thread per block runs the reference's heap construction unchanged
+//    (same tie-breaks, same overflow repair), so for equal symbol frequencies the code lengths are
+//    identical to the reference's -- checked against the oracle's build_tree in the tests.  It
+//    also serialises the dynamic header into a per-block bit blob and records the block's size.
+//  * layout kernels: stored blocks need byte alignment, so a chunk's bit length depends on the bit
+//    offset it starts at; each chunk is summarised as (bits before its first stored block, bits
+//    after), chunk starts are resolved by one warp (prefix scan when no chunk of a 32-chunk group
+//    holds a stored block, shuffle-serial otherwise), then every block gets its absolute bit offset.
+//    This is the "exclusive scan of per-chunk compressed bit lengths" of the north star.
+//  * encode_kernel: one CTA per block; per 256-symbol tile a CTA-wide scan of code lengths gives
+//    every symbol its bit offset, codes are OR-ed into a shared-memory staging tile and flushed as
+//    whole 32-bit words (boundary words with atomicOr, the output having been zeroed).  Blocks
+//    land directly at their final bit offset: the stitch is fused into the encode.
+#include <cstdio>
+
+#include "zs_common.cuh"
+
+namespace {
+
+constexpr int L_CODES = 286, D_CODES = 30, BL_CODES = 19, HEAP_SIZE = 2 * L_CODES + 1;
+constexpr int kHdrWords = 160;   // per-block header blob: word0 = control, words 1.. = bits
+constexpr uint32_t BT_STORED = 0, BT_STATIC = 1, BT_DYNAMIC = 2;
+
+__constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// ---- Huffman construction (thread-private, local memory) ---------------------------------------
+struct Tree {
+    uint16_t freq[HEAP_SIZE];
+    uint16_t dad[HEAP_SIZE];
+    uint16_t len[HEAP_SIZE];
+    int max_code;
+};
+struct Heap {
+    uint16_t heap[HEAP_SIZE + 1];
+    uint8_t depth[HEAP_SIZE];
+    int heap_len, heap_max;
+    uint16_t bl_count[16];
+    uint32_t opt_len, static_len;
+};
+
+__device__ __forceinline__ unsigned static_llen(unsigned n) { return n < 144 ? 8u : n < 256 ? 9u : n < 280 ? 7u : 8u; }
+// canonical code of the fixed literal/length tree (RFC 1951 3.2.6), not yet bit-reversed
+__device__ __forceinline__ unsigned static_lcode(unsigned n) {
+    return n < 144 ? 0x30u + n : n < 256 ? 0x190u + (n - 144u) : n < 280 ? (n - 256u) : 0xC0u + (n - 280u);
+}
+__device__ __forceinline__ unsigned bl_xbits(unsigned n) { return n == 16 ? 2u : n == 17 ? 3u : n == 18 ? 7u : 0u; }
+
+// kind: 0 literal/length, 1 distance, 2 bit-length
+__device__ __forceinline__ unsigned extra_bits(int kind, unsigned n) {
+    if (kind == 0) return n >= 257 ? zs_len_xbits(n - 257u) : 0u;
+    if (kind == 1) return zs_dist_xbits(n);
+    return bl_xbits(n);
+}
+
+__device__ __forceinline__ bool smaller(const Tree& t, const Heap& h, int n, int m) {
+    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && h.depth[n] <= h.depth[m]);
+}
+
+// pqdownheap, trees.ts:167-185
+__device__ void sift_down(const Tree& t, Heap& h, int k) {
+    const int v = h.heap[k];
+    int j = k << 1;
+    while (j <= h.heap_len) {
+        if (j < h.heap_len && smaller(t, h, h.heap[j + 1], h.heap[j])) j++;
+        if (smaller(t, h, v, h.heap[j])) break;
+        h.heap[k] = h.heap[j];
+        k = j;
+        j <<= 1;
+    }
+    h.heap[k] = (uint16_t)v;
+}
+
+// gen_bitlen, trees.ts:187-259
+__device__ void gen_bitlen(Tree& t, Heap& h, int kind, int max_length) {
+    int hh, n, m, bits, overflow = 0;
+    for (bits = 0; bits <= 15; bits++) h.bl_count[bits] = 0;
+    t.len[h.heap[h.heap_max]] = 0;
+    for (hh = h.heap_max + 1; hh < HEAP_SIZE; hh++) {
+        n = h.heap[hh];
+        bits = t.len[t.dad[n]] + 1;
+        if (bits > max_length) { bits = max_length; overflow++; }
+        t.len[n] = (uint16_t)bits;
+        if (n > t.max_code) continue;
+        h.bl_count[bits]++;
+        const unsigned xb = extra_bits(kind, (unsigned)n);
+        const uint32_t f = t.freq[n];
+        h.opt_len += f * ((uint32_t)bits + xb);
+        if (kind == 0) h.static_len += f * (static_llen((unsigned)n) + xb);
+        else if (kind == 1) h.static_len += f * (5u + xb);
+    }
+    if (overflow == 0) return;
+    do {
+        bits = max_length - 1;
+        while (h.bl_count[bits] == 0) bits--;
+        h.bl_count[bits]--;
+        h.bl_count[bits + 1] += 2;
+        h.bl_count[max_length]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (bits = max_length; bits != 0; bits--) {
+        n = h.bl_count[bits];
+        while (n != 0) {
+            m = h.heap[--hh];
+            if (m > t.max_code) continue;
+            if (t.len[m] != (unsigned)bits) {
+                h.opt_len += (uint32_t)(((int)bits - (int)t.len[m]) * (int)t.freq[m]);
+                t.len[m] = (uint16_t)bits;
+            }
+            n--;
+        }
+    }
+}
+
+// build_tree, trees.ts:261-316 (gen_codes is applied by the caller, which needs only bl_count)
+__device__ void build_tree(Tree& t, Heap& h, int kind) {
+    const int elems = kind == 0 ? L_CODES : kind == 1 ? D_CODES : BL_CODES;
+    const int max_length = kind == 2 ? 7 : 15;
+    int n, m, node, max_code = -1;
+    h.heap_len = 0;
+    h.heap_max = HEAP_SIZE;
+    for (n = 0; n < elems; n++) {
+        if (t.freq[n] != 0) { h.heap[++h.heap_len] = (uint16_t)(max_code = n); h.depth[n] = 0; }
+        else t.len[n] = 0;
+    }
+    while (h.heap_len < 2) {
+        node = h.heap[++h.heap_len] = (uint16_t)(max_code < 2 ? ++max_code : 0);
+        t.freq[node] = 1;
+        h.depth[node] = 0;
+        h.opt_len--;
+        if (kind == 0) h.static_len -= static_llen((unsigned)node);
+        else if (kind == 1) h.static_len -= 5u;
+    }
+    t.max_code = max_code;
+    for (n = h.heap_len / 2; n >= 1; n--) sift_down(t, h, n);
+    node = elems;
+    do {
+        n = h.heap[1];
+        h.heap[1] = h.heap[h.heap_len--];
+        sift_down(t, h, 1);
+        m = h.heap[1];
+        h.heap[--h.heap_max] = (uint16_t)n;
+        h.heap[--h.heap_max] = (uint16_t)m;
+        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
+        h.depth[node] = (uint8_t)((h.depth[n] >= h.depth[m] ? h.depth[n] : h.depth[m]) + 1);
+        t.dad[n] = t.dad[m] = (uint16_t)node;
+        h.heap[1] = (uint16_t)node++;
+        sift_down(t, h, 1);
+    } while (h.heap_len >= 2);
+    h.heap[--h.heap_max] = h.heap[1];
+    gen_bitlen(t, h, kind, max_length);
+}
+
+// gen_codes, trees.ts:54-76: next_code per length from bl_count
+__device__ __forceinline__ void next_codes(const uint16_t* bl_count, uint16_t* next) {
+    unsigned c = 0;
+    next[0] = 0;
+    for (int b = 1; b <= 15; b++) { c = (c + bl_count[b - 1]) << 1; next[b] = (uint16_t)c; }
+}
+
+// bit blob writer for the dynamic header (thread-private, writes 32-bit words to global memory)
+struct BlobWriter {
+    uint32_t* w;
+    uint64_t acc;
+    unsigned nacc, nwords;
+    uint32_t total;
+    __device__ __forceinline__ void put(unsigned v, unsigned n) {
+        acc |= (uint64_t)v << nacc;
+        nacc += n;
+        total += n;
+        if (nacc >= 32) { w[nwords++] = (uint32_t)acc; acc >>= 32; nacc -= 32; }
+    }
+    __device__ __forceinline__ void finish() { if (nacc) w[nwords++] = (uint32_t)acc; }
+};
+
+// scan_tree (count = true, trees.ts:318-363) / send_tree (count = false, trees.ts:365-414)
+__device__ void walk_tree(const uint16_t* len, int max_code, bool count, uint16_t* bl_freq,
+                          const uint16_t* bl_code, const uint16_t* bl_len, BlobWriter* bw) {
+    int prevlen = -1, curlen, nextlen = len[0], cnt = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    for (int n = 0; n <= max_code; n++) {
+        curlen = nextlen;
+        nextlen = n + 1 <= max_code ? len[n + 1] : 0xffff;  // the reference plants a 0xffff guard
+        if (++cnt < max_count && curlen == nextlen) continue;
+        if (cnt < min_count) {
+            if (count) bl_freq[curlen] += (uint16_t)cnt;
+            else do bw->put(bl_code[curlen], bl_len[curlen]); while (--cnt != 0);
+        } else if (curlen != 0) {
+            if (curlen != prevlen) {
+                if (count) bl_freq[curlen]++;
+                else { bw->put(bl_code[curlen], bl_len[curlen]); cnt--; }
+            }
+            if (count) bl_freq[16]++;
+            else { bw->put(bl_code[16], bl_len[16]); bw->put((unsigned)(cnt - 3), 2); }
+        } else if (cnt <= 10) {
+            if (count) bl_freq[17]++;
+            else { bw->put(bl_code[17], bl_len[17]); bw->put((unsigned)(cnt - 3), 3); }
+        } else {
+            if (count) bl_freq[18]++;
+            else { bw->put(bl_code[18], bl_len[18]); bw->put((unsigned)(cnt - 11), 7); }
+        }
+        cnt = 0;
+        prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
+struct HuffArgs {
+    uint32_t n_chunks, max_bpc;
+    const uint32_t* chunk_nblk;
+    const uint32_t* blk_desc;
+    const uint32_t* blk_freq;
+    uint32_t* blk_code;
+    uint32_t* blk_hdr;
+    uint64_t* blk_bits;
+};
+
+// _tr_flush_block's decision (trees.ts:544-583) for every block; one thread per block.
+__global__ void __launch_bounds__(64) huff_build_kernel(HuffArgs a) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)a.n_chunks * a.max_bpc;
+    if (gid >= total) return;
+    const uint32_t chunk = (uint32_t)(gid / a.max_bpc), j = (uint32_t)(gid % a.max_bpc);
+    if (j >= a.chunk_nblk[chunk]) return;
+    const uint32_t* freq = a.blk_freq + gid * 320;
+    const uint32_t in_len = a.blk_desc[gid * 4 + 3];
+
+    Tree lt, dt, bt;
+    Heap h;
+    h.opt_len = h.static_len = 0;
+    for (int n = 0; n < L_CODES; n++) lt.freq[n] = (uint16_t)freq[n];
+    lt.freq[256] = 1;  // END_BLOCK, init_block trees.ts:100
+    for (int n = 0; n < D_CODES; n++) dt.freq[n] = (uint16_t)freq[288 + n];
+    build_tree(lt, h, 0);
+    uint16_t lnext[16], dnext[16], bnext[16];
+    next_codes(h.bl_count, lnext);
+    build_tree(dt, h, 1);
+    next_codes(h.bl_count, dnext);
+    // build_bl_tree, trees.ts:416-432
+    for (int n = 0; n < BL_CODES; n++) bt.freq[n] = 0;
+    walk_tree(lt.len, lt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
+    walk_tree(dt.len, dt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
+    build_tree(bt, h, 2);
+    next_codes(h.bl_count, bnext);
+    int max_blindex;
+    for (max_blindex = BL_CODES - 1; max_blindex >= 3; max_blindex--)
+        if (bt.len[c_bl_order[max_blindex]] != 0) break;
+    h.opt_len += 3u * ((uint32_t)max_blindex + 1u) + 5u + 5u + 4u;
+    uint32_t opt_lenb = (h.opt_len + 3u + 7u) >> 3;
+    const uint32_t static_lenb = (h.static_len + 3u + 7u) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+
+    uint32_t* code = a.blk_code + gid * 320;
+    uint32_t* hdr = a.blk_hdr + gid * kHdrWords;
+    uint32_t type;
+    uint64_t bits;
+    if (in_len + 4u <= opt_lenb && in_len <= 65535u) {
+        type = BT_STORED;
+        bits = 3ull + 32ull + 8ull * in_len;  // plus alignment padding, resolved by the layout
+        hdr[0] = type;
+    } else if (static_lenb == opt_lenb) {
+        type = BT_STATIC;
+        bits = 3ull + h.static_len;
+        for (unsigned n = 0; n < (unsigned)L_CODES; n++) {
+            unsigned l = static_llen(n);
+            code[n] = zs_bitrev(static_lcode(n), l) | (l << 16);
+        }
+        for (unsigned n = 0; n < (unsigned)D_CODES; n++) code[288 + n] = zs_bitrev(n, 5) | (5u << 16);
+        hdr[0] = type;
+    } else {
+        type = BT_DYNAMIC;
+        bits = 3ull + h.opt_len;
+        for (int n = 0; n < L_CODES; n++) {
+            unsigned l = n <= lt.max_code ? lt.len[n] : 0;
+            code[n] = l ? (zs_bitrev(lnext[l]++, l) | (l << 16)) : 0u;
+        }
+        for (int n = 0; n < D_CODES; n++) {
+            unsigned l = n <= dt.max_code ? dt.len[n] : 0;
+            code[288 + n] = l ? (zs_bitrev(dnext[l]++, l) | (l << 16)) : 0u;
+        }
+        uint16_t bcode[BL_CODES], blen[BL_CODES];
+        for (int n = 0; n < BL_CODES; n++) {
+            unsigned l = n <= bt.max_code ? bt.len[n] : 0;
+            blen[n] = (uint16_t)l;
+            bcode[n] = l ? (uint16_t)zs_bitrev(bnext[l]++, l) : 0;
+        }
+        // send_all_trees, trees.ts:434-447
+        BlobWriter bw = {hdr + 1, 0, 0, 0, 0};
+        bw.put((unsigned)(lt.max_code + 1 - 257), 5);
+        bw.put((unsigned)(dt.max_code + 1 - 1), 5);
+        bw.put((unsigned)(max_blindex + 1 - 4), 4);
+        for (int r = 0; r <= max_blindex; r++) bw.put(blen[c_bl_order[r]], 3);
+        walk_tree(lt.len, lt.max_code, false, nullptr, bcode, blen, &bw);
+        walk_tree(dt.len, dt.max_code, false, nullptr, bcode, blen, &bw);
+        bw.finish();
+        hdr[0] = type | (bw.total << 8);
+    }
+    a.blk_bits[gid] = bits;
+}
+
+// ---- layout --------------------------------------------------------------------------------------
+struct LayoutArgs {
+    uint32_t n_chunks, max_bpc;
+    int wrap, mode;
+    uint32_t flags;
+    const uint64_t* in_off;
+    const uint32_t* chunk_nblk;
+    uint32_t* blk_hdr;
+    uint64_t* blk_bits;   // in: size; out: absolute bit offset of the block
+    uint64_t* chunk_pr;   // [n][2]
+    uint64_t* out_off;    // [n+1]
+    uint64_t* out_bits;   // [n]
+    uint64_t out_cap;
+    zs_deflate_result* result;
+    int32_t* error;
+    const uint32_t* check_total;
+};
+
+__device__ __forceinline__ unsigned stored_pad(uint64_t bitpos_after_hdr) { return (unsigned)((8u - (bitpos_after_hdr & 7u)) & 7u); }
+
+// chunk summary: P = bits up to (excluding) the first stored block, R = bits from that block's
+// LEN field to the end of the chunk (later stored blocks start from a known alignment)
+__global__ void layout_chunks_kernel(LayoutArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+    const uint32_t nb = a.chunk_nblk[c];
+    // no marker after the chunk that carries the BFINAL block
+    const bool sync_marker = a.mode == ZS_MODE_STITCHED && (a.flags & ZS_FLAG_SYNC) &&
+                             !(c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST));
+    uint64_t P = 0, R = 0;
+    bool seen = false;
+    for (uint32_t j = 0; j < nb + (sync_marker ? 1u : 0u); j++) {
+        const bool marker = j == nb;
+        const uint64_t gid = (uint64_t)c * a.max_bpc + j;
+        const uint32_t type = marker ? BT_STORED : (a.blk_hdr[gid * kHdrWords] & 0xffu);
+        const uint64_t bits = marker ? 35ull : a.blk_bits[gid];
+        if (type == BT_STORED) {
+            if (!seen) { seen = true; R = bits - 3; }
+            else R += 3 + stored_pad(R + 3) + (bits - 3);  // R counts from a byte boundary
+        } else {
+            if (seen) R += bits; else P += bits;
+        }
+    }
+    a.chunk_pr[2 * c] = P;
+    a.chunk_pr[2 * c + 1] = (R << 1) | (seen ? 1u : 0u);
+}
+
+__device__ __forceinline__ uint64_t chunk_len_at(uint64_t start, uint64_t P, uint64_t Rf) {
+    if (!(Rf & 1u)) return P;
+    return P + 3 + stored_pad(start + P + 3) + (Rf >> 1);
+}
+
+// One warp resolves the start of every chunk.  INDEPENDENT: byte offsets of whole streams
+// (wrapper header + body + trailer).  STITCHED: bit offsets inside the single stream.
+__global__ void __launch_bounds__(32) layout_scan_kernel(LayoutArgs a) {
+    const unsigned lane = zs_lane();
+    const uint64_t H = a.wrap == ZS_WRAP_ZLIB ? 2 : a.wrap == ZS_WRAP_GZIP ? 10 : 0;
+    const uint64_t T = a.wrap == ZS_WRAP_ZLIB ? 4 : a.wrap == ZS_WRAP_GZIP ? 8 : 0;
+    const bool stitched = a.mode == ZS_MODE_STITCHED;
+    uint64_t pos = 0;  // INDEPENDENT: bytes; STITCHED: bits
+    if (stitched && !(a.flags & ZS_FLAG_NOT_FIRST)) pos = 8 * H;
+    for (uint32_t base = 0; base < a.n_chunks; base += 32) {
+        const uint32_t c = base + lane;
+        const bool live = c < a.n_chunks;
+        const uint64_t P = live ? a.chunk_pr[2 * c] : 0, Rf = live ? a.chunk_pr[2 * c + 1] : 0;
+        const unsigned cnt = a.n_chunks - base < 32 ? a.n_chunks - base : 32;
+        uint64_t my_start, my_bits;
+        if (!stitched) {
+            my_bits = live ? chunk_len_at(0, P, Rf) : 0;
+            uint64_t sz = live ? H + ((my_bits + 7) >> 3) + T : 0, incl = sz;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            my_start = pos + incl - sz;
+            pos += __shfl_sync(ZS_FULL_MASK, incl, 31);
+        } else if (__ballot_sync(ZS_FULL_MASK, (Rf & 1u) != 0) == 0) {
+            my_bits = P;
+            uint64_t incl = P;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            my_start = pos + incl - P;
+            pos += __shfl_sync(ZS_FULL_MASK, incl, 31);
+        } else {
+            my_start = 0; my_bits = 0;
+            for (unsigned i = 0; i < cnt; i++) {
+                const uint64_t Pi = __shfl_sync(ZS_FULL_MASK, P, i), Ri = __shfl_sync(ZS_FULL_MASK, Rf, i);
+                const uint64_t len = chunk_len_at(pos, Pi, Ri);
+                if (lane == i) { my_start = pos; my_bits = len; }
+                pos += len;
+            }
+        }
+        if (live) { a.out_off[c] = my_start; a.out_bits[c] = my_bits; }
+    }
+    if (lane == 0) {
+        uint64_t total_bits, total_bytes;
+        if (stitched) {
+            total_bits = pos;
+            total_bytes = (pos + 7) >> 3;
+            if (!(a.flags & ZS_FLAG_NOT_LAST)) {
+                // the trailer covers the whole stream, so only a call that holds the whole stream
+                // writes it; the last part of a multi-part stream is just padded to a byte
+                if (!(a.flags & ZS_FLAG_NOT_FIRST)) total_bytes += T;
+                total_bits = total_bytes * 8;
+            }
+        } else {
+            total_bytes = pos;
+            total_bits = pos * 8;
+        }
+        a.out_off[a.n_chunks] = pos;
+        a.result->total_out_bytes = total_bytes;
+        a.result->total_out_bits = total_bits;
+        if (total_bytes > a.out_cap) *a.error = ZS_BUF_ERROR;
+    }
+}
+
+// absolute bit offset + BFINAL flag for every block
+__global__ void layout_blocks_kernel(LayoutArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+    const uint32_t nb = a.chunk_nblk[c];
+    const bool stitched = a.mode == ZS_MODE_STITCHED;
+    const uint64_t H = a.wrap == ZS_WRAP_ZLIB ? 2 : a.wrap == ZS_WRAP_GZIP ? 10 : 0;
+    uint64_t pos = stitched ? a.out_off[c] : 8 * (a.out_off[c] + H);
+    const bool chunk_final = stitched ? (c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST)) : true;
+    for (uint32_t j = 0; j < nb; j++) {
+        const uint64_t gid = (uint64_t)c * a.max_bpc + j;
+        const uint32_t h0 = a.blk_hdr[gid * kHdrWords];
+        const uint64_t bits = a.blk_bits[gid];
+        a.blk_bits[gid] = pos;
+        if (chunk_final && j + 1 == nb) a.blk_hdr[gid * kHdrWords] = h0 | 0x80000000u;
+        if ((h0 & 0xffu) == BT_STORED) pos += 3 + stored_pad(pos + 3) + (bits - 3);
+        else pos += bits;
+    }
+}
+
+// ---- encode --------------------------------------------------------------------------------------
+struct EncodeArgs {
+    uint32_t n_chunks, max_bpc;
+    int wrap, mode;
+    uint32_t flags;
+    const uint8_t* in;          // d_in
+    const uint64_t* in_off;
+    const uint32_t* sym;
+    const uint32_t* chunk_nblk;
+    const uint32_t* blk_desc;
+    const uint32_t* blk_code;
+    const uint32_t* blk_hdr;
+    const uint64_t* blk_abs;    // absolute bit offsets
+    const uint64_t* out_off;
+    const uint64_t* out_bits;
+    const uint32_t* checks;     // per-chunk check values (wrapper trailers), may be null
+    const uint32_t* check_total;
+    uint8_t* out;
+    const zs_deflate_result* result;
+    const int32_t* error;
+    int level;
+};
+
+__device__ __forceinline__ void or_bits_global(uint32_t* out32, uint64_t bitpos, uint64_t v, unsigned n) {
+    if (n == 0) return;
+    uint64_t w = bitpos >> 5;
+    unsigned sh = (unsigned)(bitpos & 31u);
+    atomicOr(out32 + w, (uint32_t)(v << sh));
+    if (sh + n > 32) {
+        uint64_t rest = v >> (32 - sh);
+        atomicOr(out32 + w + 1, (uint32_t)rest);
+        if (sh + n > 64) atomicOr(out32 + w + 2, (uint32_t)(rest >> 32));
+    }
+}
+
+__global__ void zero_output_kernel(uint8_t* out, const zs_deflate_result* result, const int32_t* error, uint64_t cap) {
+    if (*error) return;
+    uint64_t nbytes = result->total_out_bytes + 8;  // the encoder ORs whole words near the end
+    if (nbytes > cap) nbytes = cap;
+    uint64_t nvec = nbytes >> 4;
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x)
+        o[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x < 16) {
+        uint64_t i = (nvec << 4) + threadIdx.x;
+        if (i < nbytes) out[i] = 0;
+    }
+}
+
+constexpr int kEncThreads = 256;
+
+// compress_block (trees.ts:476-520) for one block per CTA
+__global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
+    if (*a.error) return;
+    const uint64_t gid = blockIdx.x;
+    const uint32_t chunk = (uint32_t)(gid / a.max_bpc), j = (uint32_t)(gid % a.max_bpc);
+    if (j >= a.chunk_nblk[chunk]) return;
+    __shared__ uint32_t s_code[320];
+    __shared__ uint32_t s_stage[kEncThreads * 2 + 4];  // up to 48+ bits per symbol, plus a lead-in word
+    __shared__ uint32_t s_warp[kEncThreads / 32];
+    const unsigned t = threadIdx.x, lane = t & 31u, wid = t >> 5;
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(a.out);
+    const uint32_t h0 = a.blk_hdr[gid * kHdrWords];
+    const uint32_t type = h0 & 0xffu, final = h0 >> 31, hdr_bits = (h0 >> 8) & 0x7fffffu;
+    uint64_t pos = a.blk_abs[gid];
+    const uint32_t sym0 = a.blk_desc[gid * 4 + 0], nsym = a.blk_desc[gid * 4 + 1];
+    const uint32_t in0 = a.blk_desc[gid * 4 + 2], in_len = a.blk_desc[gid * 4 + 3];
+    const uint64_t cbase = a.in_off[chunk];
+
+    if (type == BT_STORED) {
+        // _tr_stored_block, trees.ts:449-464
+        if (t == 0) or_bits_global(out32, pos, final, 3);
+        pos += 3;
+        pos += stored_pad(pos);
+        uint8_t* o = a.out + (pos >> 3);
+        if (t == 0) {
+            o[0] = (uint8_t)in_len; o[1] = (uint8_t)(in_len >> 8);
+            o[2] = (uint8_t)~in_len; o[3] = (uint8_t)(~in_len >> 8);
+        }
+        const uint8_t* src = a.in + cbase + in0;
+        for (uint32_t i = t; i < in_len; i += kEncThreads) o[4 + i] = __ldg(src + i);
+        return;
+    }
+
+    for (unsigned i = t; i < 320; i += kEncThreads) s_code[i] = a.blk_code[gid * 320 + i];
+    // block header: BFINAL | BTYPE << 1, then the serialised trees of a dynamic block
+    if (t == 0) or_bits_global(out32, pos, final | (type << 1), 3);
+    pos += 3;
+    if (type == BT_DYNAMIC) {
+        const uint32_t* hw = a.blk_hdr + gid * kHdrWords + 1;
+        const unsigned nw = (hdr_bits + 31) >> 5;
+        for (unsigned i = t; i < nw; i += kEncThreads) {
+            unsigned nb = (i + 1 == nw && (hdr_bits & 31u)) ? (hdr_bits & 31u) : 32u;
+            or_bits_global(out32, pos + 32ull * i, hw[i], nb);
+        }
+        pos += hdr_bits;
+    }
+    __syncthreads();
+
+    const uint32_t* sym = a.sym + cbase + sym0;
+    for (uint32_t tile = 0; tile < nsym; tile += kEncThreads) {
+        const uint32_t i = tile + t;
+        uint64_t v = 0;
+        unsigned nb = 0;
+        if (i < nsym) {
+            const uint32_t s = sym[i];
+            const unsigned dist = s >> 16, lc = s & 0xffffu;
+            if (dist == 0) {
+                const uint32_t e = s_code[lc];
+                v = e & 0xffffu; nb = e >> 16;
+            } else {
+                const unsigned l3 = lc - 3u;
+                const unsigned lcode = zs_len_code(l3);
+                uint32_t e = s_code[257u + lcode];
+                v = e & 0xffffu; nb = e >> 16;
+                unsigned xb = zs_len_xbits(lcode);
+                v |= (uint64_t)(l3 - zs_len_base(lcode)) << nb; nb += xb;
+                const unsigned d1 = dist - 1u;
+                const unsigned dcode = zs_dist_code(d1);
+                e = s_code[288u + dcode];
+                v |= (uint64_t)(e & 0xffffu) << nb; nb += e >> 16;
+                xb = zs_dist_xbits(dcode);
+                v |= (uint64_t)(d1 - zs_dist_base(dcode)) << nb; nb += xb;
+            }
+        }
+        // CTA-wide exclusive scan of nb
+        unsigned incl = nb;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned x = __shfl_up_sync(ZS_FULL_MASK, incl, o);
+            if ((int)lane >= o) incl += x;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        for (unsigned k = t; k < kEncThreads * 2 + 4; k += kEncThreads) s_stage[k] = 0;
+        __syncthreads();
+        unsigned wbase = 0, tile_bits = 0;
+        for (unsigned k = 0; k < kEncThreads / 32; k++) {
+            const unsigned x = s_warp[k];
+            if (k < wid) wbase += x;
+            tile_bits += x;
+        }
+        const unsigned lead = (unsigned)(pos & 31u);
+        const unsigned off = lead + wbase + incl - nb;
+        if (nb) {
+            const unsigned w = off >> 5, sh = off & 31u;
+            atomicOr(&s_stage[w], (uint32_t)(v << sh));
+            if (sh + nb > 32) {
+                const uint64_t rest = v >> (32 - sh);
+                atomicOr(&s_stage[w + 1], (uint32_t)rest);
+                if (sh + nb > 64) atomicOr(&s_stage[w + 2], (uint32_t)(rest >> 32));
+            }
+        }
+        __syncthreads();
+        const unsigned nwords = (lead + tile_bits + 31) >> 5;
+        const uint64_t w0 = pos >> 5;
+        for (unsigned k = t; k < nwords; k += kEncThreads) {
+            const uint32_t x = s_stage[k];
+            if (k == 0 || k + 1 == nwords) { if (x) atomicOr(out32 + w0 + k, x); }
+            else out32[w0 + k] = x;
+        }
+        pos += tile_bits;
+        __syncthreads();
+    }
+    if (t == 0) {
+        const uint32_t e = s_code[256];
+        or_bits_global(out32, pos, e & 0xffffu, e >> 16);
+    }
+}
+
+// wrapper header / trailer bytes (deflate.ts:750-832, 964-988) and the optional sync markers
+__global__ void frame_kernel(EncodeArgs a) {
+    if (*a.error) return;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool stitched = a.mode == ZS_MODE_STITCHED;
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(a.out);
+    if (c >= a.n_chunks) return;
+    // Z_SYNC_FLUSH marker after each chunk: empty stored block 000 + pad + 00 00 ff ff
+    if (stitched && (a.flags & ZS_FLAG_SYNC) && !(c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST))) {
+        uint64_t end = a.out_off[c] + a.out_bits[c];  // marker is the tail of the chunk's bits
+        uint64_t p = (end >> 3) - 4;                   // marker ends byte aligned
+        a.out[p] = 0; a.out[p + 1] = 0; a.out[p + 2] = 0xff; a.out[p + 3] = 0xff;
+    }
+    const bool first = stitched ? (c == 0 && !(a.flags & ZS_FLAG_NOT_FIRST)) : true;
+    const bool last = stitched ? (c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST)) : true;
+    uint8_t* hp = stitched ? a.out : a.out + a.out_off[c];
+    if (first) {
+        if (a.wrap == ZS_WRAP_ZLIB) {
+            unsigned header = (8u + (7u << 4)) << 8;
+            unsigned lf = a.level < 2 ? 0u : a.level < 6 ? 1u : a.level == 6 ? 2u : 3u;
+            header |= lf << 6;
+            header += 31u - header % 31u;
+            hp[0] = (uint8_t)(header >> 8); hp[1] = (uint8_t)header;
+        } else if (a.wrap == ZS_WRAP_GZIP) {
+            hp[0] = 0x1f; hp[1] = 0x8b; hp[2] = 8;
+            for (int k = 3; k < 8; k++) hp[k] = 0;
+            hp[8] = a.level == 9 ? 2 : a.level < 2 ? 4 : 0;
+            hp[9] = 255;  // OS_CODE of the reference, deflate/constants.ts:30
+        }
+    }
+    if (last && a.wrap != ZS_WRAP_RAW && !(stitched && (a.flags & ZS_FLAG_NOT_FIRST))) {
+        uint64_t body_end_bits = stitched ? a.out_off[a.n_chunks] : 0;
+        uint8_t* tp;
+        uint32_t ck;
+        uint64_t isize;
+        if (stitched) {
+            tp = a.out + ((body_end_bits + 7) >> 3);
+            ck = *a.check_total;
+            isize = a.in_off[a.n_chunks];
+        } else {
+            const uint64_t H = a.wrap == ZS_WRAP_ZLIB ? 2 : 10;
+            tp = a.out + a.out_off[c] + H + ((a.out_bits[c] + 7) >> 3);
+            ck = a.checks[c];
+            isize = a.in_off[c + 1] - a.in_off[c];
+        }
+        if (a.wrap == ZS_WRAP_ZLIB) {
+            tp[0] = (uint8_t)(ck >> 24); tp[1] = (uint8_t)(ck >> 16); tp[2] = (uint8_t)(ck >> 8); tp[3] = (uint8_t)ck;
+        } else {
+            tp[0] = (uint8_t)ck; tp[1] = (uint8_t)(ck >> 8); tp[2] = (uint8_t)(ck >> 16); tp[3] = (uint8_t)(ck >> 24);
+            tp[4] = (uint8_t)isize; tp[5] = (uint8_t)(isize >> 8); tp[6] = (uint8_t)(isize >> 16); tp[7] = (uint8_t)(isize >> 24);
+        }
+    }
+    (void)out32;
+}
+
+__global__ void count_blocks_kernel(const uint32_t* nblk, uint32_t n, zs_deflate_result* result, const uint32_t* check_total) {
+    __shared__ uint32_t s[256];
+    uint32_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256) acc += nblk[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        result->n_blocks = s[0];
+        result->check = check_total ? *check_total : 0u;
+    }
+}
+
+// K9: OR n_bits of src into dst at bit offset dst_off (dst bits must be zero)
+__global__ void bit_concat_kernel(uint32_t* dst32, uint64_t dst_off, const uint8_t* __restrict__ src, uint64_t n_bits) {
+    const uint64_t n_words = (n_bits + 31) >> 5;
+    const unsigned sh = (unsigned)(dst_off & 31u);
+    const uint64_t w0 = dst_off >> 5;
+    const uint64_t src_bytes = (n_bits + 7) >> 3;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+        // destination word w0+i receives the high part of source word i-1 and the low part of word i
+        auto load = [&](uint64_t k) -> uint32_t {
+            if (k >= n_words) return 0u;
+            uint32_t v = 0;
+            uint64_t b = k << 2;
+            for (unsigned q = 0; q < 4 && b + q < src_bytes; q++) v |= (uint32_t)__ldg(src + b + q) << (8 * q);
+            if (k + 1 == n_words && (n_bits & 31u)) v &= (1u << (n_bits & 31u)) - 1u;
+            return v;
+        };
+        const uint32_t lo = i ? load(i - 1) : 0u, hi = load(i);
+        const uint32_t x = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+        if (x) {
+            if (i == 0 || i + 1 >= n_words) atomicOr(dst32 + w0 + i, x);
+            else dst32[w0 + i] |= x;  // interior words belong to this call alone
+        }
+    }
+}
+
+}  // namespace
+
+int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
+    const uint64_t nblk_slots = (uint64_t)p.n_chunks * p.max_bpc;
+    if (nblk_slots == 0) return ZS_OK;
+    if (nblk_slots > 0x7fffffffull) {
+        snprintf(ctx->err, sizeof(ctx->err), "deflate: too many block slots");
+        return ZS_STREAM_ERROR;
+    }
+    HuffArgs h = {p.n_chunks, p.max_bpc, p.d_chunk_nblk, p.d_blk_desc, p.d_blk_freq, p.d_blk_code, p.d_blk_hdr, p.d_blk_bits};
+    huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h);
+    ZS_LAUNCH_CHECK(ctx, "huff_build_kernel");
+
+    LayoutArgs l;
+    l.n_chunks = p.n_chunks; l.max_bpc = p.max_bpc; l.wrap = p.wrap; l.mode = p.mode; l.flags = p.flags;
+    l.in_off = p.d_in_off; l.chunk_nblk = p.d_chunk_nblk; l.blk_hdr = p.d_blk_hdr; l.blk_bits = p.d_blk_bits;
+    l.chunk_pr = p.d_chunk_pr; l.out_off = p.d_out_off; l.out_bits = p.d_out_bits; l.out_cap = p.out_cap;
+    l.result = p.d_result; l.error = p.d_error; l.check_total = p.d_check_total;
+    const unsigned cgrid = (p.n_chunks + 127) / 128;
+    layout_chunks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l);
+    ZS_LAUNCH_CHECK(ctx, "layout_chunks_kernel");
+    layout_scan_kernel<<<1, 32, 0, ctx->stream>>>(l);
+    ZS_LAUNCH_CHECK(ctx, "layout_scan_kernel");
+    layout_blocks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l);
+    ZS_LAUNCH_CHECK(ctx, "layout_blocks_kernel");
+
+    zero_output_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p.d_out, p.d_result, p.d_error, p.out_cap);
+    ZS_LAUNCH_CHECK(ctx, "zero_output_kernel");
+
+    EncodeArgs e;
+    e.n_chunks = p.n_chunks; e.max_bpc = p.max_bpc; e.wrap = p.wrap; e.mode = p.mode; e.flags = p.flags;
+    e.in = p.d_in; e.in_off = p.d_in_off; e.sym = p.d_sym; e.chunk_nblk = p.d_chunk_nblk; e.blk_desc = p.d_blk_desc;
+    e.blk_code = p.d_blk_code; e.blk_hdr = p.d_blk_hdr; e.blk_abs = p.d_blk_bits; e.out_off = p.d_out_off;
+    e.out_bits = p.d_out_bits; e.checks = p.d_checks; e.check_total = p.d_check_total; e.out = p.d_out;
+    e.result = p.d_result; e.error = p.d_error; e.level = p.level;
+    encode_kernel<<<(unsigned)nblk_slots, kEncThreads, 0, ctx->stream>>>(e);
+    ZS_LAUNCH_CHECK(ctx, "encode_kernel");
+    frame_kernel<<<cgrid, 128, 0, ctx->stream>>>(e);
+    ZS_LAUNCH_CHECK(ctx, "frame_kernel");
+    count_blocks_kernel<<<1, 256, 0, ctx->stream>>>(p.d_chunk_nblk, p.n_chunks, p.d_result, p.d_check_total);
+    ZS_LAUNCH_CHECK(ctx, "count_blocks_kernel");
+    return ZS_OK;
+}
+
+int zs_launch_bit_concat(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits) {
+    if (n_bits == 0) return ZS_OK;
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(d_dst) & 3u;
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(d_dst - mis);
+    const uint64_t off = dst_bit_off + 8ull * mis;
+    const uint64_t n_words = (n_bits + 31) >> 5;
+    uint64_t blocks = (n_words + 1 + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    bit_concat_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst32, off, d_src, n_bits);
+    ZS_LAUNCH_CHECK(ctx, "bit_concat_kernel");
+    return ZS_OK;
+}

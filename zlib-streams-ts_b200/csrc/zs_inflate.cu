@@ -1,0 +1,612 @@
+// zs_inflate.cu -- K6/K7: batch inflate of independent streams (deflate and raw deflate64).
+//
+// One warp per stream.  Results must be bit-exact with the reference decoder: inflate_fast
+// (src/mod/inflate/inffast.ts:5), inflate_table (inftrees.ts:62), the block / header / trailer modes
+// of inflate() (inflate.ts:332-1100) when called as inflate(strm, Z_FINISH) on a whole stream: same
+// output bytes, same total_in / total_out, same return code and message.
+//
+// Layout: every warp owns a private decode-table arena in shared memory (852 length + 594 distance
+// entries of 32 bits, the reference's ENOUGH bounds).  The dynamic-block header is parsed and the
+// tables are built by lane 0 (serial by nature: run-length coded code lengths, canonical code
+// assignment); symbol decoding is warp-uniform (every lane tracks the same bit buffer, shared
+// memory table reads are broadcasts) so that back-reference copies and stored-block copies are
+// executed by all 32 lanes without any hand-off.  Output goes straight to HBM; the history window
+// of the reference (32/64 KiB ring) is the already written output itself plus the optional preset
+// dictionary.
+#include <cstdio>
+
+#include "zs_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kEnoughLens = 852;
+constexpr int kEnoughDists = 592;
+constexpr int kEnoughDists9 = 594;
+
+// detail codes -> reference messages (see zs_inflate_message)
+enum {
+    D_NONE = 0, D_HEADER_CHECK, D_METHOD, D_WINDOW, D_HDR_FLAGS, D_HDR_CRC, D_BLOCK_TYPE, D_STORED_LEN,
+    D_TOO_MANY, D_TOO_MANY_9, D_CODE_LENGTHS, D_BIT_REPEAT, D_NO_EOB, D_LITLEN_SET, D_DIST_SET, D_LITLEN_CODE,
+    D_DIST_CODE, D_TOO_FAR, D_DATA_CHECK, D_LENGTH_CHECK
+};
+
+#define E_OP(e) ((e) >> 24)
+#define E_BITS(e) (((e) >> 16) & 0xffu)
+#define E_VAL(e) ((e) & 0xffffu)
+#define E_PACK(op, bits, val) (((uint32_t)(op) << 24) | ((uint32_t)(bits) << 16) | (uint32_t)(val))
+
+struct WarpArena {
+    uint32_t codes[kEnoughLens + kEnoughDists9];
+    uint16_t lens[320];
+    uint16_t work[288];
+};
+
+struct FixedTables {
+    uint32_t len[512];
+    uint32_t dist[32];
+};
+
+// ---- base / extra tables for length and distance symbols (inflate/constants.ts:8-45) -------------
+__device__ __forceinline__ void len_sym(unsigned idx, bool d64, unsigned& base, unsigned& op) {
+    // idx = symbol - 257
+    if (idx < 28) {
+        unsigned eb = idx < 8 ? 0u : (idx - 4u) >> 2;
+        base = 3u + (idx < 8 ? idx : ((4u + (idx & 3u)) << eb));
+        op = (d64 ? 128u : 16u) + eb;
+    } else if (idx == 28) {
+        base = d64 ? 3u : 258u;
+        op = d64 ? 144u : 16u;
+    } else {
+        base = 0;
+        op = 64u;  // invalid code marker (the reference stores 73/200 resp. 72/78: bit 64 set)
+    }
+}
+__device__ __forceinline__ void dist_sym(unsigned idx, bool d64, unsigned& base, unsigned& op) {
+    if (idx < 30) {
+        unsigned eb = idx < 4 ? 0u : (idx - 2u) >> 1;
+        base = 1u + (idx < 4 ? idx : ((2u + (idx & 1u)) << eb));
+        op = (d64 ? 128u : 16u) + eb;
+    } else if (d64) {
+        base = idx == 30 ? 32769u : 49153u;
+        op = 142u;
+    } else {
+        base = 0;
+        op = 64u;
+    }
+}
+
+__device__ __forceinline__ uint32_t table_entry(unsigned sym, unsigned nbits, int type, bool d64) {
+    if (type == 0) return E_PACK(0, nbits, sym);
+    if (type == 1) {
+        if (sym < 256) return E_PACK(0, nbits, sym);
+        if (sym == 256) return E_PACK(96, nbits, 0);
+        unsigned base, op;
+        len_sym(sym - 257, d64, base, op);
+        return E_PACK(op, nbits, base);
+    }
+    unsigned base, op;
+    dist_sym(sym, d64, base, op);
+    return E_PACK(op, nbits, base);
+}
+
+// inflate_table (inftrees.ts:62-277), executed by a single lane.  Returns 0 ok, -1 invalid set,
+// 1 not enough table space.  *index advances by the space used, *bits receives the root bits.
+__device__ int build_table(int type, const uint16_t* lens, unsigned codes, uint32_t* table, unsigned* bits,
+                           uint16_t* work, unsigned* index, bool d64) {
+    unsigned len, sym, mn, mx, root, curr, drop, used, huff, incr, fill, mask, next;
+    int left, low;
+    uint16_t count[16], offs[16];
+    const unsigned enough_d = d64 ? kEnoughDists9 : kEnoughDists;
+
+    for (len = 0; len <= 15; len++) count[len] = 0;
+    for (sym = 0; sym < codes; sym++) count[lens[sym]]++;
+    root = *bits;
+    for (mx = 15; mx >= 1; mx--)
+        if (count[mx] != 0) break;
+    if (root > mx) root = mx;
+    if (mx == 0) {
+        if (!d64) {  // inftrees.ts:113-123
+            table[*index] = E_PACK(64, 1, 0);
+            table[*index + 1] = E_PACK(64, 1, 0);
+            *index += 2;
+            *bits = 1;
+            return 0;
+        }
+        return -1;
+    }
+    for (mn = 1; mn < mx; mn++)
+        if (count[mn] != 0) break;
+    if (root < mn) root = mn;
+    left = 1;
+    for (len = 1; len <= 15; len++) {
+        left <<= 1;
+        left -= count[len];
+        if (left < 0) return -1;
+    }
+    if (left > 0 && (type == 0 || mx != 1)) return -1;
+
+    offs[1] = 0;
+    for (len = 1; len < 15; len++) offs[len + 1] = offs[len] + count[len];
+    for (sym = 0; sym < codes; sym++)
+        if (lens[sym] != 0) work[offs[lens[sym]]++] = (uint16_t)sym;
+
+    huff = 0; sym = 0; len = mn; next = *index; curr = root; drop = 0; low = -1;
+    used = 1u << root;
+    mask = used - 1;
+#define TOO_BIG() ((type == 1 && (d64 ? used >= (unsigned)kEnoughLens : used > (unsigned)kEnoughLens)) || \
+                   (type == 2 && (d64 ? used >= enough_d : used > enough_d)))
+    if (TOO_BIG()) return 1;
+    for (;;) {
+        uint32_t here = table_entry(work[sym], len - drop, type, d64);
+        incr = 1u << (len - drop);
+        fill = 1u << curr;
+        do {
+            fill -= incr;
+            table[next + (huff >> drop) + fill] = here;
+        } while (fill != 0);
+        incr = 1u << (len - 1);
+        while (huff & incr) incr >>= 1;
+        if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
+        sym++;
+        if (--count[len] == 0) {
+            if (len == mx) break;
+            len = lens[work[sym]];
+        }
+        if (len > root && (int)(huff & mask) != low) {
+            if (drop == 0) drop = root;
+            next += 1u << curr;
+            curr = len - drop;
+            left = 1 << curr;
+            while (curr + drop < mx) {
+                left -= count[curr + drop];
+                if (left <= 0) break;
+                curr++;
+                left <<= 1;
+            }
+            used += 1u << curr;
+            if (TOO_BIG()) return 1;
+            low = (int)(huff & mask);
+            table[*index + (unsigned)low] = E_PACK(curr, root, next - *index);
+        }
+    }
+    if (huff != 0) {  // incomplete code (only the single 1-bit code case gets here)
+        uint32_t here = E_PACK(64, len - drop, 0);
+        while (huff != 0) {
+            if (drop != 0 && (int)(huff & mask) != low) {
+                drop = 0; len = root; next = *index; curr = root;
+                here = E_PACK(64, len, 0);
+            }
+            table[next + (huff >> drop)] = here;
+            incr = 1u << (len - 1);
+            while (huff & incr) incr >>= 1;
+            if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
+        }
+    }
+    *index += used;
+    *bits = root;
+    return 0;
+#undef TOO_BIG
+}
+
+// ---- bit reader over a global buffer ------------------------------------------------------------
+struct BitReader {
+    const uint8_t* base;
+    uint64_t pos, end, safe_end;
+    uint64_t hold;
+    unsigned bits;
+    __device__ __forceinline__ void refill() {
+        if (bits <= 32) {
+            if (end - pos >= 4) {
+                hold |= (uint64_t)zs_ld32(base, pos, safe_end) << bits;
+                bits += 32;
+                pos += 4;
+            } else {
+                while (pos < end && bits <= 56) {
+                    hold |= (uint64_t)__ldg(base + pos) << bits;
+                    bits += 8;
+                    pos++;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ bool need(unsigned n) {
+        if (bits < n) refill();
+        return bits >= n;
+    }
+    __device__ __forceinline__ unsigned peek(unsigned n) const { return (unsigned)hold & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(unsigned n) { hold >>= n; bits -= n; }
+    __device__ __forceinline__ unsigned take(unsigned n) { unsigned v = peek(n); drop(n); return v; }
+    __device__ __forceinline__ void align_byte() { drop(bits & 7u); }
+    // rewind so that `pos` is the next unread byte and the bit buffer is empty (call when byte aligned)
+    __device__ __forceinline__ void unload() { pos -= bits >> 3; hold = 0; bits = 0; }
+};
+
+__constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// TABLE / LENLENS / CODELENS of inflate() (inflate.ts:673-835); lane 0 only.
+// Returns 0 ok, >0 detail code (data error), -1 truncated input.
+__device__ int read_dynamic_header(BitReader& br, WarpArena& A, bool d64, unsigned& lenbits, unsigned& distbits,
+                                   unsigned& dist_at) {
+    if (!br.need(14)) return -1;
+    unsigned nlen = br.take(5) + 257, ndist = br.take(5) + 1, ncode = br.take(4) + 4;
+    if (nlen > 286 || (!d64 && ndist > 30)) return d64 ? D_TOO_MANY_9 : D_TOO_MANY;
+    unsigned have = 0;
+    while (have < ncode) {
+        if (!br.need(3)) return -1;
+        A.lens[c_bl_order[have++]] = (uint16_t)br.take(3);
+    }
+    while (have < 19) A.lens[c_bl_order[have++]] = 0;
+    unsigned idx = 0, cbits = 7;
+    if (build_table(0, A.lens, 19, A.codes, &cbits, A.work, &idx, d64)) return D_CODE_LENGTHS;
+    have = 0;
+    const unsigned total = nlen + ndist;
+    while (have < total) {
+        br.refill();
+        uint32_t here = A.codes[br.peek(cbits)];
+        if (E_BITS(here) > br.bits) return -1;
+        if (E_OP(here) & 64) return D_CODE_LENGTHS;  // unreachable: the code-length code is complete
+        unsigned v = E_VAL(here);
+        if (v < 16) {
+            br.drop(E_BITS(here));
+            A.lens[have++] = (uint16_t)v;
+        } else {
+            unsigned xb = v == 16 ? 2u : v == 17 ? 3u : 7u;
+            if (E_BITS(here) + xb > br.bits) return -1;
+            br.drop(E_BITS(here));
+            unsigned rep_len = 0, rep;
+            if (v == 16) {
+                if (have == 0) return D_BIT_REPEAT;
+                rep_len = A.lens[have - 1];
+                rep = 3 + br.take(2);
+            } else if (v == 17) {
+                rep = 3 + br.take(3);
+            } else {
+                rep = 11 + br.take(7);
+            }
+            if (have + rep > total) return D_BIT_REPEAT;
+            while (rep--) A.lens[have++] = (uint16_t)rep_len;
+        }
+    }
+    if (A.lens[256] == 0) return D_NO_EOB;
+    idx = 0;
+    lenbits = 9;
+    if (build_table(1, A.lens, nlen, A.codes, &lenbits, A.work, &idx, d64)) return D_LITLEN_SET;
+    dist_at = idx;
+    distbits = 6;
+    if (build_table(2, A.lens + nlen, ndist, A.codes, &distbits, A.work, &idx, d64)) return D_DIST_SET;
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t crc_bitwise(uint32_t crc, unsigned byte) {
+    crc ^= byte;
+    for (int k = 0; k < 8; k++) crc = (crc & 1u) ? (0xedb88320u ^ (crc >> 1)) : (crc >> 1);
+    return crc;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a) {
+    __shared__ WarpArena s_arena[kWarps];
+    __shared__ FixedTables s_fixed;
+    const unsigned lane = zs_lane();
+    const unsigned wid = threadIdx.x >> 5;
+    const bool d64 = a.deflate64 != 0;
+
+    // fixedtables (inflate.ts:218-280): built once per CTA
+    if (wid == 0 && lane == 0) {
+        WarpArena& A = s_arena[0];
+        unsigned sym = 0;
+        while (sym < 144) A.lens[sym++] = 8;
+        while (sym < 256) A.lens[sym++] = 9;
+        while (sym < 280) A.lens[sym++] = 7;
+        while (sym < 288) A.lens[sym++] = 8;
+        unsigned bits = 9, idx = 0;
+        build_table(1, A.lens, 288, s_fixed.len, &bits, A.work, &idx, d64);
+        for (sym = 0; sym < 32; sym++) A.lens[sym] = 5;
+        bits = 5; idx = 0;
+        build_table(2, A.lens, 32, s_fixed.dist, &bits, A.work, &idx, d64);
+    }
+    __syncthreads();
+
+    WarpArena& A = s_arena[wid];
+    const uint64_t in_total = a.d_in_off[a.n];
+    const uint64_t safe_end = (in_total + 7) & ~7ull;
+
+    for (uint64_t sidx = (uint64_t)blockIdx.x * kWarps + wid; sidx < a.n; sidx += (uint64_t)gridDim.x * kWarps) {
+        BitReader br;
+        br.base = a.d_in;
+        br.pos = a.d_in_off[sidx];
+        br.end = a.d_in_off[sidx + 1];
+        br.safe_end = safe_end;
+        br.hold = 0;
+        br.bits = 0;
+        const uint64_t in_start = br.pos;
+        uint8_t* out = a.d_out + a.d_out_off[sidx];
+        const uint64_t cap = a.d_out_off[sidx + 1] - a.d_out_off[sidx];
+        uint64_t op = 0;
+        const uint8_t* dict = nullptr;
+        uint64_t dict_len = 0;
+        if (a.d_dict && a.d_dict_rng) {
+            dict = a.d_dict + a.d_dict_rng[2 * sidx];
+            dict_len = a.d_dict_rng[2 * sidx + 1] - a.d_dict_rng[2 * sidx];
+        }
+        int status = ZS_OK;  // ZS_OK while running
+        int detail = D_NONE;
+        unsigned tflags = 0;  // 1 zlib trailer, 2 gzip trailer
+        uint32_t t_check = 0, t_isize = 0;
+
+        // ---- wrapper header: HEAD..HCRC / DICTID of inflate() (inflate.ts:377-593) ----
+        if (a.wrap) {
+            if (!br.need(16)) {
+                status = ZS_BUF_ERROR;
+            } else {
+                unsigned h = br.peek(16);
+                if ((a.wrap & 2) && h == 0x8b1fu) {
+                    uint32_t hcrc = crc_bitwise(crc_bitwise(0xffffffffu, 0x1f), 0x8b);
+                    br.drop(16);
+                    // FLAGS
+                    if (!br.need(16)) status = ZS_BUF_ERROR;
+                    unsigned flg = 0;
+                    if (status == ZS_OK) {
+                        unsigned w = br.take(16);
+                        flg = w >> 8;
+                        if ((w & 0xff) != 8) { status = ZS_DATA_ERROR; detail = D_METHOD; }
+                        else if (w & 0xe000) { status = ZS_DATA_ERROR; detail = D_HDR_FLAGS; }
+                        hcrc = crc_bitwise(crc_bitwise(hcrc, w & 0xff), w >> 8);
+                    }
+                    // TIME(4) XFL OS
+                    for (int k = 0; k < 6 && status == ZS_OK; k++) {
+                        if (!br.need(8)) status = ZS_BUF_ERROR;
+                        else hcrc = crc_bitwise(hcrc, br.take(8));
+                    }
+                    if (status == ZS_OK && (flg & 4)) {  // FEXTRA
+                        unsigned xlen = 0;
+                        if (!br.need(16)) status = ZS_BUF_ERROR;
+                        else {
+                            xlen = br.take(16);
+                            hcrc = crc_bitwise(crc_bitwise(hcrc, xlen & 0xff), xlen >> 8);
+                        }
+                        while (status == ZS_OK && xlen--) {
+                            if (!br.need(8)) status = ZS_BUF_ERROR;
+                            else hcrc = crc_bitwise(hcrc, br.take(8));
+                        }
+                    }
+                    for (int which = 0; which < 2 && status == ZS_OK; which++) {  // FNAME, FCOMMENT
+                        if (!(flg & (which ? 16 : 8))) continue;
+                        for (;;) {
+                            if (!br.need(8)) { status = ZS_BUF_ERROR; break; }
+                            unsigned c = br.take(8);
+                            hcrc = crc_bitwise(hcrc, c);
+                            if (c == 0) break;
+                        }
+                    }
+                    if (status == ZS_OK && (flg & 2)) {  // FHCRC
+                        if (!br.need(16)) status = ZS_BUF_ERROR;
+                        else if (br.take(16) != ((~hcrc) & 0xffffu)) { status = ZS_DATA_ERROR; detail = D_HDR_CRC; }
+                    }
+                    tflags = 2;
+                } else if (!(a.wrap & 1) || (((h & 0xff) << 8) + (h >> 8)) % 31) {
+                    status = ZS_DATA_ERROR; detail = D_HEADER_CHECK;
+                } else if ((h & 0xf) != 8) {
+                    status = ZS_DATA_ERROR; detail = D_METHOD;
+                } else if (((h >> 4) & 0xf) + 8 > 15) {
+                    status = ZS_DATA_ERROR; detail = D_WINDOW;
+                } else {
+                    br.drop(16);
+                    tflags = 1;
+                    if (h & 0x2000) {  // FDICT: DICTID follows; preset dictionaries for zlib streams
+                        if (!br.need(32)) status = ZS_BUF_ERROR;  // are host-side framing
+                        else { br.drop(32); status = ZS_NEED_DICT; }
+                    }
+                }
+            }
+        }
+
+        // ---- blocks ----
+        bool last = false;
+        while (status == ZS_OK && !last) {
+            if (!br.need(3)) { status = ZS_BUF_ERROR; break; }
+            last = br.take(1) != 0;
+            unsigned type = br.take(2);
+            const uint32_t* lcode;
+            const uint32_t* dcode;
+            unsigned lenbits, distbits;
+            if (type == 0) {
+                // STORED / COPY (inflate.ts:631-672)
+                br.align_byte();
+                if (!br.need(32)) { status = ZS_BUF_ERROR; break; }
+                unsigned w = (unsigned)br.hold;
+                if ((w & 0xffffu) != ((w >> 16) ^ 0xffffu)) { status = ZS_DATA_ERROR; detail = D_STORED_LEN; break; }
+                br.drop(32);
+                br.unload();
+                uint64_t n = w & 0xffffu, avail_in = br.end - br.pos, avail_out = cap - op;
+                uint64_t c = n < avail_in ? n : avail_in;
+                if (c > avail_out) c = avail_out;
+                for (uint64_t j = lane; j < c; j += 32) out[op + j] = __ldg(a.d_in + br.pos + j);
+                br.pos += c;
+                op += c;
+                if (c < n) { status = ZS_BUF_ERROR; break; }
+                continue;
+            } else if (type == 1) {
+                lcode = s_fixed.len; dcode = s_fixed.dist; lenbits = 9; distbits = 5;
+            } else if (type == 2) {
+                int rc = 0;
+                unsigned dist_at = 0;
+                lenbits = distbits = 0;
+                if (lane == 0) rc = read_dynamic_header(br, A, d64, lenbits, distbits, dist_at);
+                __syncwarp();
+                rc = __shfl_sync(ZS_FULL_MASK, rc, 0);
+                br.pos = __shfl_sync(ZS_FULL_MASK, br.pos, 0);
+                br.hold = __shfl_sync(ZS_FULL_MASK, br.hold, 0);
+                br.bits = __shfl_sync(ZS_FULL_MASK, br.bits, 0);
+                lenbits = __shfl_sync(ZS_FULL_MASK, lenbits, 0);
+                distbits = __shfl_sync(ZS_FULL_MASK, distbits, 0);
+                dist_at = __shfl_sync(ZS_FULL_MASK, dist_at, 0);
+                if (rc < 0) { status = ZS_BUF_ERROR; break; }
+                if (rc > 0) { status = ZS_DATA_ERROR; detail = rc; break; }
+                lcode = A.codes; dcode = A.codes + dist_at;
+            } else {
+                status = ZS_DATA_ERROR; detail = D_BLOCK_TYPE; break;
+            }
+
+            // LEN..MATCH / LIT (inflate.ts:840-1005, inffast.ts:31-214), one symbol per trip
+            const unsigned lmask = (1u << lenbits) - 1u, dmask = (1u << distbits) - 1u;
+            for (;;) {
+                br.refill();
+                uint32_t here = lcode[(unsigned)br.hold & lmask];
+                unsigned used = E_BITS(here);
+                if (E_OP(here) && (E_OP(here) & 0xf0u) == 0) {  // second-level table
+                    uint32_t first = here;
+                    here = lcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                    used = E_BITS(first) + E_BITS(here);
+                }
+                if (used > br.bits) { status = ZS_BUF_ERROR; break; }
+                unsigned lop = E_OP(here);
+                if (lop == 0) {  // literal
+                    if (op >= cap) { status = ZS_BUF_ERROR; break; }
+                    br.drop(used);
+                    if (lane == 0) out[op] = (uint8_t)E_VAL(here);
+                    op++;
+                    continue;
+                }
+                if (lop & 32) { br.drop(used); break; }  // end of block
+                if (lop & 64) { status = ZS_DATA_ERROR; detail = D_LITLEN_CODE; break; }
+                // length
+                unsigned xb = lop & (d64 ? 31u : 15u);
+                if (used + xb > br.bits) { status = ZS_BUF_ERROR; break; }
+                br.drop(used);
+                unsigned len = E_VAL(here) + br.take(xb);
+                // distance
+                br.refill();
+                here = dcode[(unsigned)br.hold & dmask];
+                used = E_BITS(here);
+                if ((E_OP(here) & 0xf0u) == 0) {
+                    uint32_t first = here;
+                    here = dcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                    used = E_BITS(first) + E_BITS(here);
+                }
+                if (used > br.bits) { status = ZS_BUF_ERROR; break; }
+                if (E_OP(here) & 64) { status = ZS_DATA_ERROR; detail = D_DIST_CODE; break; }
+                xb = E_OP(here) & 15u;
+                if (used + xb > br.bits) { status = ZS_BUF_ERROR; break; }
+                br.drop(used);
+                uint64_t dist = E_VAL(here) + br.take(xb);
+                if (op >= cap) { status = ZS_BUF_ERROR; break; }  // MATCH with left == 0 (inflate.ts:944)
+                if (dist > op + dict_len) { status = ZS_DATA_ERROR; detail = D_TOO_FAR; break; }
+                // copy: all lanes, periodic source so that overlapping copies need no ordering
+                uint64_t c = len;
+                if (c > cap - op) c = cap - op;
+                __syncwarp();
+                for (uint64_t j = lane; j < c; j += 32) {
+                    uint64_t k = (dist >= c) ? j : (j % dist);
+                    int64_t src = (int64_t)op - (int64_t)dist + (int64_t)k;
+                    out[op + j] = src >= 0 ? out[src] : __ldg(dict + dict_len + src);
+                }
+                __syncwarp();
+                op += c;
+                if (c < len) { status = ZS_BUF_ERROR; break; }
+            }
+        }
+
+        // ---- trailer: CHECK / LENGTH (inflate.ts:1006-1037) ----
+        if (status == ZS_OK) {
+            br.align_byte();
+            if (tflags) {
+                if (!br.need(32)) status = ZS_BUF_ERROR;
+                else {
+                    uint32_t w = (uint32_t)br.hold;
+                    br.drop(32);
+                    t_check = tflags == 1 ? __byte_perm(w, 0, 0x0123) : w;
+                }
+                if (status == ZS_OK && tflags == 2) {
+                    if (!br.need(32)) status = ZS_BUF_ERROR;
+                    else { t_isize = (uint32_t)br.hold; br.drop(32); }
+                }
+            }
+            if (status == ZS_OK) status = ZS_STREAM_END;
+        }
+        if (lane == 0) {
+            a.d_out_len[sidx] = op;
+            // a Z_BUF_ERROR with output space left means the input ran dry: the reference has
+            // pulled every available byte by then (PULLBYTE, inflate.ts:1147-1158)
+            uint64_t used_in = (status == ZS_BUF_ERROR && op < cap) ? br.end - in_start
+                                                                    : br.pos - (br.bits >> 3) - in_start;
+            if (a.d_in_used) a.d_in_used[sidx] = used_in;
+            a.d_status[sidx] = status;
+            a.d_detail[sidx] = detail;
+            a.d_trailer[2 * sidx] = t_check;
+            a.d_trailer[2 * sidx + 1] = t_isize;
+            a.d_flags[sidx] = (status == ZS_STREAM_END) ? tflags : 0u;
+        }
+        __syncwarp();
+    }
+}
+
+// Compare the checksum of the produced output with the stored trailer ("incorrect data check",
+// "incorrect length check", inflate.ts:1012-1033) and publish the per-stream check value.
+__global__ void inflate_verify_kernel(uint32_t n, const uint32_t* __restrict__ adler, const uint32_t* __restrict__ crc,
+                                      const uint32_t* __restrict__ trailer, const uint32_t* __restrict__ flags,
+                                      const uint64_t* __restrict__ out_len, uint32_t* __restrict__ checks,
+                                      int32_t* __restrict__ status, int32_t* __restrict__ detail) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned f = flags[i];
+    uint32_t ck = (f == 0 && crc) ? crc[i] : 0u;  // raw streams report the crc32 of what they produced
+    if (f == 1) {
+        ck = adler[i];
+        if (ck != trailer[2 * i]) { status[i] = ZS_DATA_ERROR; detail[i] = D_DATA_CHECK; }
+    } else if (f == 2) {
+        ck = crc[i];
+        if (ck != trailer[2 * i]) { status[i] = ZS_DATA_ERROR; detail[i] = D_DATA_CHECK; }
+        else if ((uint32_t)out_len[i] != trailer[2 * i + 1]) { status[i] = ZS_DATA_ERROR; detail[i] = D_LENGTH_CHECK; }
+    }
+    if (checks) checks[i] = ck;
+}
+
+}  // namespace
+
+int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a) {
+    if (a.n == 0) return ZS_OK;
+    unsigned ctas = (a.n + kWarps - 1) / kWarps;
+    unsigned cap = (unsigned)ctx->sm_count * 8u;
+    if (ctas > cap) ctas = cap;
+    inflate_kernel<<<ctas, kWarps * 32, 0, ctx->stream>>>(a);
+    ZS_LAUNCH_CHECK(ctx, "inflate_kernel");
+    return ZS_OK;
+}
+
+int zs_launch_inflate_verify(zs_ctx* ctx, uint32_t n, const uint32_t* d_adler, const uint32_t* d_crc,
+                             const uint32_t* d_trailer, const uint32_t* d_flags, const uint64_t* d_out_len,
+                             uint32_t* d_checks, int32_t* d_status, int32_t* d_detail) {
+    if (n == 0) return ZS_OK;
+    inflate_verify_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_adler, d_crc, d_trailer, d_flags, d_out_len,
+                                                                    d_checks, d_status, d_detail);
+    ZS_LAUNCH_CHECK(ctx, "inflate_verify_kernel");
+    return ZS_OK;
+}
+
+extern "C" const char* zs_inflate_message(int detail) {
+    static const char* const msgs[] = {
+        "",
+        "incorrect header check",
+        "unknown compression method",
+        "invalid window size",
+        "unknown header flags set",
+        "header crc mismatch",
+        "invalid block type",
+        "invalid stored block lengths",
+        "too many length or distance symbols",
+        "too many length",
+        "invalid code lengths set",
+        "invalid bit length repeat",
+        "invalid code -- missing end-of-block",
+        "invalid literal/lengths set",
+        "invalid distances set",
+        "invalid literal/length code",
+        "invalid distance code",
+        "invalid distance too far back",
+        "incorrect data check",
+        "incorrect length check",
+    };
+    if (detail < 0 || detail > D_LENGTH_CHECK) return "";
+    return msgs[detail];
+}
