@@ -1,0 +1,150 @@
+"""GPU parity: K6/K7 batch inflate against the oracle restatement of inflate.ts / inftrees.ts /
+inffast.ts (incl. deflate64) and against the reference's known-answer vectors -- bit-exact output,
+total_in / total_out, return code and message."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import make_mixed, make_text, pkg, rand_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(streams, wbits, caps, dicts=None):
+    return pkg("batch").inflate_batch(streams, wbits, caps, dicts)
+
+
+def _same_as_oracle(oracle, streams, wbits, caps, dicts=None, check_used=True):
+    r = _run(streams, wbits, caps, dicts)
+    for i, s in enumerate(streams):
+        ret, out, used, check = oracle.inflate(s, wbits, int(caps[i]), dicts[i] if dicts else None)
+        assert int(r.status[i]) == ret, (i, int(r.status[i]), ret, r.message(i))
+        assert r.output(i) == out, (i, len(r.output(i)), len(out))
+        if check_used and ret in (oracle.Z_STREAM_END, oracle.Z_DATA_ERROR):
+            pass
+        if ret == oracle.Z_STREAM_END:
+            assert int(r.in_used[i]) == used, (i, int(r.in_used[i]), used)
+    return r
+
+
+def test_kats(gpu_ctx, oracle, kat):
+    for v in kat["inflate"]:
+        data = bytes.fromhex(v["in_hex"])
+        r = _run([data], v["window_bits"], [1 << 17])
+        ret = int(r.status[0])
+        if "ret" in v:
+            assert ret == v["ret"], v["ref"]
+        if "ret_le" in v:
+            assert ret <= v["ret_le"], v["ref"]
+        if "ret_not" in v:
+            assert ret not in v["ret_not"], v["ref"]
+        if "out_hex" in v:
+            assert r.output(0) == bytes.fromhex(v["out_hex"]), v["ref"]
+        if "out_len" in v:
+            assert r.output(0) == bytes([v["out_byte"]]) * v["out_len"], v["ref"]
+
+
+def test_deflate64_fixtures(gpu_ctx, oracle, fixtures64):
+    streams = [f["data"] for f in fixtures64]
+    caps = [f["out_len"] + 100 for f in fixtures64]
+    r = _same_as_oracle(oracle, streams, -16, caps)
+    for i, f in enumerate(fixtures64):
+        out = r.output(i)
+        assert int(r.status[i]) == 1 and len(out) == f["out_len"], f["name"]
+        assert zlib.crc32(out) == f["crc32"] and zlib.adler32(out) == f["adler32"], f["name"]
+        assert int(r.checks[i]) == f["crc32"], f["name"]          # raw streams report crc32(out)
+        assert int(r.in_used[i]) == f["length"]
+
+
+@pytest.mark.parametrize("wbits", [15, -15, 31, 47])
+def test_zlib_streams_all_levels(gpu_ctx, oracle, wbits):
+    streams, datas = [], []
+    enc_wbits = 31 if wbits == 47 else wbits
+    for level in (0, 1, 6, 9):
+        for data in (make_text(120000, level), make_mixed(90000, level), rand_bytes(70000, level), b"", b"a",
+                     bytes(100000), bytes(j % 251 for j in range(60000))):
+            co = zlib.compressobj(level, 8, enc_wbits)
+            streams.append(co.compress(data) + co.flush())
+            datas.append(data)
+    caps = [len(d) + 16 for d in datas]
+    r = _same_as_oracle(oracle, streams, wbits, caps)
+    for i, d in enumerate(datas):
+        assert int(r.status[i]) == 1 and r.output(i) == d
+        if wbits == 15:
+            assert int(r.checks[i]) == zlib.adler32(d)
+        if wbits in (31, 47):
+            assert int(r.checks[i]) == zlib.crc32(d)
+
+
+def test_many_small_gzip_records(gpu_ctx, oracle):
+    # config 4 shape: independent 4 KiB gzip records, ~5 % stored (random) records, crc32 verify
+    rnd = random.Random(4)
+    text = make_text(4096 * 400, 11)
+    streams, datas = [], []
+    for i in range(400):
+        d = rnd.randbytes(4096) if rnd.random() < 0.05 else text[i * 4096: (i + 1) * 4096]
+        co = zlib.compressobj(6, 8, 31)
+        streams.append(co.compress(d) + co.flush())
+        datas.append(d)
+    r = _run(streams, 31, [4096] * 400)
+    assert (r.status == 1).all()
+    for i, d in enumerate(datas):
+        assert r.output(i) == d and int(r.checks[i]) == zlib.crc32(d) and int(r.in_used[i]) == len(streams[i])
+
+
+def test_errors_match_oracle(gpu_ctx, oracle):
+    data = make_text(50000, 5)
+    z = zlib.compress(data, 6)
+    g = zlib.compressobj(6, 8, 31)
+    gz = g.compress(data) + g.flush()
+    streams, caps, wb = [], [], 15
+    bad = bytearray(z); bad[-1] ^= 0xFF
+    streams += [z[:-5], bytes(bad), z, z[:100], b"\x78", b"\x79\x9c\x03\x00", b"\x78\x9c\x07\x00"]
+    caps += [60000, 60000, 1000, 60000, 100, 100, 100]
+    r = _same_as_oracle(oracle, streams, wb, caps)
+    assert int(r.status[1]) == -3 and r.message(1) == "incorrect data check"
+    assert int(r.status[5]) == -3 and r.message(5) == "incorrect header check"
+    assert int(r.status[6]) == -3 and r.message(6) == "invalid block type"
+    badg = bytearray(gz); badg[-2] ^= 1
+    r = _same_as_oracle(oracle, [gz, bytes(badg), gz[:-1]], 31, [60000, 60000, 60000])
+    assert int(r.status[0]) == 1 and int(r.status[1]) == -3 and r.message(1) == "incorrect length check"
+    assert int(r.status[2]) == -5
+    # bit flips anywhere in the stream: same verdict, same output prefix as the oracle
+    rnd = random.Random(9)
+    streams = []
+    for _ in range(300):
+        junk = bytearray(z[:600])
+        junk[rnd.randrange(2, 600)] ^= 1 << rnd.randrange(8)
+        streams.append(bytes(junk))
+    r = _same_as_oracle(oracle, streams, 15, [60000] * len(streams))
+    msgs = {r.message(i) for i in range(len(streams)) if int(r.status[i]) == -3}
+    assert msgs  # at least some data errors, all with reference messages
+    # deflate64-specific header rule (coverage-too-many-len.spec.ts:28-46)
+    def hdr(nlen, ndist):
+        v = 0b101 | ((nlen - 257) << 3) | ((ndist - 1) << 8)
+        return v.to_bytes(3, "little") + bytes(8)
+    r = _same_as_oracle(oracle, [hdr(257, 31), hdr(287, 1)], -15, [64, 64])
+    assert int(r.status[0]) == -3 and r.message(0) == "too many length or distance symbols"
+    r = _same_as_oracle(oracle, [hdr(257, 31), hdr(287, 1)], -16, [64, 64])
+    assert r.message(0) != "too many length" and r.message(1) == "too many length"
+
+
+def test_preset_dictionary_raw(gpu_ctx, oracle):
+    d = make_text(200000, 3)
+    dic, body = d[:40000], d[40000:140000]
+    co = zlib.compressobj(6, 8, -15, 8, 0, dic[-32768:])
+    z = co.compress(body) + co.flush()
+    r = _same_as_oracle(oracle, [z, z], -15, [len(body), len(body)], [dic[-32768:], None])
+    assert int(r.status[0]) == 1 and r.output(0) == body
+    assert int(r.status[1]) == -3 and r.message(1) == "invalid distance too far back"
+
+
+def test_window_wrap_and_long_matches(gpu_ctx, oracle):
+    # test-inffast-window-wrap.ts: 64 KiB+ of a 32-byte pattern; plus runs that use length 258
+    pat = bytes(range(32)) * 4096
+    runs = b"".join(bytes([i]) * 1000 for i in range(200))
+    streams = [zlib.compress(pat, 9), zlib.compress(runs, 9), zlib.compress(pat + runs, 1)]
+    r = _same_as_oracle(oracle, streams, 15, [len(pat), len(runs), len(pat) + len(runs)])
+    assert (r.status == 1).all()

@@ -29,7 +29,9 @@ def default_context(device: int | None = None) -> Context:
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     ctx = _contexts.get(key)
     if ctx is None:
-        ctx = Context(device, key[1])
+        # torch's default stream has handle 0; the C ABI reads NULL as "make your own stream", so
+        # name the legacy default stream explicitly (cudaStreamLegacy == (cudaStream_t)1)
+        ctx = Context(device, key[1] if key[1] else 1)
         _contexts[key] = ctx
     return ctx
 
