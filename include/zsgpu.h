@@ -82,6 +82,11 @@ ZS_API const char* zs_last_error(const zs_ctx* ctx);
 ZS_API int zs_ctx_synchronize(zs_ctx* ctx);
 /* number of kernel launches issued through this context so far */
 ZS_API uint64_t zs_ctx_launch_count(const zs_ctx* ctx);
+/* Per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on the
+ * context's stream.  zs_ctx_profile_read synchronises, writes one line "name launches total_ms" per
+ * kernel into buf and clears the records. */
+ZS_API int zs_ctx_profile(zs_ctx* ctx, int enable);
+ZS_API int zs_ctx_profile_read(zs_ctx* ctx, char* buf, uint64_t cap);
 
 /* deflateBound, src/mod/deflate/deflate.ts:615-674 (windowBits 15, memLevel 8) */
 ZS_API uint64_t zs_deflate_bound(uint64_t source_len, int wrap);

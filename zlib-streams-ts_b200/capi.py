@@ -49,6 +49,8 @@ _PROTOTYPES = {
     "zs_last_error": (C.c_char_p, [C.c_void_p]),
     "zs_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "zs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "zs_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "zs_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "zs_deflate_bound": (C.c_uint64, [C.c_uint64, C.c_int]),
     "zs_deflate_batch_bound": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "zs_crc32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
@@ -144,3 +146,16 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.zs_ctx_launch_count(self._h))
+
+    def profile(self, enable: bool):
+        self.check(self._lib.zs_ctx_profile(self._h, 1 if enable else 0), "zs_ctx_profile")
+
+    def profile_read(self) -> dict:
+        """{kernel name: (launches, total device ms)} since the last read (synchronises)."""
+        buf = C.create_string_buffer(1 << 14)
+        self.check(self._lib.zs_ctx_profile_read(self._h, buf, len(buf)), "zs_ctx_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out

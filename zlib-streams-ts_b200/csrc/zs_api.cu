@@ -43,6 +43,36 @@ void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
     return s.p;
 }
 
+// ---- per-kernel timing -------------------------------------------------------------------------------
+struct zs_prof_rec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct zs_profile {
+    std::vector<zs_prof_rec> recs;      // one per launch since the last read
+    std::vector<cudaEvent_t> pool;      // recycled events
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+void zs_prof_begin(zs_ctx* ctx, const char* name) {
+    if (!ctx->prof_on) return;
+    zs_profile* pr = (zs_profile*)ctx->prof;
+    zs_prof_rec r = {name, pr->get(), pr->get()};
+    cudaEventRecord(r.a, ctx->stream);
+    pr->recs.push_back(r);
+}
+
+void zs_prof_end(zs_ctx* ctx) {
+    if (!ctx->prof_on) return;
+    zs_profile* pr = (zs_profile*)ctx->prof;
+    cudaEventRecord(pr->recs.back().b, ctx->stream);
+}
+
 int zs_set_cuda_error(zs_ctx* ctx, cudaError_t e, const char* where) {
     snprintf(ctx->err, sizeof(ctx->err), "CUDA error at %s: %s", where, cudaGetErrorString(e));
     return ZS_E_CUDA;
@@ -103,8 +133,49 @@ void zs_ctx_destroy(zs_ctx* ctx) {
     for (auto& s : ctx->scr)
         if (s.p) cudaFree(s.p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->prof) {
+        zs_profile* pr = (zs_profile*)ctx->prof;
+        for (auto& r : pr->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : pr->pool) cudaEventDestroy(e);
+        delete pr;
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int zs_ctx_profile(zs_ctx* ctx, int enable) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (!ctx->prof) ctx->prof = new zs_profile();
+    ctx->prof_on = enable != 0;
+    return ZS_OK;
+}
+
+int zs_ctx_profile_read(zs_ctx* ctx, char* buf, uint64_t cap) {
+    if (!ctx || !buf || cap == 0) return ZS_STREAM_ERROR;
+    buf[0] = 0;
+    zs_profile* pr = (zs_profile*)ctx->prof;
+    if (!pr) return ZS_OK;
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char* name; double ms; uint64_t n; };
+    std::vector<Agg> agg;
+    for (auto& r : pr->recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (auto& g : agg)
+            if (!strcmp(g.name, r.name)) { g.ms += ms; g.n++; found = true; break; }
+        if (!found) agg.push_back({r.name, (double)ms, 1});
+        pr->pool.push_back(r.a);
+        pr->pool.push_back(r.b);
+    }
+    pr->recs.clear();
+    uint64_t pos = 0;
+    for (auto& g : agg) {
+        int w = snprintf(buf + pos, (size_t)(cap - pos), "%s %llu %.6f\n", g.name, (unsigned long long)g.n, g.ms);
+        if (w < 0 || pos + (uint64_t)w >= cap) break;
+        pos += (uint64_t)w;
+    }
+    return ZS_OK;
 }
 
 const char* zs_last_error(const zs_ctx* ctx) { return ctx ? ctx->err : "no context"; }
@@ -215,8 +286,7 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     if (d_in_off) {
         p.d_in_off = d_in_off;
     } else {
-        make_chunk_offsets_kernel<<<(n_chunks + 1 + 255) / 256, 256, 0, ctx->stream>>>(off, in_len, chunk_size, n_chunks);
-        ZS_LAUNCH_CHECK(ctx, "make_chunk_offsets_kernel");
+        ZS_KERNEL(ctx, "make_chunk_offsets_kernel", make_chunk_offsets_kernel<<<(n_chunks + 1 + 255) / 256, 256, 0, ctx->stream>>>(off, in_len, chunk_size, n_chunks));
         p.d_in_off = off;
     }
     p.d_out = d_out; p.out_cap = out_cap;

@@ -262,8 +262,7 @@ int zs_launch_checksum_segments(zs_ctx* ctx, int kind, const uint8_t* d_buf, con
     if (kind)
         checksum_segments_kernel<1><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out);
     else
-        checksum_segments_kernel<0><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out);
-    ZS_LAUNCH_CHECK(ctx, "checksum_segments_kernel");
+        ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<0><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
     return ZS_OK;
 }
 
@@ -274,8 +273,7 @@ int zs_launch_checksum_fold(zs_ctx* ctx, int kind, const uint32_t* d_part, const
     if (kind)
         checksum_fold_kernel<1><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result);
     else
-        checksum_fold_kernel<0><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result);
-    ZS_LAUNCH_CHECK(ctx, "checksum_fold_kernel");
+        ZS_KERNEL(ctx, "checksum_fold_kernel", checksum_fold_kernel<0><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result));
     return ZS_OK;
 }
 
@@ -293,8 +291,7 @@ int zs_launch_checksum_whole(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64
     uint64_t* d_off = (uint64_t*)zs_scratch_get(ctx, 0, (size_t)(n + 1) * sizeof(uint64_t));
     uint32_t* d_part = (uint32_t*)zs_scratch_get(ctx, 1, (size_t)n * sizeof(uint32_t));
     if (!d_off || !d_part) return ZS_MEM_ERROR;
-    make_offsets_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_off, len, piece, n);
-    ZS_LAUNCH_CHECK(ctx, "make_offsets_kernel");
+    ZS_KERNEL(ctx, "make_offsets_kernel", make_offsets_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_off, len, piece, n));
     int rc = zs_launch_checksum_segments(ctx, kind, d_buf, d_off, nullptr, n, d_part);
     if (rc != ZS_OK) return rc;
     return zs_launch_checksum_fold(ctx, kind, d_part, d_off, n, init, d_result);

@@ -28,6 +28,9 @@ struct zs_ctx {
     // last inflate details (device ptr into scratch) for zs_inflate_last_details
     int32_t* d_last_detail = nullptr;
     uint32_t last_detail_n = 0;
+    // profiling (zs_ctx_profile)
+    bool prof_on = false;
+    void* prof = nullptr;  // zs_profile*, zs_api.cu
 };
 
 void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes);  // nullptr on failure (err set)
@@ -42,6 +45,17 @@ int zs_set_cuda_error(zs_ctx* ctx, cudaError_t e, const char* where);
         (ctx)->launches++;                                                       \
         cudaError_t _e = cudaGetLastError();                                     \
         if (_e != cudaSuccess) return zs_set_cuda_error((ctx), _e, name);        \
+    } while (0)
+
+// per-kernel CUDA-event timing (zs_ctx_profile): begin/end bracket one launch on ctx->stream
+void zs_prof_begin(zs_ctx* ctx, const char* name);
+void zs_prof_end(zs_ctx* ctx);
+#define ZS_KERNEL(ctx, name, ...)        \
+    do {                                 \
+        zs_prof_begin((ctx), name);      \
+        __VA_ARGS__;                     \
+        zs_prof_end((ctx));              \
+        ZS_LAUNCH_CHECK((ctx), name);    \
     } while (0)
 
 // ---- device helpers --------------------------------------------------------------------------------

@@ -215,6 +215,41 @@ __device__ void walk_tree(const uint16_t* len, int max_code, bool count, uint16_
     }
 }
 
+// K3: symbol histogram of every block (_tr_tally_lit/_tr_tally_dist, deflate/utils.ts:55-81): one CTA
+// per block, shared-memory atomics, 286 literal/length + 30 distance counters.
+struct HistArgs {
+    uint32_t n_chunks, max_bpc;
+    const uint64_t* in_off;
+    const uint32_t* chunk_nblk;
+    const uint32_t* blk_desc;
+    const uint32_t* sym;
+    uint32_t* blk_freq;
+};
+
+__global__ void __launch_bounds__(256) histogram_kernel(HistArgs a) {
+    const uint64_t gid = blockIdx.x;
+    const uint32_t chunk = (uint32_t)(gid / a.max_bpc), j = (uint32_t)(gid % a.max_bpc);
+    if (j >= a.chunk_nblk[chunk]) return;
+    __shared__ uint32_t h[320];
+    for (unsigned i = threadIdx.x; i < 320; i += 256) h[i] = 0;
+    __syncthreads();
+    const uint32_t sym0 = a.blk_desc[gid * 4 + 0], nsym = a.blk_desc[gid * 4 + 1];
+    const uint32_t* sym = a.sym + a.in_off[chunk] + sym0;
+    for (uint32_t i = threadIdx.x; i < nsym; i += 256) {
+        const uint32_t s = sym[i];
+        const unsigned dist = s >> 16, lc = s & 0xffffu;
+        if (dist == 0) {
+            atomicAdd(&h[lc], 1u);
+        } else {
+            atomicAdd(&h[257u + zs_len_code(lc - 3u)], 1u);
+            atomicAdd(&h[288u + zs_dist_code(dist - 1u)], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t* f = a.blk_freq + gid * 320;
+    for (unsigned i = threadIdx.x; i < 320; i += 256) f[i] = h[i];
+}
+
 struct HuffArgs {
     uint32_t n_chunks, max_bpc;
     const uint32_t* chunk_nblk;
@@ -719,9 +754,10 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
         snprintf(ctx->err, sizeof(ctx->err), "deflate: too many block slots");
         return ZS_STREAM_ERROR;
     }
+    HistArgs hs = {p.n_chunks, p.max_bpc, p.d_in_off, p.d_chunk_nblk, p.d_blk_desc, p.d_sym, p.d_blk_freq};
+    ZS_KERNEL(ctx, "histogram_kernel", histogram_kernel<<<(unsigned)nblk_slots, 256, 0, ctx->stream>>>(hs));
     HuffArgs h = {p.n_chunks, p.max_bpc, p.d_chunk_nblk, p.d_blk_desc, p.d_blk_freq, p.d_blk_code, p.d_blk_hdr, p.d_blk_bits};
-    huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h);
-    ZS_LAUNCH_CHECK(ctx, "huff_build_kernel");
+    ZS_KERNEL(ctx, "huff_build_kernel", huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h));
 
     LayoutArgs l;
     l.n_chunks = p.n_chunks; l.max_bpc = p.max_bpc; l.wrap = p.wrap; l.mode = p.mode; l.flags = p.flags;
@@ -729,15 +765,11 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     l.chunk_pr = p.d_chunk_pr; l.out_off = p.d_out_off; l.out_bits = p.d_out_bits; l.out_cap = p.out_cap;
     l.result = p.d_result; l.error = p.d_error; l.check_total = p.d_check_total;
     const unsigned cgrid = (p.n_chunks + 127) / 128;
-    layout_chunks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l);
-    ZS_LAUNCH_CHECK(ctx, "layout_chunks_kernel");
-    layout_scan_kernel<<<1, 32, 0, ctx->stream>>>(l);
-    ZS_LAUNCH_CHECK(ctx, "layout_scan_kernel");
-    layout_blocks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l);
-    ZS_LAUNCH_CHECK(ctx, "layout_blocks_kernel");
+    ZS_KERNEL(ctx, "layout_chunks_kernel", layout_chunks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l));
+    ZS_KERNEL(ctx, "layout_scan_kernel", layout_scan_kernel<<<1, 32, 0, ctx->stream>>>(l));
+    ZS_KERNEL(ctx, "layout_blocks_kernel", layout_blocks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l));
 
-    zero_output_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p.d_out, p.d_result, p.d_error, p.out_cap);
-    ZS_LAUNCH_CHECK(ctx, "zero_output_kernel");
+    ZS_KERNEL(ctx, "zero_output_kernel", zero_output_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p.d_out, p.d_result, p.d_error, p.out_cap));
 
     EncodeArgs e;
     e.n_chunks = p.n_chunks; e.max_bpc = p.max_bpc; e.wrap = p.wrap; e.mode = p.mode; e.flags = p.flags;
@@ -745,12 +777,9 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     e.blk_code = p.d_blk_code; e.blk_hdr = p.d_blk_hdr; e.blk_abs = p.d_blk_bits; e.out_off = p.d_out_off;
     e.out_bits = p.d_out_bits; e.checks = p.d_checks; e.check_total = p.d_check_total; e.out = p.d_out;
     e.result = p.d_result; e.error = p.d_error; e.level = p.level;
-    encode_kernel<<<(unsigned)nblk_slots, kEncThreads, 0, ctx->stream>>>(e);
-    ZS_LAUNCH_CHECK(ctx, "encode_kernel");
-    frame_kernel<<<cgrid, 128, 0, ctx->stream>>>(e);
-    ZS_LAUNCH_CHECK(ctx, "frame_kernel");
-    count_blocks_kernel<<<1, 256, 0, ctx->stream>>>(p.d_chunk_nblk, p.n_chunks, p.d_result, p.d_check_total);
-    ZS_LAUNCH_CHECK(ctx, "count_blocks_kernel");
+    ZS_KERNEL(ctx, "encode_kernel", encode_kernel<<<(unsigned)nblk_slots, kEncThreads, 0, ctx->stream>>>(e));
+    ZS_KERNEL(ctx, "frame_kernel", frame_kernel<<<cgrid, 128, 0, ctx->stream>>>(e));
+    ZS_KERNEL(ctx, "count_blocks_kernel", count_blocks_kernel<<<1, 256, 0, ctx->stream>>>(p.d_chunk_nblk, p.n_chunks, p.d_result, p.d_check_total));
     return ZS_OK;
 }
 
@@ -763,7 +792,6 @@ int zs_launch_bit_concat(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, cons
     uint64_t blocks = (n_words + 1 + 255) / 256;
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    bit_concat_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst32, off, d_src, n_bits);
-    ZS_LAUNCH_CHECK(ctx, "bit_concat_kernel");
+    ZS_KERNEL(ctx, "bit_concat_kernel", bit_concat_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst32, off, d_src, n_bits));
     return ZS_OK;
 }

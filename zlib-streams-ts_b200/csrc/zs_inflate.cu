@@ -569,8 +569,7 @@ int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a) {
     unsigned ctas = (a.n + kWarps - 1) / kWarps;
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;
-    inflate_kernel<<<ctas, kWarps * 32, 0, ctx->stream>>>(a);
-    ZS_LAUNCH_CHECK(ctx, "inflate_kernel");
+    ZS_KERNEL(ctx, "inflate_kernel", inflate_kernel<<<ctas, kWarps * 32, 0, ctx->stream>>>(a));
     return ZS_OK;
 }
 
@@ -578,9 +577,8 @@ int zs_launch_inflate_verify(zs_ctx* ctx, uint32_t n, const uint32_t* d_adler, c
                              const uint32_t* d_trailer, const uint32_t* d_flags, const uint64_t* d_out_len,
                              uint32_t* d_checks, int32_t* d_status, int32_t* d_detail) {
     if (n == 0) return ZS_OK;
-    inflate_verify_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_adler, d_crc, d_trailer, d_flags, d_out_len,
-                                                                    d_checks, d_status, d_detail);
-    ZS_LAUNCH_CHECK(ctx, "inflate_verify_kernel");
+    ZS_KERNEL(ctx, "inflate_verify_kernel", inflate_verify_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_adler, d_crc, d_trailer, d_flags, d_out_len,
+                                                                    d_checks, d_status, d_detail));
     return ZS_OK;
 }
 
