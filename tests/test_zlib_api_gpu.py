@@ -1,0 +1,239 @@
+"""GPU: the reference-facing API (createDeflateStream/deflateInit/deflate/deflateEnd, inflateInit2_/
+inflate/inflateEnd, CompressionStream/DecompressionStream) -- the parity tests read like the
+reference's own (test/deflate/test-main-roundtrip.ts, test-small-buffers.ts,
+test-avail-out-guard.ts, test-errors.ts, test/inflate/test-multistream.ts,
+test/round-trip/test-streams-roundtrip.ts, test-streams-empty-input.ts)."""
+import zlib
+
+import pytest
+
+from conftest import make_text, pkg, rand_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _Z():
+    return pkg("zlib_api")
+
+
+def chunked_deflate(data, level, wbits, in_chunk, out_chunk):
+    Z = _Z()
+    s = Z.createDeflateStream()
+    assert Z.deflateInit2_(s, level, Z.Z_DEFLATED, wbits, 8, 0) == Z.Z_OK
+    out = bytearray()
+    pos = 0
+    while pos < len(data):
+        piece = data[pos: pos + in_chunk]
+        s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+        while s.avail_in > 0:
+            buf = bytearray(out_chunk)
+            s.next_out, s.next_out_index, s.avail_out = buf, 0, out_chunk
+            assert Z.deflate(s, Z.Z_NO_FLUSH) == Z.Z_OK
+            out += buf[: s.next_out_index]
+        pos += len(piece)
+    while True:
+        buf = bytearray(out_chunk)
+        s.next_in, s.next_in_index, s.avail_in = b"", 0, 0
+        s.next_out, s.next_out_index, s.avail_out = buf, 0, out_chunk
+        r = Z.deflate(s, Z.Z_FINISH)
+        out += buf[: s.next_out_index]
+        if r == Z.Z_STREAM_END:
+            break
+        assert r == Z.Z_OK
+    assert s.total_in == len(data) and s.total_out == len(out)
+    adler = s._adler
+    assert Z.deflateEnd(s) == Z.Z_OK
+    return bytes(out), adler
+
+
+def chunked_inflate(stream, wbits, in_chunk, out_chunk):
+    Z = _Z()
+    s = Z.createInflateStream()
+    assert Z.inflateInit2_(s, wbits) == Z.Z_OK
+    out = bytearray()
+    pos = 0
+    r = Z.Z_OK
+    while r != Z.Z_STREAM_END:
+        piece = stream[pos: pos + in_chunk]
+        s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+        buf = bytearray(out_chunk)
+        s.next_out, s.next_out_index, s.avail_out = buf, 0, out_chunk
+        r = Z.inflate(s, Z.Z_NO_FLUSH)
+        assert r in (Z.Z_OK, Z.Z_STREAM_END, Z.Z_BUF_ERROR), (r, s.msg)
+        out += buf[: s.next_out_index]
+        pos += len(piece) - s.avail_in
+        if r == Z.Z_BUF_ERROR and pos >= len(stream) and s.next_out_index == 0:
+            break
+    total_in = s.total_in
+    assert Z.inflateEnd(s) == Z.Z_OK
+    return bytes(out), r, total_in
+
+
+@pytest.mark.parametrize("wbits", [15, 31, -15])
+def test_main_roundtrip(gpu_ctx, oracle, wbits):
+    # test/deflate/test-main-roundtrip.ts:9-43 -- C zlib (and the oracle) inflate what we deflate
+    for data in (make_text(300000, 1), rand_bytes(100000, 2), bytes(j % 251 for j in range(1 << 20)), b"", b"x"):
+        out, adler = chunked_deflate(data, 6, wbits, 65536, 65536)
+        d = zlib.decompressobj(wbits)
+        assert d.decompress(out) + d.flush() == data and d.eof
+        ret, o2, used, _ = oracle.inflate(out, wbits, len(data) + 64)
+        assert ret == 1 and o2 == data and used == len(out)
+        if wbits == 15:
+            assert adler == zlib.adler32(data)
+        if wbits == 31:
+            assert adler == zlib.crc32(data) and out[9] == 255
+        # and our own inflate gives it back through the same API
+        back, r, total_in = chunked_inflate(out, wbits, 65536, 65536)
+        assert back == data and r == 1 and total_in == len(out)
+
+
+def test_small_buffers(gpu_ctx, oracle):
+    # test/deflate/test-small-buffers.ts:7-35, test/common/utils.ts:21-71
+    data = make_text(5000, 3)
+    for in_chunk, out_chunk in ((1, 64), (31, 7), (4096, 1)):
+        out, _ = chunked_deflate(data, 9, 15, in_chunk, out_chunk)
+        assert zlib.decompress(out) == data
+    z = zlib.compress(data, 6)
+    for in_chunk, out_chunk in ((3, 8), (1, 4096), (4096, 1)):
+        back, r, _ = chunked_inflate(z, 15, in_chunk, out_chunk)
+        assert back == data and r == 1
+
+
+def test_protocol_pins(gpu_ctx):
+    Z = _Z()
+    # null stream -> Z_STREAM_ERROR for every entry point except deflateBound (test-errors.ts)
+    assert Z.deflateInit(None, 6) == Z.Z_STREAM_ERROR and Z.deflate(None, 0) == Z.Z_STREAM_ERROR
+    assert Z.deflateEnd(None) == Z.Z_STREAM_ERROR and Z.inflateInit(None) == Z.Z_STREAM_ERROR
+    assert Z.inflate(None, 0) == Z.Z_STREAM_ERROR and Z.inflateEnd(None) == Z.Z_STREAM_ERROR
+    assert Z.deflateBound(None, 1000) > 1000
+    s = Z.createDeflateStream()
+    for bad in (dict(level=10), dict(level=6, method=7), dict(level=6, windowBits=16 + 16), dict(level=6, memLevel=0),
+                dict(level=6, strategy=5), dict(level=6, windowBits=-8)):
+        args = dict(level=6, method=8, windowBits=15, memLevel=8, strategy=0)
+        args.update(bad)
+        assert Z.deflateInit2_(s, args["level"], args["method"], args["windowBits"], args["memLevel"], args["strategy"]) == Z.Z_STREAM_ERROR
+    # Z_FINISH with avail_out == 0 -> Z_BUF_ERROR, stream still usable (test-avail-out-guard.ts:20-50)
+    assert Z.deflateInit(s, 6) == Z.Z_OK
+    s.next_in, s.next_in_index, s.avail_in = b"hello", 0, 5
+    s.next_out, s.next_out_index, s.avail_out = bytearray(0), 0, 0
+    assert Z.deflate(s, Z.Z_FINISH) == Z.Z_BUF_ERROR
+    buf = bytearray(64)
+    s.next_out, s.next_out_index, s.avail_out = buf, 0, 64
+    assert Z.deflate(s, Z.Z_FINISH) == Z.Z_STREAM_END
+    assert zlib.decompress(bytes(buf[: s.next_out_index])) == b"hello"
+    assert Z.deflateEnd(s) == Z.Z_OK                       # finished stream -> Z_OK
+    assert Z.deflate(s, Z.Z_FINISH) == Z.Z_STREAM_ERROR    # ended stream
+    # deflateEnd in the middle of a stream -> Z_DATA_ERROR (deflate.ts:1012)
+    s = Z.createDeflateStream()
+    Z.deflateInit(s, 1)
+    s.next_in, s.next_in_index, s.avail_in = b"abc", 0, 3
+    s.next_out, s.next_out_index, s.avail_out = bytearray(64), 0, 64
+    assert Z.deflate(s, Z.Z_NO_FLUSH) == Z.Z_OK
+    assert Z.deflateEnd(s) == Z.Z_DATA_ERROR
+    # inflate: bad windowBits, empty input -> Z_BUF_ERROR (test-inflate9-needmore.spec.ts)
+    i = Z.createInflateStream()
+    assert Z.inflateInit2_(i, -17) == Z.Z_STREAM_ERROR
+    assert Z.inflateInit2_(i, -16) == Z.Z_OK
+    i.next_in, i.next_in_index, i.avail_in = b"", 0, 0
+    i.next_out, i.next_out_index, i.avail_out = bytearray(16), 0, 16
+    assert Z.inflate(i, Z.Z_NO_FLUSH) == Z.Z_BUF_ERROR
+    assert Z.inflateEnd(i) == Z.Z_OK
+
+
+def test_flush_modes_and_dictionary(gpu_ctx, oracle):
+    Z = _Z()
+    data = make_text(200000, 4)
+    # sync / full flush points: everything fed so far must be decodable (test-flush-modes.ts)
+    s = Z.createDeflateStream()
+    assert Z.deflateInit2_(s, 6, 8, -15, 8, 0) == Z.Z_OK
+    out = bytearray()
+    d = zlib.decompressobj(-15)
+    got = b""
+    for k, flush in enumerate((Z.Z_SYNC_FLUSH, Z.Z_FULL_FLUSH, Z.Z_SYNC_FLUSH, Z.Z_FINISH)):
+        piece = data[k * 50000: (k + 1) * 50000]
+        s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+        while True:
+            buf = bytearray(1 << 16)
+            s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+            r = Z.deflate(s, flush)
+            out += buf[: s.next_out_index]
+            got += d.decompress(bytes(buf[: s.next_out_index]))
+            if s.avail_out != 0:
+                break
+        assert got == data[: (k + 1) * 50000], k
+        assert r == (Z.Z_STREAM_END if flush == Z.Z_FINISH else Z.Z_OK)
+    assert Z.deflateEnd(s) == Z.Z_OK
+    # preset dictionary, zlib wrapper: FDICT + DICTID framing, C zlib decodes with zdict
+    dic = data[:20000]
+    s = Z.createDeflateStream()
+    Z.deflateInit(s, 6)
+    assert Z.deflateSetDictionary(s, dic, len(dic)) == Z.Z_OK
+    body = data[20000:90000]
+    s.next_in, s.next_in_index, s.avail_in = body, 0, len(body)
+    buf = bytearray(1 << 17)
+    s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+    assert Z.deflate(s, Z.Z_FINISH) == Z.Z_STREAM_END
+    stream = bytes(buf[: s.next_out_index])
+    assert stream[1] & 0x20
+    assert zlib.decompressobj(15, zdict=dic).decompress(stream) == body
+    ret, o2, _, _ = oracle.inflate(stream, 15, len(body) + 64, dic)
+    assert ret == 1 and o2 == body
+    assert len(stream) < len(zlib.compress(body, 6))          # the dictionary helped
+    # ... and our inflate asks for it (Z_NEED_DICT, inflate.ts:587-590)
+    i = Z.createInflateStream()
+    Z.inflateInit(i)
+    i.next_in, i.next_in_index, i.avail_in = stream, 0, len(stream)
+    ob = bytearray(len(body) + 64)
+    i.next_out, i.next_out_index, i.avail_out = ob, 0, len(ob)
+    assert Z.inflate(i, Z.Z_NO_FLUSH) == Z.Z_NEED_DICT
+    assert i._adler == zlib.adler32(dic)
+    assert Z.inflateSetDictionary(i, b"wrong", 5) == Z.Z_DATA_ERROR
+    assert Z.inflateSetDictionary(i, dic, len(dic)) == Z.Z_OK
+    assert Z.inflate(i, Z.Z_FINISH) == Z.Z_STREAM_END
+    assert bytes(ob[: i.next_out_index]) == body
+
+
+def test_multi_member_gzip(gpu_ctx):
+    # test/inflate/test-multistream.ts:16-79
+    Z = _Z()
+    a, b = make_text(30000, 1), make_text(20000, 2)
+    blob = zlib.compress(a, 6, 31) + zlib.compress(b, 9, 31)
+    s = Z.createInflateStream()
+    Z.inflateInit2_(s, 31)
+    s.next_in, s.next_in_index, s.avail_in = blob, 0, len(blob)
+    ob = bytearray(1 << 16)
+    s.next_out, s.next_out_index, s.avail_out = ob, 0, len(ob)
+    assert Z.inflate(s, Z.Z_NO_FLUSH) == Z.Z_STREAM_END
+    first = s.total_in
+    assert bytes(ob[: s.next_out_index]) == a and 0 < first < len(blob) and s.avail_in == len(blob) - first
+    assert Z.inflateReset(s) == Z.Z_OK
+    s.next_out, s.next_out_index, s.avail_out = ob, 0, len(ob)
+    assert Z.inflate(s, Z.Z_NO_FLUSH) == Z.Z_STREAM_END
+    assert bytes(ob[: s.next_out_index]) == b and first + s.total_in == len(blob)
+    Z.inflateEnd(s)
+
+
+@pytest.mark.parametrize("fmt", ["deflate", "gzip", "deflate-raw"])
+def test_streams_roundtrip(gpu_ctx, fmt):
+    # test/round-trip/test-streams-roundtrip.ts, test-streams-options.ts, test-streams-empty-input.ts
+    S = pkg("streams")
+    wb = {"deflate": 15, "gzip": 31, "deflate-raw": -15}[fmt]
+    for level in (None, 1, 9):
+        for data in (make_text(1 << 20, 5), rand_bytes(70000, 6), b""):
+            cs = S.CompressionStream(fmt, {"level": level} if level is not None else None)
+            comp = b"".join(cs.write(data[: len(data) // 2]) + cs.write(data[len(data) // 2:]) + cs.close())
+            d = zlib.decompressobj(wb)
+            assert d.decompress(comp) + d.flush() == data
+            assert S.DecompressionStream(fmt).transform(comp) == data
+    assert S.CompressionStream("deflate-raw").transform(b"") == bytes([3, 0])
+    with pytest.raises(RuntimeError):
+        S.DecompressionStream(fmt).transform(b"")               # truncated stream rejects
+    with pytest.raises(TypeError):
+        S.CompressionStream("deflate64-raw")
+
+
+def test_decompression_stream_deflate64(gpu_ctx, fixtures64):
+    S = pkg("streams")
+    f = next(x for x in fixtures64 if x["name"] == "10k_lines.deflate64")
+    out = S.DecompressionStream("deflate64-raw").transform(f["data"])
+    assert len(out) == f["out_len"] and zlib.crc32(out) == f["crc32"]

@@ -1,13 +1,490 @@
-// zs_stream.cu -- placeholder, replaced by the streaming shim
+// zs_stream.cu -- the z_stream protocol of the reference's deflate()/inflate() on top of the batch engine.
+//
+// Mirrors, call for call: createDeflateStream/deflateInit2_ (src/mod/deflate/deflate.ts:80,253),
+// deflate (:716, argument and progress rules :720-748, flush handling :936-961, trailers :964-988),
+// deflateSetDictionary (:367), deflateEnd (:991); createInflateStream/inflateInit2_
+// (src/mod/inflate/inflate.ts:68,174), inflate (:332, return rules of inf_leave :1059-1100),
+// inflateSetDictionary (:1220), inflateReset (:124), inflateEnd (:1187).
+//
+// The GPU needs whole chunks, so the shim is framing + buffering only (no codec work on the host):
+//  * deflate: input is buffered; a flush, Z_FINISH or 16 MiB of pending input sends one *part* to
+//    zs_deflate_batch_dev as a STITCHED + SYNC run of chunks whose first chunk is primed with the
+//    last 32 KiB of the previous part.  Every non-final part therefore ends with the reference's
+//    own Z_SYNC_FLUSH marker (empty stored block) and is byte aligned; the wrapper trailer of a
+//    multi-part stream is assembled from the per-part checksums with *_combine.
+//  * inflate: input is buffered and the stream is decoded from its start whenever enough new input
+//    has arrived (every call below 4 MiB, then geometrically); bytes decoded so far are final and
+//    are handed out immediately, Z_STREAM_END gives back the unused input.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 #include "zs_common.cuh"
-extern "C" {
-int zs_stream_deflate_init(zs_ctx*, zs_stream*, int, int, int, int, int) { return ZS_STREAM_ERROR; }
-int zs_stream_deflate_set_dictionary(zs_stream*, const uint8_t*, uint32_t) { return ZS_STREAM_ERROR; }
-int zs_stream_deflate(zs_stream*, int) { return ZS_STREAM_ERROR; }
-int zs_stream_deflate_end(zs_stream*) { return ZS_STREAM_ERROR; }
-int zs_stream_inflate_init(zs_ctx*, zs_stream*, int) { return ZS_STREAM_ERROR; }
-int zs_stream_inflate_set_dictionary(zs_stream*, const uint8_t*, uint32_t) { return ZS_STREAM_ERROR; }
-int zs_stream_inflate(zs_stream*, int) { return ZS_STREAM_ERROR; }
-int zs_stream_inflate_reset(zs_stream*) { return ZS_STREAM_ERROR; }
-int zs_stream_inflate_end(zs_stream*) { return ZS_STREAM_ERROR; }
+
+namespace {
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = (n + (n >> 2) + 4095) & ~(size_t)255;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+        cap = want;
+        return true;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
+constexpr size_t kPartThreshold = 16u << 20;
+
+struct DeflateState {
+    uint32_t magic = 0x44464c54;  // 'DFLT'
+    zs_ctx* ctx = nullptr;
+    int level = 6, wrap = 1, status = ST_INIT, last_flush = -2;
+    std::vector<uint8_t> hist;      // last <= 32 KiB already compressed (or the preset dictionary)
+    std::vector<uint8_t> in;        // buffered, not yet compressed
+    std::vector<uint8_t> out;       // compressed, not yet delivered
+    size_t out_pos = 0;
+    bool header_done = false, any_part = false, trailer_done = false, have_dict = false;
+    uint32_t check = 0, dict_id = 0;
+    uint64_t total_in_len = 0;
+    DevBuf d_in, d_out, d_res;
+};
+
+struct InflateState {
+    uint32_t magic = 0x494e464c;  // 'INFL'
+    zs_ctx* ctx = nullptr;
+    int window_bits = 15;
+    std::vector<uint8_t> in;        // the whole stream so far
+    std::vector<uint8_t> out;       // decoded so far
+    std::vector<uint8_t> dict;
+    std::vector<uint8_t> leftover;  // input after the end of the stream that could not be handed back
+    size_t delivered = 0, next_attempt = 0;
+    size_t out_cap_hint = 1 << 20;
+    bool done = false, failed = false, need_dict = false, have_dict = false;
+    int fail_code = 0;
+    const char* fail_msg = "";
+    uint32_t check = 0;
+};
+
+int rank_of(int f) { return f * 2 - (f > 4 ? 9 : 0); }  // RANK, deflate.ts:105
+
+DeflateState* dstate(zs_stream* s) {
+    if (!s || !s->state) return nullptr;
+    DeflateState* st = (DeflateState*)s->state;
+    return st->magic == 0x44464c54 ? st : nullptr;
 }
+InflateState* istate(zs_stream* s) {
+    if (!s || !s->state) return nullptr;
+    InflateState* st = (InflateState*)s->state;
+    return st->magic == 0x494e464c ? st : nullptr;
+}
+
+void put_be32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
+}
+void put_le32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 24));
+}
+
+// Compress everything buffered as one part.  `finish` makes it the last part of the stream.
+int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
+    zs_ctx* ctx = st->ctx;
+    const size_t hist_len = st->hist.size(), n = st->in.size();
+    // zlib header with a preset dictionary carries FDICT + DICTID: host framing (deflate.ts:754-777)
+    if (!st->header_done && st->wrap == ZS_WRAP_ZLIB && st->have_dict) {
+        unsigned header = (8u + (7u << 4)) << 8;
+        unsigned lf = st->level < 2 ? 0u : st->level < 6 ? 1u : st->level == 6 ? 2u : 3u;
+        header |= lf << 6;
+        header |= 0x20;
+        header += 31u - header % 31u;
+        st->out.push_back((uint8_t)(header >> 8));
+        st->out.push_back((uint8_t)header);
+        put_be32(st->out, st->dict_id);
+        st->header_done = true;
+    }
+    const bool whole = !st->any_part && finish && !st->header_done;  // the GPU frames a single-part stream completely
+    uint32_t flags = ZS_FLAG_SYNC;
+    if (st->header_done || st->any_part) flags |= ZS_FLAG_NOT_FIRST;
+    if (!finish) flags |= ZS_FLAG_NOT_LAST;
+    const uint32_t chunk = n >= (148u * 4u * 262144u) ? 262144u : 65536u;
+    const uint32_t n_chunks = n ? (uint32_t)((n + chunk - 1) / chunk) : 1u;
+    const uint64_t cap = zs_deflate_batch_bound(n, n_chunks, chunk, st->wrap, ZS_MODE_STITCHED);
+    if (!st->d_in.ensure(hist_len + n + 64) || !st->d_out.ensure(cap + 64) || !st->d_res.ensure(256)) return ZS_MEM_ERROR;
+    // history and input are contiguous on the device; keep the input 16-byte aligned
+    const size_t pad = (16 - (hist_len & 15)) & 15;
+    uint8_t* d_hist = st->d_in.p + pad;
+    if (hist_len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_hist, st->hist.data(), hist_len, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_hist + hist_len, st->in.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+    zs_deflate_result* d_result = (zs_deflate_result*)st->d_res.p;
+    int rc = zs_deflate_batch_dev(ctx, d_hist + hist_len, n, nullptr, n_chunks, chunk, chunk, (uint32_t)hist_len, st->level,
+                                  st->wrap, ZS_MODE_STITCHED, flags, st->d_out.p, cap, nullptr, nullptr, nullptr, d_result);
+    if (rc != ZS_OK) return rc;
+    zs_deflate_result res;
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(&res, d_result, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (res.total_out_bytes > cap) return ZS_BUF_ERROR;
+    const size_t old = st->out.size();
+    st->out.resize(old + res.total_out_bytes);
+    ZS_CUDA_TRY(ctx, cudaMemcpy(st->out.data() + old, st->d_out.p, res.total_out_bytes, cudaMemcpyDeviceToHost));
+    // running check over the uncompressed data (read_buf, deflate.ts:155-159)
+    if (st->wrap == ZS_WRAP_ZLIB) st->check = st->total_in_len || st->any_part ? zs_host_adler32_combine(st->check, res.check, n) : res.check;
+    else if (st->wrap == ZS_WRAP_GZIP) st->check = st->total_in_len || st->any_part ? zs_host_crc32_combine(st->check, res.check, n) : res.check;
+    st->total_in_len += n;
+    if (st->wrap != ZS_WRAP_RAW) strm->adler = st->check;
+    st->header_done = true;
+    st->any_part = true;
+    if (finish && !whole && !st->trailer_done) {
+        // trailer of a multi-part stream (deflate.ts:964-988)
+        if (st->wrap == ZS_WRAP_ZLIB) put_be32(st->out, st->check);
+        else if (st->wrap == ZS_WRAP_GZIP) { put_le32(st->out, st->check); put_le32(st->out, (uint32_t)st->total_in_len); }
+    }
+    if (finish) st->trailer_done = true;
+    // history for the next part: the last 32 KiB of (history + input); none after Z_FULL_FLUSH
+    if (full_flush || finish) {
+        st->hist.clear();
+    } else {
+        std::vector<uint8_t> h;
+        const size_t total = hist_len + n, keep = total < 32768 ? total : 32768;
+        h.resize(keep);
+        for (size_t i = 0; i < keep; i++) {
+            size_t idx = total - keep + i;
+            h[i] = idx < hist_len ? st->hist[idx] : st->in[idx - hist_len];
+        }
+        st->hist.swap(h);
+    }
+    st->in.clear();
+    return ZS_OK;
+}
+
+void drain(zs_stream* strm, std::vector<uint8_t>& out, size_t& pos) {
+    size_t avail = out.size() - pos;
+    size_t c = avail < strm->avail_out ? avail : (size_t)strm->avail_out;
+    if (c) {
+        memcpy(strm->next_out, out.data() + pos, c);
+        strm->next_out += c;
+        strm->avail_out -= c;
+        strm->total_out += c;
+        pos += c;
+    }
+    if (pos == out.size()) { out.clear(); pos = 0; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int zs_stream_deflate_init(zs_ctx* ctx, zs_stream* strm, int level, int method, int window_bits, int mem_level,
+                           int strategy) {
+    if (!strm || !ctx) return ZS_STREAM_ERROR;
+    strm->msg = "";
+    // deflateInit2_, deflate.ts:263-297
+    int wrap = 1;
+    if (level == -1) level = 6;
+    if (window_bits < 0) {
+        wrap = 0;
+        if (window_bits < -15) return ZS_STREAM_ERROR;
+        window_bits = -window_bits;
+    } else if (window_bits > 15) {
+        wrap = 2;
+        window_bits -= 16;
+    }
+    if (mem_level < 1 || mem_level > 9 || method != 8 || window_bits < 8 || window_bits > 15 || level < 0 || level > 9 ||
+        strategy < 0 || strategy > 4 || (window_bits == 8 && wrap != 1))
+        return ZS_STREAM_ERROR;
+    if (level == 0 || strategy != 0) {
+        // deflate_stored / Z_FILTERED / Z_HUFFMAN_ONLY / Z_RLE / Z_FIXED are outside the GPU hot path
+        strm->msg = "level 0 and non-default strategies are not implemented by the GPU engine";
+        return ZS_STREAM_ERROR;
+    }
+    DeflateState* st = new DeflateState();
+    st->ctx = ctx;
+    st->level = level;
+    st->wrap = wrap;
+    st->status = ST_INIT;
+    strm->state = st;
+    strm->total_in = strm->total_out = 0;
+    strm->adler = wrap == 2 ? 0u : 1u;
+    strm->data_type = 2;  // Z_UNKNOWN
+    return ZS_OK;
+}
+
+int zs_stream_deflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len) {
+    DeflateState* st = dstate(strm);
+    if (!st || !dict) return ZS_STREAM_ERROR;
+    // deflate.ts:372-375: not for gzip, for zlib only before the first deflate call, never mid-block
+    if (st->wrap == 2 || (st->wrap == 1 && st->status != ST_INIT) || !st->in.empty()) return ZS_STREAM_ERROR;
+    if (st->wrap == 1) {
+        uint32_t id = 0;
+        int rc = zs_checksum(st->ctx, 0, dict, dict_len, strm->adler, &id);
+        if (rc != ZS_OK) return rc;
+        strm->adler = id;
+        st->dict_id = id;
+        st->have_dict = true;
+    }
+    const uint32_t keep = dict_len < 32768 ? dict_len : 32768;
+    st->hist.assign(dict + (dict_len - keep), dict + dict_len);
+    return ZS_OK;
+}
+
+int zs_stream_deflate(zs_stream* strm, int flush) {
+    DeflateState* st = dstate(strm);
+    if (!st || flush > ZS_BLOCK || flush < 0) return ZS_STREAM_ERROR;
+    if (!strm->next_out || (strm->avail_in != 0 && !strm->next_in) || (st->status == ST_FINISH && flush != ZS_FINISH)) {
+        strm->msg = "stream error";
+        return ZS_STREAM_ERROR;
+    }
+    if (strm->avail_out == 0) { strm->msg = "buffer error"; return ZS_BUF_ERROR; }
+    const int old_flush = st->last_flush;
+    st->last_flush = flush;
+    if (st->out_pos < st->out.size()) {
+        drain(strm, st->out, st->out_pos);
+        if (strm->avail_out == 0) { st->last_flush = -1; return ZS_OK; }
+    } else if (strm->avail_in == 0 && rank_of(flush) <= rank_of(old_flush) && flush != ZS_FINISH) {
+        strm->msg = "buffer error";
+        return ZS_BUF_ERROR;
+    }
+    if (st->status == ST_FINISH && strm->avail_in != 0) { strm->msg = "buffer error"; return ZS_BUF_ERROR; }
+    if (st->status == ST_INIT) {
+        if (st->wrap == 1 && !st->have_dict) strm->adler = 1u;
+        st->status = ST_BUSY;
+    }
+    if (strm->avail_in) {
+        st->in.insert(st->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+        strm->next_in += strm->avail_in;
+        strm->total_in += strm->avail_in;
+        strm->avail_in = 0;
+    }
+    if (st->status == ST_BUSY) {
+        int rc = ZS_OK;
+        if (flush == ZS_FINISH) {
+            rc = run_part(strm, st, true, false);
+            if (rc == ZS_OK) st->status = ST_FINISH;
+        } else if (flush != ZS_NO_FLUSH) {
+            if (!st->in.empty() || !st->any_part) {
+                rc = run_part(strm, st, false, flush == ZS_FULL_FLUSH);
+            } else {
+                // nothing new since the last flush point: just the marker (deflate.ts:945-946)
+                static const uint8_t marker[5] = {0, 0, 0, 0xff, 0xff};
+                st->out.insert(st->out.end(), marker, marker + 5);
+                if (flush == ZS_FULL_FLUSH) st->hist.clear();
+            }
+        } else if (st->in.size() >= kPartThreshold) {
+            rc = run_part(strm, st, false, false);
+        }
+        if (rc != ZS_OK) {
+            strm->msg = zs_last_error(st->ctx);
+            return rc;
+        }
+    }
+    drain(strm, st->out, st->out_pos);
+    if (flush == ZS_FINISH && st->status == ST_FINISH && st->out_pos >= st->out.size()) return ZS_STREAM_END;
+    return ZS_OK;
+}
+
+int zs_stream_deflate_end(zs_stream* strm) {
+    DeflateState* st = dstate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    const int status = st->status;
+    delete st;
+    strm->state = nullptr;
+    return status == ST_BUSY ? ZS_DATA_ERROR : ZS_OK;  // deflate.ts:1012
+}
+
+// ---- inflate ----------------------------------------------------------------------------------------
+int zs_stream_inflate_init(zs_ctx* ctx, zs_stream* strm, int window_bits) {
+    if (!strm || !ctx) return ZS_STREAM_ERROR;
+    strm->msg = "";
+    // inflateReset2, inflate.ts:138-172
+    int wb = window_bits;
+    if (wb < 0) {
+        if (wb < -16) return ZS_STREAM_ERROR;
+        wb = -wb;
+        if (wb < 8) return ZS_STREAM_ERROR;
+    } else {
+        if (wb < 48) wb &= 15;
+        if (wb && (wb < 8 || wb > 15)) return ZS_STREAM_ERROR;
+    }
+    InflateState* st = new InflateState();
+    st->ctx = ctx;
+    st->window_bits = window_bits;
+    strm->state = st;
+    strm->total_in = strm->total_out = 0;
+    strm->adler = (window_bits > 0 && ((window_bits >> 4) + 5) & 1) ? 1u : 0u;
+    strm->data_type = 0;
+    return ZS_OK;
+}
+
+int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len) {
+    InflateState* st = istate(strm);
+    if (!st || !dict) return ZS_STREAM_ERROR;
+    // inflate.ts:1229: raw streams any time before data, wrapped streams only when Z_NEED_DICT was returned
+    if (st->window_bits > 0 && !st->need_dict) return ZS_STREAM_ERROR;
+    if (st->need_dict) {
+        // DICTID check (inflate.ts:1233-1238): bytes 2..5 of the zlib stream
+        uint32_t id = 0;
+        int rc = zs_checksum(st->ctx, 0, dict, dict_len, 1u, &id);
+        if (rc != ZS_OK) return rc;
+        uint32_t want = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
+        if (id != want) return ZS_DATA_ERROR;
+        st->need_dict = false;
+    }
+    const uint32_t keep = dict_len < 65536 ? dict_len : 65536;
+    st->dict.assign(dict + (dict_len - keep), dict + dict_len);
+    st->have_dict = true;
+    st->next_attempt = 0;
+    return ZS_OK;
+}
+
+static int inflate_attempt(zs_stream* strm, InflateState* st) {
+    zs_ctx* ctx = st->ctx;
+    // a zlib stream with a preset dictionary: the 2-byte header and the DICTID are host framing, the
+    // body is decoded as a raw stream with the dictionary and the adler32 trailer is checked here
+    const bool zdict = st->have_dict && st->window_bits > 0;
+    const uint8_t* src = st->in.data();
+    size_t src_len = st->in.size();
+    int wb = st->window_bits;
+    if (zdict) {
+        if (src_len < 6) return ZS_OK;
+        src += 6;
+        src_len -= 6;
+        wb = -15;
+    }
+    for (;;) {
+        const uint64_t in_off[2] = {0, src_len}, out_off[2] = {0, st->out_cap_hint};
+        st->out.resize(st->out_cap_hint);
+        uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->dict.size()};
+        uint32_t check = 0;
+        int32_t status = 0, detail = 0;
+        int rc = zs_inflate_batch(ctx, src, in_off, 1, wb, st->out.data(), out_off, &out_len, &in_used, &check, &status,
+                                  st->dict.empty() ? nullptr : st->dict.data(), st->dict.empty() ? nullptr : rng,
+                                  st->dict.size());
+        if (rc != ZS_OK) { strm->msg = zs_last_error(ctx); return rc; }
+        if (status == ZS_BUF_ERROR && out_len == st->out_cap_hint) {  // output full: grow and decode again
+            st->out_cap_hint *= 4;
+            continue;
+        }
+        st->out.resize(out_len);
+        st->check = check;
+        if (status == ZS_STREAM_END) {
+            if (zdict) {
+                // adler32 trailer of the wrapped stream follows the raw body
+                if (src_len - in_used < 4) { st->out.resize(out_len); return ZS_OK; }  // trailer not here yet
+                const uint8_t* t = src + in_used;
+                uint32_t want = (uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3];
+                uint32_t got = 1;
+                rc = zs_checksum(ctx, 0, st->out.data(), out_len, 1u, &got);
+                if (rc != ZS_OK) return rc;
+                st->check = got;
+                if (got != want) { st->failed = true; st->fail_code = ZS_DATA_ERROR; st->fail_msg = "incorrect data check"; return ZS_OK; }
+                in_used += 4 + 6;
+            }
+            st->done = true;
+            // unused input goes back to the caller (or is kept for the next member)
+            const size_t extra = st->in.size() - (size_t)in_used;
+            if (extra) {
+                st->leftover.assign(st->in.end() - extra, st->in.end());
+                st->in.resize((size_t)in_used);
+            }
+        } else if (status == ZS_NEED_DICT) {
+            st->need_dict = true;
+        } else if (status == ZS_DATA_ERROR) {
+            zs_inflate_last_details(ctx, &detail, 1);
+            st->failed = true;
+            st->fail_code = ZS_DATA_ERROR;
+            st->fail_msg = zs_inflate_message(detail);
+        }
+        return ZS_OK;
+    }
+}
+
+int zs_stream_inflate(zs_stream* strm, int flush) {
+    InflateState* st = istate(strm);
+    if (!st || !strm->next_out || (!strm->next_in && strm->avail_in != 0)) return ZS_STREAM_ERROR;
+    const uint64_t in0 = strm->avail_in, out0 = strm->avail_out;
+    if (!st->done && !st->failed) {
+        // input left over from the previous member is consumed first (inflateReset flow)
+        if (!st->leftover.empty() && st->in.empty()) {
+            st->in.swap(st->leftover);
+            st->leftover.clear();
+            st->next_attempt = 0;
+        }
+        if (strm->avail_in) {
+            st->in.insert(st->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+            strm->next_in += strm->avail_in;
+            strm->total_in += strm->avail_in;
+            strm->avail_in = 0;
+        }
+        if (st->need_dict) return ZS_NEED_DICT;
+        const bool due = flush == ZS_FINISH || st->in.size() >= st->next_attempt;
+        if (due && !st->in.empty()) {
+            int rc = inflate_attempt(strm, st);
+            if (rc != ZS_OK) return rc;
+            st->next_attempt = st->in.size() < (4u << 20) ? st->in.size() + 1 : st->in.size() + st->in.size() / 4;
+            if (st->need_dict) {
+                strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
+                return ZS_NEED_DICT;
+            }
+            if (st->done && !st->leftover.empty()) {
+                // hand back what the caller gave us in this call and we did not need
+                const size_t give = st->leftover.size() <= in0 ? st->leftover.size() : (size_t)in0;
+                strm->next_in -= give;
+                strm->avail_in += give;
+                strm->total_in -= give;
+                st->leftover.resize(st->leftover.size() - give);  // handed back from the tail of the call's input
+            }
+        }
+    }
+    // deliver what has been decoded
+    if (st->delivered < st->out.size()) {
+        size_t c = st->out.size() - st->delivered;
+        if (c > strm->avail_out) c = (size_t)strm->avail_out;
+        memcpy(strm->next_out, st->out.data() + st->delivered, c);
+        strm->next_out += c;
+        strm->avail_out -= c;
+        strm->total_out += c;
+        st->delivered += c;
+    }
+    const bool all_out = st->delivered >= st->out.size();
+    if (st->failed && all_out) {
+        strm->msg = st->fail_msg;
+        return st->fail_code;
+    }
+    if (st->done && all_out) {
+        strm->adler = st->check;
+        return ZS_STREAM_END;
+    }
+    // inf_leave, inflate.ts:1092-1098: no progress, or Z_FINISH without reaching the end
+    const bool progress = (in0 != strm->avail_in) || (out0 != strm->avail_out);
+    if (!progress || flush == ZS_FINISH) return ZS_BUF_ERROR;
+    return ZS_OK;
+}
+
+int zs_stream_inflate_reset(zs_stream* strm) {
+    InflateState* st = istate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    st->in.clear();
+    st->out.clear();
+    st->dict.clear();
+    st->delivered = 0;
+    st->next_attempt = 0;
+    st->done = st->failed = st->need_dict = st->have_dict = false;
+    strm->total_in = strm->total_out = 0;
+    strm->msg = "";
+    return ZS_OK;
+}
+
+int zs_stream_inflate_end(zs_stream* strm) {
+    InflateState* st = istate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    delete st;
+    strm->state = nullptr;
+    return ZS_OK;
+}
+
+}  // extern "C"

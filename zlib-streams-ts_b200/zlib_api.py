@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's zlib-style API over the GPU engine.
+
+Same names, argument meaning, return codes and draining protocol as
+src/mod/deflate/deflate.ts (createDeflateStream :80, deflateInit :238, deflateInit2_ :253, deflate
+:716, deflateEnd :991, deflateSetDictionary :367, deflateBound :615) and src/mod/inflate/inflate.ts
+(createInflateStream :68, inflateInit :74, inflateInit2_ :174, inflate :332, inflateEnd :1187,
+inflateSetDictionary :1220, inflateReset :124).  The data carrier is the reference's Stream
+(src/mod/common/types.ts:1-15): next_in / next_in_index / avail_in / total_in, next_out /
+next_out_index / avail_out / total_out, msg, _adler, _data_type, _state.
+
+All work is delegated to the C ABI streaming shim (zs_stream_* in include/zsgpu.h); this module is
+marshalling only -- it is what the TypeScript facade of INTEGRATION.md does through the addon.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import capi
+from .capi import (Z_BLOCK, Z_BUF_ERROR, Z_DATA_ERROR, Z_FINISH, Z_FULL_FLUSH, Z_MEM_ERROR, Z_NEED_DICT,  # noqa: F401
+                   Z_NO_FLUSH, Z_OK, Z_PARTIAL_FLUSH, Z_STREAM_END, Z_STREAM_ERROR, Z_SYNC_FLUSH)
+
+Z_DEFLATED = 8
+Z_DEFAULT_COMPRESSION = -1
+Z_DEFAULT_STRATEGY = 0
+DEF_WBITS = 15
+DEF_MEM_LEVEL = 8
+
+
+class Stream:
+    """The reference's Stream object (createStream, src/mod/common/utils.ts:44-60)."""
+
+    def __init__(self):
+        self.next_in = b""
+        self.next_in_index = 0
+        self.avail_in = 0
+        self.total_in = 0
+        self.next_out = bytearray(0)
+        self.next_out_index = 0
+        self.avail_out = 0
+        self.total_out = 0
+        self.msg = ""
+        self._data_type = 0
+        self._adler = 0
+        self._state = None      # ("deflate" | "inflate", ZStream)
+        self._keep = None
+
+
+def _ctx():
+    from .batch import default_context
+    return default_context()
+
+
+def createDeflateStream() -> Stream:
+    return Stream()
+
+
+def createInflateStream() -> Stream:
+    return Stream()
+
+
+def _kind(strm, kind):
+    return strm is not None and isinstance(strm, Stream) and strm._state is not None and strm._state[0] == kind
+
+
+def deflateInit(strm: Stream, level: int) -> int:
+    return deflateInit2_(strm, level)
+
+
+def deflateInit2_(strm: Stream, level: int, method: int = Z_DEFLATED, windowBits: int = DEF_WBITS,
+                  memLevel: int = DEF_MEM_LEVEL, strategy: int = Z_DEFAULT_STRATEGY) -> int:
+    if strm is None:
+        return Z_STREAM_ERROR
+    strm.msg = ""
+    zs = capi.ZStream()
+    rc = capi.load().zs_stream_deflate_init(_ctx().handle, C.byref(zs), level, method, windowBits, memLevel, strategy)
+    if rc != Z_OK:
+        strm.msg = (zs.msg or b"").decode() if zs.msg else ""
+        return rc
+    strm._state = ("deflate", zs)
+    strm.total_in = strm.total_out = 0
+    strm._adler = zs.adler
+    strm._data_type = zs.data_type
+    return Z_OK
+
+
+deflateInit2 = deflateInit2_
+
+
+def deflateSetDictionary(strm: Stream, dictionary, dictLength: int | None = None) -> int:
+    if not _kind(strm, "deflate") or dictionary is None:
+        return Z_STREAM_ERROR
+    d = bytes(dictionary[: dictLength] if dictLength is not None else dictionary)
+    buf = (C.c_ubyte * max(len(d), 1)).from_buffer_copy(d or b"\0")
+    zs = strm._state[1]
+    rc = capi.load().zs_stream_deflate_set_dictionary(C.byref(zs), buf, len(d))
+    strm._adler = zs.adler
+    return rc
+
+
+def _call(strm: Stream, fn, flush: int) -> int:
+    zs = strm._state[1]
+    n_in, n_out = strm.avail_in, strm.avail_out
+    src = bytes(strm.next_in[strm.next_in_index: strm.next_in_index + n_in]) if n_in else b""
+    in_buf = (C.c_ubyte * max(n_in, 1)).from_buffer_copy(src or b"\0")
+    out_buf = (C.c_ubyte * max(n_out, 1))()
+    zs.next_in = C.addressof(in_buf)
+    zs.avail_in = n_in
+    zs.next_out = C.addressof(out_buf)
+    zs.avail_out = n_out
+    rc = fn(C.byref(zs), flush)
+    used = n_in - zs.avail_in
+    made = n_out - zs.avail_out
+    if made:
+        strm.next_out[strm.next_out_index: strm.next_out_index + made] = bytes(out_buf[:made])
+    strm.next_in_index += used
+    strm.avail_in -= used
+    strm.next_out_index += made
+    strm.avail_out -= made
+    strm.total_in = zs.total_in
+    strm.total_out = zs.total_out
+    strm._adler = zs.adler
+    strm._data_type = zs.data_type
+    strm.msg = (zs.msg or b"").decode() if zs.msg else ""
+    return rc
+
+
+def deflate(strm: Stream, flush: int) -> int:
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    if strm.next_out is None or (strm.avail_in != 0 and strm.next_in is None):
+        return Z_STREAM_ERROR
+    return _call(strm, capi.load().zs_stream_deflate, flush)
+
+
+def deflateEnd(strm: Stream) -> int:
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    rc = capi.load().zs_stream_deflate_end(C.byref(strm._state[1]))
+    strm._state = None
+    return rc
+
+
+def deflateBound(strm, sourceLen: int) -> int:
+    """deflate.ts:615-674 for the default windowBits 15 / memLevel 8 state; like the reference it
+    also answers for a null stream (conservative bound + 18)."""
+    n = sourceLen
+    if not _kind(strm, "deflate"):
+        fixedlen = n + (n >> 3) + (n >> 8) + (n >> 9) + 4
+        storelen = n + (n >> 5) + (n >> 7) + (n >> 11) + 7
+        return max(fixedlen, storelen) + 18
+    return n + (n >> 12) + (n >> 14) + (n >> 25) + 13 - 6 + 18
+
+
+def inflateInit(strm: Stream) -> int:
+    return inflateInit2_(strm, DEF_WBITS)
+
+
+def inflateInit2_(strm: Stream, windowBits: int) -> int:
+    if strm is None:
+        return Z_STREAM_ERROR
+    strm.msg = ""
+    zs = capi.ZStream()
+    rc = capi.load().zs_stream_inflate_init(_ctx().handle, C.byref(zs), windowBits)
+    if rc != Z_OK:
+        return rc
+    strm._state = ("inflate", zs)
+    strm.total_in = strm.total_out = 0
+    strm._adler = zs.adler
+    return Z_OK
+
+
+inflateInit2 = inflateInit2_
+
+
+def inflateSetDictionary(strm: Stream, dictionary, dictLength: int | None = None) -> int:
+    if not _kind(strm, "inflate"):
+        return Z_STREAM_ERROR
+    d = bytes(dictionary[: dictLength] if dictLength is not None else dictionary)
+    buf = (C.c_ubyte * max(len(d), 1)).from_buffer_copy(d or b"\0")
+    return capi.load().zs_stream_inflate_set_dictionary(C.byref(strm._state[1]), buf, len(d))
+
+
+def inflate(strm: Stream, flush: int) -> int:
+    if not _kind(strm, "inflate"):
+        return Z_STREAM_ERROR
+    if strm.next_out is None or (strm.next_in is None and strm.avail_in != 0):
+        return Z_STREAM_ERROR
+    return _call(strm, capi.load().zs_stream_inflate, flush)
+
+
+def inflateReset(strm: Stream) -> int:
+    if not _kind(strm, "inflate"):
+        return Z_STREAM_ERROR
+    zs = strm._state[1]
+    rc = capi.load().zs_stream_inflate_reset(C.byref(zs))
+    strm.total_in = strm.total_out = 0
+    strm.msg = ""
+    return rc
+
+
+def inflateEnd(strm: Stream) -> int:
+    if not _kind(strm, "inflate"):
+        return Z_STREAM_ERROR
+    rc = capi.load().zs_stream_inflate_end(C.byref(strm._state[1]))
+    strm._state = None
+    return rc
