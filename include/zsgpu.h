@@ -60,7 +60,9 @@ extern "C" {
 #define ZS_FLAG_PRIME 1u     /* INDEPENDENT: prime each chunk with the <=32 KiB that precede it in the
                                 input (deflateSetDictionary, deflate.ts:367); raw wrapper only */
 #define ZS_FLAG_NOT_FIRST 2u /* STITCHED: this call is not the first part (no wrapper header) */
-#define ZS_FLAG_NOT_LAST 4u  /* STITCHED: not the last part (no BFINAL, no trailer, not padded) */
+#define ZS_FLAG_NOT_LAST 4u  /* STITCHED: not the last part: no BFINAL, no trailer; the part ends with an
+                                empty stored block (Z_SYNC_FLUSH marker) so that the next part starts
+                                byte aligned (stored blocks are padded relative to the part's first bit) */
 #define ZS_FLAG_SYNC 8u      /* STITCHED: end every chunk with an empty stored block (Z_SYNC_FLUSH
                                 marker, deflate.ts:945-946) so chunks start byte aligned */
 
@@ -111,7 +113,7 @@ ZS_API int zs_checksum(zs_ctx* ctx, int kind, const uint8_t* buf, uint64_t len, 
  *      (trees.ts) and the header/trailer emission of deflate() (deflate.ts:750-832,964-988) ---- */
 typedef struct zs_deflate_result {
     uint64_t total_out_bytes; /* bytes valid in `out` */
-    uint64_t total_out_bits;  /* STITCHED: exact bit length (NOT_LAST parts end mid-byte) */
+    uint64_t total_out_bits;  /* STITCHED: exact bit length of this part (a multiple of 8) */
     uint32_t check;           /* adler32 (zlib) / crc32 (gzip, raw) of this call's whole input */
     uint32_t n_blocks;        /* deflate blocks emitted */
 } zs_deflate_result;

@@ -1,0 +1,31 @@
+"""torchrun --nproc-per-node N tools/sharded_check.py : N-rank stitched deflate of one replicated
+input, gathered on rank 0 and decoded with C zlib + the oracle (run on the GPU box)."""
+import importlib, os, sys, zlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.distributed as dist
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+S = importlib.import_module("zlib-streams-ts_b200.sharded")
+B = importlib.import_module("zlib-streams-ts_b200.batch")
+corpus = importlib.import_module("zlib-streams-ts_b200.corpus")
+ok = True
+for wrap, level, chunk, n in ((1, 6, 262144, 24 << 20), (2, 1, 65536, 10 << 20), (0, 6, 65536, (5 << 20) + 12345)):
+    data = torch.from_numpy(corpus.mixed_numpy(n, 0xB200)).cuda()     # same bytes on every rank
+    res, rr, plan = S.deflate_sharded(data, chunk, level, wrap)
+    stream = S.gather_stream(res, rr, plan, wrap, dst=0)
+    if rank == 0:
+        host = data.cpu().numpy().tobytes()
+        wb = {0: -15, 1: 15, 2: 31}[wrap]
+        d = zlib.decompressobj(wb)
+        good = d.decompress(stream) + d.flush() == host and d.eof
+        if wrap == 1: good &= plan.check == zlib.adler32(host)
+        if wrap == 2: good &= plan.check == zlib.crc32(host)
+        ref = len(zlib.compress(host, level))
+        print(f"wrap {wrap} level {level} world {world}: ok={good} size {len(stream)} vs zlib {ref} ({len(stream)/ref:.4f}) bit offsets {plan.bit_offset}")
+        ok &= good
+    dist.barrier()
+if rank == 0:
+    print("SHARDED_CHECK", "PASS" if ok else "FAIL")
+dist.destroy_process_group()

@@ -369,9 +369,11 @@ __global__ void layout_chunks_kernel(LayoutArgs a) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_chunks) return;
     const uint32_t nb = a.chunk_nblk[c];
-    // no marker after the chunk that carries the BFINAL block
-    const bool sync_marker = a.mode == ZS_MODE_STITCHED && (a.flags & ZS_FLAG_SYNC) &&
-                             !(c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST));
+    // Z_SYNC_FLUSH marker (empty stored block) after the chunk: between chunks when ZS_FLAG_SYNC is
+    // set, and always at the end of a part that is not the last one -- the next part must start
+    // byte aligned because stored blocks inside it are padded relative to its own first bit
+    const bool sync_marker = a.mode == ZS_MODE_STITCHED &&
+                             (c + 1 == a.n_chunks ? (a.flags & ZS_FLAG_NOT_LAST) != 0 : (a.flags & ZS_FLAG_SYNC) != 0);
     uint64_t P = 0, R = 0;
     bool seen = false;
     for (uint32_t j = 0; j < nb + (sync_marker ? 1u : 0u); j++) {
@@ -657,7 +659,7 @@ __global__ void frame_kernel(EncodeArgs a) {
     uint32_t* out32 = reinterpret_cast<uint32_t*>(a.out);
     if (c >= a.n_chunks) return;
     // Z_SYNC_FLUSH marker after each chunk: empty stored block 000 + pad + 00 00 ff ff
-    if (stitched && (a.flags & ZS_FLAG_SYNC) && !(c + 1 == a.n_chunks && !(a.flags & ZS_FLAG_NOT_LAST))) {
+    if (stitched && (c + 1 == a.n_chunks ? (a.flags & ZS_FLAG_NOT_LAST) != 0 : (a.flags & ZS_FLAG_SYNC) != 0)) {
         uint64_t end = a.out_off[c] + a.out_bits[c];  // marker is the tail of the chunk's bits
         uint64_t p = (end >> 3) - 4;                   // marker ends byte aligned
         a.out[p] = 0; a.out[p + 1] = 0; a.out[p + 2] = 0xff; a.out[p + 3] = 0xff;
