@@ -182,11 +182,14 @@ def main():
         r = B.deflate_batch_dev(data, CHUNK, LEVEL, B.WRAP_RAW, B.MODE_INDEPENDENT, flags, ctx=ctx, reuse=bufs,
                                 want_checks=False)
         if world > 1:
-            # the path's exchange step: per-rank compressed size -> all_gather -> exclusive scan
-            mine = r.out_off[-1:].clone()
-            allv = torch.empty(world, dtype=torch.int64, device=dev)
+            # the path's exchange step (sharded.exchange_meta): per-rank compressed size / length ->
+            # all_gather -> exclusive scan of the offsets on every rank
+            mine = torch.stack([r.out_off[-1] * 8, torch.zeros((), dtype=torch.int64, device=dev),
+                                torch.tensor(n, dtype=torch.int64, device=dev)])
+            allv = torch.empty(world * 3, dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allv, mine)
-            _ = torch.cumsum(allv, 0) - allv
+            bits = allv.view(world, 3)[:, 0]
+            _ = torch.cumsum(bits, 0) - bits
         return r
 
     bufs = step(None)
