@@ -207,44 +207,70 @@ __device__ __forceinline__ void link_batch(Smem& S, uint64_t b, uint64_t lo, uin
 }
 
 // ---- stage 3: search (wide), one lane per position -----------------------------------------------
+// All arithmetic is on 16-bit ring indices and 32-bit distances (the ring is a multiple of the
+// 32 KiB prev[] period, so prev[] is indexed by the ring index too).
+__device__ __forceinline__ uint32_t ring32(const Smem& S, unsigned idx) {
+    idx &= kRing - 1u;
+    const unsigned al = idx & ~3u;
+    const uint32_t lo = *reinterpret_cast<const uint32_t*>(S.ring + al);
+    const uint32_t hi = *reinterpret_cast<const uint32_t*>(S.ring + al + 4);
+    return __funnelshift_r(lo, hi, (idx & 3u) * 8u);
+}
+__device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
+    idx &= kRing - 1u;
+    const unsigned al = idx & ~3u, sh = (idx & 3u) * 8u;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(S.ring + al);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(S.ring + al + 4);
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(S.ring + al + 8);
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+__device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
+
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, uint64_t p, uint64_t chunk_end,
                                                     uint64_t lo) {
-    uint64_t room = chunk_end - p;
+    const uint64_t room = chunk_end - p;
     const unsigned max_len = room < 258 ? (unsigned)room : 258u;
-    const uint64_t p0 = win64(S, p);
-    const uint32_t lit = ((uint32_t)p0 & 0xffu) << 24;
+    const unsigned pi = (unsigned)p & (kRing - 1u);
+    const uint32_t pw0 = ring32(S, pi), pw1 = ring32(S, pi + 4);
+    const uint32_t lit = (pw0 & 0xffu) << 24;
     if (max_len < 3) return lit;
     const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
+    const uint64_t back = p - lo;
+    const unsigned max_back = back < kMaxDist ? (unsigned)back : kMaxDist;
     unsigned best_len = 2, best_dist = 0;
-    uint64_t cur = p;
+    unsigned ci = pi, dist = 0;
     for (int chain = cfg.chain; chain > 0; --chain) {
-        unsigned delta = ((unsigned)cur - S.prev[cur & 32767u]) & 0xffffu;
+        const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
         if (delta == 0) break;
-        if (cur < lo + delta) break;
-        uint64_t cand = cur - delta;
-        if (p - cand > kMaxDist) break;
-        cur = cand;
-        uint64_t x = win64(S, cand) ^ p0;
-        if ((x & 0xffffffull) != 0) continue;  // hash collision
-        if (best_len >= 8) {                    // cannot beat the best unless the bytes up to best_len agree
-            uint64_t y = win64(S, cand + best_len - 7) ^ win64(S, p + best_len - 7);
-            if (y) continue;
-        }
+        dist += delta;
+        if (dist > max_back) break;
+        ci = (ci - delta) & (kRing - 1u);
+        uint32_t x = ring32(S, ci) ^ pw0;
+        if ((x & 0xffffffu) != 0) continue;  // hash collision
         unsigned len;
         if (x) {
-            len = (unsigned)(__ffsll((long long)x) - 1) >> 3;
+            len = 3;
         } else {
-            len = 8;
-            while (len < max_len) {
-                uint64_t y = win64(S, cand + len) ^ win64(S, p + len);
-                if (y) { len += (unsigned)(__ffsll((long long)y) - 1) >> 3; break; }
-                len += 8;
+            x = ring32(S, ci + 4) ^ pw1;
+            if (x) {
+                len = 4 + first_diff_byte(x);
+            } else {
+                len = 8;
+                while (len < max_len) {
+                    const uint64_t y = ring64(S, ci + len) ^ ring64(S, pi + len);
+                    if (y) {
+                        const uint32_t yl = (uint32_t)y;
+                        len += yl ? first_diff_byte(yl) : 4 + first_diff_byte((uint32_t)(y >> 32));
+                        break;
+                    }
+                    len += 8;
+                }
             }
         }
         if (len > max_len) len = max_len;
         if (len > best_len) {
             best_len = len;
-            best_dist = (unsigned)(p - cand);
+            best_dist = dist;
             if (len >= nice) break;
         }
     }
