@@ -13,7 +13,7 @@ enum {
     SCR_D_PR = 10, SCR_D_OFF = 11, SCR_D_CHECKS = 12,
     SCR_I_MISC = 13,
     SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
-    SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22,
+    SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23,
 };
 
 void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
@@ -133,6 +133,10 @@ void zs_ctx_destroy(zs_ctx* ctx) {
     for (auto& s : ctx->scr)
         if (s.p) cudaFree(s.p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (auto e : ctx->ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->prof) {
         zs_profile* pr = (zs_profile*)ctx->prof;
         for (auto& r : pr->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -260,6 +264,7 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     p.d_in = d_in; p.in_len = in_len; p.history = history; p.n_chunks = n_chunks; p.max_chunk = max_chunk;
     p.max_bpc = max_chunk / 16351u + 2u;
     p.level = level; p.wrap = wrap; p.mode = mode; p.flags = flags;
+    p.seg_hint = ctx->seg_hint;
     const size_t slots = (size_t)n_chunks * p.max_bpc;
 
     uint64_t* off = (uint64_t*)zs_scratch_get(ctx, SCR_D_OFF, (size_t)(n_chunks + 1) * 8);
@@ -311,6 +316,116 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     return zs_launch_huffman(ctx, p);
 }
 
+static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t n_chunks, uint32_t chunk_size,
+                                   int level, int wrap, uint32_t flags, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
+                                   uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
+    constexpr int kMaxSlices = 16;
+    // slices of whole 16-chunk segments (the LZ77 kernel's segment size for large batches)
+    uint32_t slice_chunks = ((n_chunks / 8u) + 15u) & ~15u;
+    if (slice_chunks < 64) slice_chunks = 64;
+    const int n_slices = (int)((n_chunks + slice_chunks - 1) / slice_chunks);
+    if (n_slices > kMaxSlices) return bad_arg(ctx, "deflate: internal slicing error");
+    if (!ctx->s_in) {
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev) ZS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!ctx->h_pin) {
+        ZS_CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pin, 4096));
+        ctx->h_pin_cap = 4096;
+    }
+    zs_deflate_result* h_res = (zs_deflate_result*)ctx->h_pin;
+    const uint64_t slice_bytes = (uint64_t)slice_chunks * chunk_size;
+    const uint64_t region = zs_deflate_batch_bound(slice_bytes, slice_chunks, chunk_size, wrap, ZS_MODE_INDEPENDENT);
+    const uint64_t region_al = (region + 255) & ~255ull;
+    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_len + 64);
+    uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, region_al * n_slices + 64);
+    uint64_t* d_ooff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF2, ((size_t)n_chunks + n_slices) * 8);
+    uint64_t* d_obits = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)n_chunks * 8);
+    uint32_t* d_cks = (uint32_t*)zs_scratch_get(ctx, SCR_H_CHECKS, (size_t)n_chunks * 4);
+    zs_deflate_result* d_res = (zs_deflate_result*)zs_scratch_get(ctx, SCR_H_RES, sizeof(zs_deflate_result) * kMaxSlices);
+    if (!d_in || !d_out || !d_ooff || !d_obits || !d_cks || !d_res) return ZS_MEM_ERROR;
+    const bool want_checks = checks != nullptr || wrap != ZS_WRAP_RAW;
+    cudaEvent_t* ev_in = ctx->ev;          // [s]      slice s is on the device
+    cudaEvent_t* ev_k = ctx->ev + 16;      // [s]      kernels of slice s are done
+    cudaEvent_t* ev_r = ctx->ev + 32;      // [s]      result of slice s is on the host
+    // everything issued so far on the context stream (e.g. the caller's producers) comes first
+    ZS_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[48], ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev[48], 0));
+    ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev[48], 0));
+    // same LZ77 segmentation as the single-shot call over the whole batch
+    uint32_t seg = n_chunks / (4u * (uint32_t)ctx->sm_count);
+    seg = seg < 1 ? 1 : seg > 16 ? 16 : seg;
+    struct HintGuard { zs_ctx* c; ~HintGuard() { c->seg_hint = 0; } } guard{ctx};
+    ctx->seg_hint = seg;
+    for (int s = 0; s < n_slices; s++) {
+        const uint32_t c0 = (uint32_t)s * slice_chunks;
+        const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+        const uint64_t b0 = (uint64_t)c0 * chunk_size;
+        const uint64_t len = (b0 + (uint64_t)nc * chunk_size <= in_len) ? (uint64_t)nc * chunk_size : in_len - b0;
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + b0, in + b0, len, cudaMemcpyHostToDevice, ctx->s_in));
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_in[s], ctx->s_in));
+        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        const uint32_t hist = (flags & ZS_FLAG_PRIME) ? (uint32_t)(b0 < 32768 ? b0 : 32768) : 0u;
+        int rc = zs_deflate_batch_dev(ctx, d_in + b0, len, nullptr, nc, chunk_size, chunk_size, hist, level, wrap,
+                                      ZS_MODE_INDEPENDENT, flags, d_out + region_al * s, region, d_ooff + c0 + s,
+                                      d_obits + c0, want_checks ? d_cks + c0 : nullptr, d_res + s);
+        if (rc != ZS_OK) return rc;
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_k[s], ctx->stream));
+        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ev_k[s], 0));
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(h_res + s, d_res + s, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->s_out));
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_r[s], ctx->s_out));
+    }
+    uint64_t host_off = 0;
+    uint64_t base[kMaxSlices];
+    uint32_t blocks = 0, check = 0;
+    bool have_check = false;
+    int rc_final = ZS_OK;
+    for (int s = 0; s < n_slices; s++) {
+        const uint32_t c0 = (uint32_t)s * slice_chunks;
+        const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+        const uint64_t b0 = (uint64_t)c0 * chunk_size;
+        const uint64_t len = (b0 + (uint64_t)nc * chunk_size <= in_len) ? (uint64_t)nc * chunk_size : in_len - b0;
+        ZS_CUDA_TRY(ctx, cudaEventSynchronize(ev_r[s]));
+        const uint64_t total = h_res[s].total_out_bytes;
+        base[s] = host_off;
+        if (total > region || host_off + total > out_cap) { rc_final = ZS_BUF_ERROR; break; }
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out + host_off, d_out + region_al * s, total, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (out_off)
+            ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_off + c0, d_ooff + c0 + s, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (out_bits)
+            ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_bits + c0, d_obits + c0, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (checks)
+            ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks + c0, d_cks + c0, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        host_off += total;
+        blocks += h_res[s].n_blocks;
+        if (want_checks) {
+            if (!have_check) { check = h_res[s].check; have_check = true; }
+            else check = wrap == ZS_WRAP_ZLIB ? zs_host_adler32_combine(check, h_res[s].check, len)
+                                              : zs_host_crc32_combine(check, h_res[s].check, len);
+        }
+    }
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rc_final != ZS_OK) {
+        snprintf(ctx->err, sizeof(ctx->err), "deflate: output capacity %llu too small", (unsigned long long)out_cap);
+        return rc_final;
+    }
+    if (out_off) {
+        for (int s = 0; s < n_slices; s++) {
+            const uint32_t c0 = (uint32_t)s * slice_chunks;
+            const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+            for (uint32_t i = 0; i < nc; i++) out_off[c0 + i] += base[s];
+        }
+        out_off[n_chunks] = host_off;
+    }
+    result->total_out_bytes = host_off;
+    result->total_out_bits = host_off * 8;
+    result->check = check;
+    result->n_blocks = blocks;
+    return ZS_OK;
+}
+
 int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
                      uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out, uint64_t out_cap,
                      uint64_t* out_off, uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
@@ -327,6 +442,13 @@ int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint
             if (l > max_chunk) max_chunk = (uint32_t)l;
         }
     }
+    // Large batches of independent streams with fixed chunking are software-pipelined: the batch is cut
+    // into slices of whole segments, and the H2D copy of slice s+1, the kernels of slice s and the D2H
+    // copy of slice s-1 run concurrently on three streams.  The bytes produced are those of the
+    // single-shot path.
+    if (!in_off && mode == ZS_MODE_INDEPENDENT && n_chunks >= 512 && chunk_size >= 4096)
+        return deflate_batch_pipelined(ctx, in, in_len, n_chunks, chunk_size, level, wrap, flags, out, out_cap, out_off,
+                                       out_bits, checks, result);
     uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_len + 64);
     uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, out_cap + 64);
     uint64_t* d_off = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)(n_chunks + 1) * 8);

@@ -28,6 +28,10 @@ struct zs_ctx {
     // last inflate details (device ptr into scratch) for zs_inflate_last_details
     int32_t* d_last_detail = nullptr;
     uint32_t last_detail_n = 0;
+    // copy streams + events of the pipelined host-buffer path (zs_deflate_batch)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
+    cudaEvent_t ev[64] = {nullptr};
     // profiling (zs_ctx_profile)
     bool prof_on = false;
     void* prof = nullptr;  // zs_profile*, zs_api.cu
@@ -163,6 +167,7 @@ struct zs_deflate_plan {
     uint32_t n_chunks;
     uint32_t max_chunk;
     uint32_t max_bpc;         // block descriptor slots per chunk
+    uint32_t seg_hint;        // 0 or the LZ77 segment size to use (chunks)
     int level, wrap, mode;
     uint32_t flags;
     // scratch

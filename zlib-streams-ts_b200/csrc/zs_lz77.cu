@@ -617,7 +617,10 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     if (a.cross) {
         seg_chunks = p.n_chunks / (4u * (uint32_t)ctx->sm_count);
         if (seg_chunks < 1) seg_chunks = 1;
+        if (seg_chunks > 16) seg_chunks = 16;  // fixed for large batches: slicing a batch at multiples of 16 chunks
+                                               // (the pipelined host path) then leaves the output unchanged
     }
+    if (a.cross && p.seg_hint) seg_chunks = p.seg_hint;
     a.seg_chunks = seg_chunks;
     a.n_seg = (p.n_chunks + seg_chunks - 1) / seg_chunks;
     a.sym = p.d_sym;
