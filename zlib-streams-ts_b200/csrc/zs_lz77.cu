@@ -11,31 +11,36 @@
 // size stays within 3 % of the reference at the same level (tests/test_deflate_gpu.py).
 //
 // Work decomposition (B200: 148 SMs, 227 KB shared memory per CTA):
-//   * one persistent CTA per SM pulls *segments* (runs of consecutive chunks) from an atomic
-//     counter.  Everything the per-byte loop touches lives in shared memory: a 64 KiB ring of the
-//     window (staged from HBM once, 16 bytes per lane, coalesced) and the 2 x 64 KiB hash-chain
-//     tables head[32768] / prev[32768] (16-bit positions like the reference's).  Tables and ring
-//     are carried from chunk to chunk inside a segment, so dictionary priming costs one 32 KiB
-//     insert-only pass per segment, not per chunk.
-//   * inside the CTA the serial loop of the reference becomes a 5-stage software pipeline over
-//     448-position steps, one __syncthreads per step.  Fourteen "wide" warps do everything that is
-//     independent per position, two "thin" warps do the two inherently ordered updates:
-//        stage 1  prep    (wide) : hash 32 positions, find equal hashes inside the batch with 15
-//                                  ballots (nearest lower peer / last of its group);
-//        stage 2  insert  (thin) : thread the chains through head/prev in position order -- a
-//                                  single warp, ~25 instructions per 32 positions;
-//        stage 3  search  (wide) : one lane per position walks that position's chain (<= max_chain
-//                                  candidates, 8-byte compares in the shared-memory ring); every
-//                                  position is searched speculatively, which is what makes the
-//                                  chain walk 448-wide;
-//        stage 4  resolve (wide) : applies the greedy / lazy rule per position and runs 5 rounds of
-//                                  pointer doubling so that, for every possible entry lane of a
-//                                  32-position batch, the visited positions and the exit are known;
-//        stage 5  parse   (thin) : chains the batches (entry of batch b+1 = exit of batch b),
-//                                  writes the packed symbols and cuts blocks every <= 16383
-//                                  symbols (lit_bufsize - 1, deflate.ts:323,336).
-//     The inserter never runs more than 2 steps ahead of a searcher, so restricting matches to
-//     32768 - 2*448 bytes keeps every prev[] slot a searcher reads stable: no races, and the output
+//   * one persistent CTA (1024 threads) per SM pulls *segments* (runs of consecutive chunks) from
+//     an atomic counter.  Everything the per-byte loop touches lives in shared memory: a 64 KiB
+//     ring of the window (staged from HBM once, 16 bytes per lane, coalesced), the hash-chain
+//     tables prev[32768] (16-bit positions like the reference's) and head[16384] (one bit less than
+//     the reference's hash so that 30 wide warps fit; measured cost: +0.8 % size at level 6), and
+//     ~60 KB of rings between the pipeline stages.  Tables and ring are carried from chunk to chunk
+//     inside a segment, so dictionary priming costs one 32 KiB insert-only pass per segment.
+//   * inside the CTA the serial loop of the reference becomes a 7-stage software pipeline over
+//     960-position steps, one __syncthreads per step.  Thirty "wide" warps do everything that is
+//     independent per position; two "thin" warps do only the two inherently ordered updates (a
+//     single warp retires roughly one dependent instruction per 15-25 cycles when 32 warps are
+//     resident, so every instruction moved off the thin warps counts):
+//        prep    (wide) : hash 32 positions, find equal hashes inside the batch with ballots
+//                         (nearest lower peer / last of its group);
+//        insert  (thin) : head[] exchange in position order -- read the old head, publish the
+//                         batch's last position of every hash;
+//        link    (wide) : turn old head / in-batch peer into the prev[] link of every position;
+//        search  (wide) : one lane per position walks that position's chain (<= max_chain
+//                         candidates, compares in the shared-memory ring, 16-bit ring indices);
+//                         every position is searched speculatively, which is what makes the
+//                         chain walk 960-wide;
+//        resolve (wide) : greedy / lazy rule per position, 5 rounds of pointer doubling per batch
+//                         (for every possible entry lane: visited positions, exit, symbol count),
+//                         then two adjacent batches are composed into one 64-position hop;
+//        parse   (thin) : chains the 64-position hops with register shuffles (entry of the next
+//                         hop = exit of this one), counts symbols, cuts blocks every <= 16383
+//                         symbols (lit_bufsize - 1, deflate.ts:323,336);
+//        emit    (wide) : writes the packed symbols of every batch at the index the parse gave it.
+//     The link stage runs at most 2 steps ahead of a searcher, so restricting matches to
+//     32768 - 2*960 bytes keeps every prev[] slot a searcher reads stable: no races, and the output
 //     does not depend on scheduling (tables are reset per segment).
 #include <cstdio>
 #include <cstdlib>
@@ -45,10 +50,10 @@
 namespace {
 
 #ifndef ZS_SEARCH_WARPS
-#define ZS_SEARCH_WARPS 14
+#define ZS_SEARCH_WARPS 30
 #endif
 #ifndef ZS_HASH_BITS
-#define ZS_HASH_BITS 15
+#define ZS_HASH_BITS 14
 #endif
 constexpr int kSearchWarps = ZS_SEARCH_WARPS;
 // The two thin roles get the highest warp ids: the SMSP arbiter favours high warp ids and these
@@ -65,8 +70,9 @@ constexpr unsigned kRing = 65536;      // window ring: position p lives at ring[
 constexpr unsigned kRingGuard = 288;   // ring[kRing + i] mirrors ring[i] so that 8-byte reads never wrap
 // position-indexed rings between the stages (power-of-two sizes: cheap indexing)
 constexpr unsigned pow2_at_least(unsigned v) { unsigned r = 1; while (r < v) r <<= 1; return r; }
-constexpr unsigned kResRing = pow2_at_least(3 * kStep + 64);  // written by search, read by resolve and (two steps later) parse
-constexpr unsigned kMjRing = pow2_at_least(2 * kStep + 64);   // written by resolve, read by parse one step later
+constexpr unsigned kResRing = pow2_at_least(4 * kStep + 64);  // written by search, read by resolve and (three steps later) emit
+constexpr unsigned kMjRing = pow2_at_least(3 * kStep + 64);   // written by resolve, read by parse (one step later) and emit (two)
+constexpr unsigned kPbRing = pow2_at_least(2 * kSearchWarps + 4);  // per pair of batches (entry offset, first symbol index): parse -> emit
 
 struct LevelCfg { int lazy_fn, good, lazy, nice, chain; };
 // CONFIGURATION_TABLE, deflate.ts:86-103
@@ -82,9 +88,11 @@ struct Smem {
     uint8_t ring[kRing + kRingGuard];
     uint16_t head[1 << kHashBits];
     uint16_t prev[32768];
-    uint32_t prep[2 * kStep];  // stage 1 -> 2, double buffered by step parity
+    uint32_t prep[3 * kStep];  // prep -> insert (next step) -> link (the step after): 3 buffers
+    uint16_t oldh[2 * kStep];  // insert -> link: head[] value seen by each position, double buffered
+    uint2 pb[kPbRing];         // parse -> emit, per aligned pair of batches: (entry offset or 64 = nothing to emit, index of its first symbol)
     uint32_t res[kResRing];    // stage 3 -> 4,5: dist (15) | match len << 15 (9, 0 = none) | literal << 24
-    uint2 mj[kMjRing];         // stage 4 -> 5: (visited mask, exit | is_match << 16) of a parse entering the batch at this lane
+    uint2 mj[kMjRing];         // resolve -> parse, emit: (visited mask, packed exits/counts, see resolve) for a parse entering at this lane
     uint32_t seg;              // segment being processed
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
@@ -178,19 +186,19 @@ __device__ __forceinline__ uint32_t prep_batch(const Smem& S, const LzArgs& a, u
     return w;
 }
 
-// ---- stage 2: insert (thin) -----------------------------------------------------------------------
+// ---- stage 2: insert (thin) + link (wide) -----------------------------------------------------------
 // Chains are kept in position order: the predecessor of p is the nearest earlier position with the
 // same hash -- inside the batch (from prep) or head[h]; "none" is encoded as a self link.
-// Only the head[] accesses are ordered (read old head, then publish the batch's last position of
-// every hash); they do not depend on any loaded value, so a whole step's reads and writes are
-// issued back to back and the loaded heads are consumed afterwards (link_batch).
-__device__ __forceinline__ unsigned head_exchange(Smem& S, uint64_t b, uint32_t w) {
+// Only the head[] accesses are ordered (read the old head, then publish the batch's last position of
+// every hash); that is all the thin warp does.  Turning the old head into the prev[] link is
+// independent per position and is done by the wide warps one step later.
+__device__ __forceinline__ void head_exchange(Smem& S, uint64_t b, uint32_t w, uint16_t* oldh) {
     const unsigned h = w & 0x7fffu;
     unsigned old = 0;
     if ((w & PREP_VALID) && !(w & PREP_HAS_PRED)) old = S.head[h];
     if (w & PREP_LAST) S.head[h] = (uint16_t)(b + zs_lane());
+    oldh[zs_lane()] = (uint16_t)old;
     __syncwarp();  // orders this batch's head[] stores before the next batch's loads
-    return old;
 }
 __device__ __forceinline__ void link_batch(Smem& S, uint64_t b, uint64_t lo, uint32_t w, unsigned old) {
     if (w & PREP_VALID) {
@@ -280,9 +288,20 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
 }
 
 // ---- stage 4: resolve (wide) -----------------------------------------------------------------------
-// Batch of 32 positions starting at q0 (chunk-relative, n bytes in the chunk).  Needs the search
-// result of position q0+32 (or q0+32 >= n).
-__device__ __forceinline__ void resolve_batch(Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0) {
+// mj[].y layout: exit (9 bits) | is_match << 9 | popc(visited) << 10 (6 bits) | pair exit - 32 << 16
+// (9 bits) | pair symbol count << 25 (7 bits).  The pair fields are valid for the first batch of an
+// aligned pair of batches: a parse entering the pair at this lane leaves it at "pair exit"
+// (relative to the pair's first position) after emitting "pair symbol count" symbols.
+constexpr unsigned MJ_MATCH = 1u << 9;
+__device__ __forceinline__ unsigned mj_exit(unsigned y) { return y & 0x1ffu; }
+__device__ __forceinline__ unsigned mj_count(unsigned y) { return (y >> 10) & 0x3fu; }
+__device__ __forceinline__ unsigned mj_pair_exit(unsigned y) { return ((y >> 16) & 0x1ffu) + 32u; }
+__device__ __forceinline__ unsigned mj_pair_count(unsigned y) { return y >> 25; }
+
+// One batch of 32 positions starting at q0: greedy / lazy rule per position, then 5 rounds of
+// pointer doubling.  Needs the search result of position q0+32 (or q0+32 >= n).
+__device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0, unsigned& M,
+                                            unsigned& J, bool& is_match) {
     const unsigned lane = zs_lane();
     const uint32_t q = q0 + lane;
     const uint32_t r = q < n ? S.res[res_slot(q)] : 0u;
@@ -292,9 +311,10 @@ __device__ __forceinline__ void resolve_batch(Smem& S, const LevelCfg& cfg, uint
     // deflate_slow's lazy evaluation (deflate.ts:1372-1426): the match at q is dropped for a
     // literal when the match at q+1 is strictly longer and L < max_lazy
     const bool deferred = cfg.lazy_fn && L >= 3 && L < (unsigned)cfg.lazy && Ln > L;
-    const bool is_match = L >= 3 && !deferred;
-    unsigned J = lane + (is_match ? L : 1u);
-    unsigned M = 1u << lane;
+    is_match = L >= 3 && !deferred;
+    // positions past the end of the chunk are terminal and never visited
+    J = q < n ? lane + (is_match ? L : 1u) : 32u;
+    M = q < n ? 1u << lane : 0u;
 #pragma unroll
     for (int round = 0; round < 5; ++round) {
         const unsigned src = J < 32 ? J : lane;
@@ -302,7 +322,28 @@ __device__ __forceinline__ void resolve_batch(Smem& S, const LevelCfg& cfg, uint
         const unsigned Jj = __shfl_sync(ZS_FULL_MASK, J, src);
         if (J < 32) { M |= Mj; J = Jj; }
     }
-    if (q < n) S.mj[mj_slot(q)] = make_uint2(M, J | (is_match ? 0x10000u : 0u));
+}
+
+// An aligned pair of batches [q0, q0+64): both are resolved by the same warp and composed, so that
+// the thin parse needs one hop per 64 positions.
+__device__ __forceinline__ void resolve_pair(Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0) {
+    const unsigned lane = zs_lane();
+    unsigned Ma, Ja, Mb, Jb;
+    bool ma, mb;
+    resolve_one(S, cfg, n, q0, Ma, Ja, ma);
+    resolve_one(S, cfg, n, q0 + 32, Mb, Jb, mb);
+    const unsigned ca = __popc(Ma), cb = __popc(Mb);
+    // entering the pair at this lane of the first batch: where does the parse enter the second?
+    const unsigned xa = Ja - 32u;
+    const unsigned src = xa < 32u ? xa : lane;
+    const unsigned jb = __shfl_sync(ZS_FULL_MASK, Jb, src), cbx = __shfl_sync(ZS_FULL_MASK, cb, src);
+    const unsigned pair_exit = xa < 32u ? 32u + jb : Ja;   // >= 64 unless the chunk ends inside the pair
+    const unsigned pair_cnt = xa < 32u ? ca + cbx : ca;
+    const unsigned pe = pair_exit >= 32u ? pair_exit - 32u : 0u;
+    if (q0 + lane < n)
+        S.mj[mj_slot(q0 + lane)] = make_uint2(Ma, Ja | (ma ? MJ_MATCH : 0u) | (ca << 10) | (pe << 16) | (pair_cnt << 25));
+    if (q0 + 32 + lane < n)
+        S.mj[mj_slot(q0 + 32 + lane)] = make_uint2(Mb, Jb | (mb ? MJ_MATCH : 0u) | (cb << 10));
 }
 
 // ---- stage 5: parse (thin) ---------------------------------------------------------------------------
@@ -328,98 +369,90 @@ __device__ __forceinline__ void close_block(const LzArgs& a, ParseState& ps, uin
     ps.blk_pos0 = pos_end;
 }
 
-__device__ __forceinline__ void parse_batch(const Smem& S, const LzArgs& a, ParseState& ps, uint32_t chunk,
-                                            uint64_t sym_base, uint32_t n, uint32_t q0) {
+// Thin parse: the serial chain only, one hop per aligned pair of batches (64 positions).  For a group
+// of up to kParseGroup pairs starting at qb the entry offset of every pair (0..63, or 64 = nothing
+// to emit) and the index of its first symbol go to the pb ring; the wide warps write the symbols one
+// step later (emit_batch).
+constexpr int kParseGroup = 16;
+__device__ __forceinline__ void parse_group(Smem& S, const LzArgs& a, ParseState& ps, uint32_t chunk, uint32_t n,
+                                            uint32_t qb, int np) {
     const unsigned lane = zs_lane();
-    if (ps.skip >= 32) { ps.skip -= 32; return; }
-    const uint2 e = S.mj[mj_slot(q0 + ps.skip)];  // same address in all lanes: a broadcast
-    unsigned visited = e.x;
-    if (n - q0 < 32) visited &= (1u << (n - q0)) - 1u;
-    const unsigned nv = __popc(visited);
-    if (ps.nsym - ps.blk_sym0 + nv > kSymLimit) {
-        // the open block ends before this batch's first emitted position
-        close_block(a, ps, chunk, q0 + (__ffs(visited) - 1u));
+    unsigned ya[kParseGroup], yb[kParseGroup];   // mj[].y of this lane in the first / second batch of each pair
+#pragma unroll
+    for (int u = 0; u < kParseGroup; ++u) {
+        const uint32_t q = qb + 64u * u + lane;
+        ya[u] = (u < np && q < n) ? S.mj[mj_slot(q)].y : (32u | (32u << 16));
+        yb[u] = (u < np && q + 32 < n) ? S.mj[mj_slot(q + 32)].y : 32u;
     }
+#pragma unroll
+    for (int u = 0; u < kParseGroup; ++u) {
+        if (u < np) {
+            const uint32_t q0 = qb + 64u * u;
+            unsigned entry = 64u, cnt = 0, exit_rel = 0;
+            const uint32_t first_sym = ps.nsym;
+            if (ps.skip >= 64) {
+                ps.skip -= 64;
+            } else {
+                // the serial chain: register shuffles only
+                const unsigned wa = __shfl_sync(ZS_FULL_MASK, ya[u], ps.skip & 31u);
+                const unsigned wb = __shfl_sync(ZS_FULL_MASK, yb[u], ps.skip & 31u);
+                entry = ps.skip;
+                if (ps.skip < 32) { cnt = mj_pair_count(wa); exit_rel = mj_pair_exit(wa); }
+                else { cnt = mj_count(wb); exit_rel = 32u + mj_exit(wb); }
+                if (ps.nsym - ps.blk_sym0 + cnt > kSymLimit) close_block(a, ps, chunk, q0 + entry);  // rare
+                ps.nsym += cnt;
+                ps.skip = exit_rel >= 64u ? exit_rel - 64u : 0u;   // < 64 only where the chunk ends
+            }
+            if (lane == 0) S.pb[(q0 >> 6) & (kPbRing - 1u)] = make_uint2(entry, first_sym);
+        }
+    }
+}
+
+// Wide emit: the symbols of one batch.  The pair's entry offset and first symbol index come from
+// the thin parse; the second batch of a pair derives its own entry from the first batch's table.
+__device__ __forceinline__ void emit_batch(const Smem& S, const LzArgs& a, uint64_t sym_base, uint32_t n, uint32_t q0) {
+    const unsigned lane = zs_lane();
+    const uint2 e = S.pb[(q0 >> 6) & (kPbRing - 1u)];
+    if (e.x >= 64u) return;
+    unsigned entry, first = e.y;
+    if (!(q0 & 32u)) {                     // first batch of the pair
+        if (e.x >= 32u) return;
+        entry = e.x;
+    } else if (e.x >= 32u) {               // the parse entered the pair in its second batch
+        entry = e.x - 32u;
+    } else {                               // through the first batch: continue where it left
+        const unsigned ya = S.mj[mj_slot(q0 - 32u + e.x)].y;
+        const unsigned xa = mj_exit(ya) - 32u;
+        if (xa >= 32u) return;
+        entry = xa;
+        first += mj_count(ya);
+    }
+    const unsigned visited = S.mj[mj_slot(q0 + entry)].x;  // same address in all lanes: a broadcast
     if ((visited >> lane) & 1u) {
-        const uint32_t r = S.res[res_slot(q0 + lane)];
-        const bool is_match = (S.mj[mj_slot(q0 + lane)].y >> 16) & 1u;
+        const uint32_t q = q0 + lane;
+        const uint32_t r = S.res[res_slot(q)];
+        const bool is_match = (S.mj[mj_slot(q)].y & MJ_MATCH) != 0;
         // packed symbol: distance << 16 | length, or the literal byte (distance 0)
-        a.sym[sym_base + ps.nsym + __popc(visited & zs_lanemask_lt())] =
+        a.sym[sym_base + first + __popc(visited & zs_lanemask_lt())] =
             is_match ? (((r & 0x7fffu) << 16) | ((r >> 15) & 0x1ffu)) : (r >> 24);
     }
-    ps.nsym += nv;
-    ps.skip = (n - q0 < 32) ? 0u : (e.y & 0xffffu) - 32u;
 }
 
-// The same for a group of up to kParseGroup batches, arranged for instruction-level parallelism: the
-// only truly serial chain is skip -> mj lookup -> next skip (one shared-memory load per batch);
-// the symbol stores of all batches are independent once that chain is known.
-constexpr int kParseGroup = 16;
-__device__ __forceinline__ void parse_group(const Smem& S, const LzArgs& a, ParseState& ps, uint32_t chunk,
-                                            uint64_t sym_base, uint32_t n, uint32_t qb, int nb, long long t_begin) {
-    const unsigned lane = zs_lane();
-    unsigned vis[kParseGroup];
-    uint32_t base[kParseGroup];
-    uint2 mine[kParseGroup];   // (visited, exit | is_match << 16) for a parse entering at this lane
-#pragma unroll
-    for (int u = 0; u < kParseGroup; ++u) {
-        const uint32_t q = qb + 32u * u + lane;
-        mine[u] = (u < nb && q < n) ? S.mj[mj_slot(q)] : make_uint2(0u, 32u);
-    }
-    uint32_t nsym = ps.nsym, skip = ps.skip;
-#pragma unroll
-    for (int u = 0; u < kParseGroup; ++u) {
-        vis[u] = 0;
-        base[u] = nsym;
-        if (u < nb) {
-            const uint32_t q0 = qb + 32u * u;
-            if (skip >= 32) {
-                skip -= 32;
-            } else {
-                // the serial chain: one register shuffle per batch
-                unsigned v = __shfl_sync(ZS_FULL_MASK, mine[u].x, skip);
-                const unsigned ex = __shfl_sync(ZS_FULL_MASK, mine[u].y, skip) & 0xffffu;
-                if (n - q0 < 32) v &= (1u << (n - q0)) - 1u;
-                vis[u] = v;
-                nsym += __popc(v);
-                skip = (n - q0 < 32) ? 0u : ex - 32u;
-            }
-        }
-    }
-#ifdef ZS_LZ_PROF
-    if (lane == 0) atomicAdd(&g_prof[11], (unsigned long long)(clock64() - t_begin));
-#endif
-    if (nsym - ps.blk_sym0 > kSymLimit) {
-        // a block boundary falls inside this group: take the batch-by-batch path
-        for (int u = 0; u < nb; ++u) parse_batch(S, a, ps, chunk, sym_base, n, qb + 32u * u);
-        return;
-    }
-#pragma unroll
-    for (int u = 0; u < kParseGroup; ++u) {
-        if ((vis[u] >> lane) & 1u) {
-            const uint32_t q = qb + 32u * u + lane;
-            const uint32_t r = S.res[res_slot(q)];
-            const bool is_match = (mine[u].y >> 16) & 1u;
-            a.sym[sym_base + base[u] + __popc(vis[u] & zs_lanemask_lt())] =
-                is_match ? (((r & 0x7fffu) << 16) | ((r >> 15) & 0x1ffu)) : (r >> 24);
-        }
-    }
-    ps.nsym = nsym;
-    ps.skip = skip;
-}
-
-// Searched frontier (exclusive, chunk-relative) at the start of pipeline iteration k: the search
-// of step j runs in iteration j + 2.
+// Pipeline schedule (k = iteration): prep of step k, head exchange of step k-1, link of step k-2,
+// search of step k-3; then, by position: resolve up to resolved_after(k), thin parse up to
+// resolved_after(k-1), emit up to resolved_after(k-2).
+// Searched frontier (exclusive, chunk-relative) at the start of iteration k.
 __device__ __forceinline__ uint32_t searched_at(uint32_t k, uint32_t n) {
-    if (k < 3) return 0;
-    const uint64_t f = (uint64_t)(k - 2) * kStep;
+    if (k < 4) return 0;
+    const uint64_t f = (uint64_t)(k - 3) * kStep;
     return f < n ? (uint32_t)f : n;
 }
-// Resolved frontier after iteration k: batches whose successor position has been searched.
+// Resolved frontier after iteration k: aligned pairs of batches (64 positions) whose successor
+// position has been searched.
 __device__ __forceinline__ uint32_t resolved_after(uint32_t k, uint32_t n) {
     const uint32_t f = searched_at(k, n);
     if (f == n) return n;
-    return f >= 32 ? f - 32 : 0;
+    return f >= 64 ? (f - 1) & ~63u : 0;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
@@ -467,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
             const uint32_t nsteps = (n + kStep - 1) / kStep;
             const uint64_t lo = a.cross ? a.valid_lo : cbase;
             const uint64_t sym_base = cbase - a.org;
-            const uint32_t n_iter = priming ? nsteps + 1 : nsteps + 4;
+            const uint32_t n_iter = priming ? nsteps + 2 : nsteps + 6;
             ParseState ps = {0, 0, 0, 0, 0, 0};
             {   // look-ahead for the first two steps of the range (no-op when already staged)
                 const uint64_t target = (cbase + 2ull * kStep + kRingGuard + 15) & ~15ull;
@@ -481,12 +514,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
             for (uint32_t k = 0; k < n_iter; ++k) {
 #ifdef ZS_LZ_PROF
                 const long long t_begin = clock64();
-#else
-                const long long t_begin = 0;
 #endif
                 if (wid == kWarpInsert) {
                     // Bytes the next iteration reads (prep of step k+1, look-ahead of the search of step
-                    // k-1) replace positions 64 KiB older, which nobody reads any more.  The global
+                    // k-2) replace positions 64 KiB older, which nobody reads any more.  The global
                     // loads are issued first and stored last so that their latency hides behind the
                     // table updates.
                     constexpr int kStageVec = (kStep + 16 + 511) / 512;   // 16-byte vectors per lane and step
@@ -503,21 +534,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                         sv[v] = make_uint4(0, 0, 0, 0);
                         if (pos < stage_to && pos < safe16) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + pos));
                     }
-                    PROF_T(8);
                     if (k >= 1 && k - 1 < nsteps) {
                         const uint64_t sb = cbase + (uint64_t)(k - 1) * kStep;
-                        const uint32_t* pw = S.prep + ((k - 1) & 1u) * kStep;
-                        uint32_t w[kSearchWarps];
-#pragma unroll
-                        for (int u = 0; u < kSearchWarps; ++u) w[u] = pw[32 * u + lane];
-                        PROF_T(9);
-                        unsigned old[kSearchWarps];
-#pragma unroll
-                        for (int u = 0; u < kSearchWarps; ++u) old[u] = head_exchange(S, sb + 32u * u, w[u]);
-#pragma unroll
-                        for (int u = 0; u < kSearchWarps; ++u) link_batch(S, sb + 32u * u, lo, w[u], old[u]);
+                        const uint32_t* pw = S.prep + ((k - 1) % 3u) * kStep;
+                        uint16_t* oh = S.oldh + ((k - 1) & 1u) * kStep;
+#pragma unroll 8
+                        for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, sb + 32u * u, pw[32 * u + lane], oh + 32 * u);
                     }
-                    PROF_T(10);
 #pragma unroll
                     for (int v = 0; v < kStageVec; ++v) {
                         const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
@@ -530,33 +553,45 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                     // anything beyond kStageVec vectors per lane (only after a short first range)
                     if (stage_to > stage_from + 512ull * kStageVec) stage_window(S, a, stage_from + 512ull * kStageVec, stage_to, lane, 32);
                 } else if (wid == kWarpParse) {
-                    if (!priming && k >= 4) {
+                    if (!priming && k >= 5) {
                         const uint32_t upto = resolved_after(k - 1, n);
                         while (ps.ppos < upto) {
-                            int nb = (int)((upto - ps.ppos + 31) / 32);
-                            if (nb > kParseGroup) nb = kParseGroup;
-                            parse_group(S, a, ps, c, sym_base, n, ps.ppos, nb, t_begin);
-                            ps.ppos += 32u * nb;
+                            int np = (int)((upto - ps.ppos + 63) / 64);
+                            if (np > kParseGroup) np = kParseGroup;
+                            parse_group(S, a, ps, c, n, ps.ppos, np);
+                            ps.ppos += 64u * np;
                         }
                     }
                 } else {
-                    // stage 1: prep of step k
+                    // prep of step k
                     if (k < nsteps) {
                         const uint64_t sb = cbase + (uint64_t)k * kStep;
                         const uint64_t se = sb + kStep < cend ? sb + kStep : cend;
-                        S.prep[(k & 1u) * kStep + wid * 32 + lane] = prep_batch(S, a, sb + 32u * wid, se);
+                        S.prep[(k % 3u) * kStep + wid * 32 + lane] = prep_batch(S, a, sb + 32u * wid, se);
+                    }
+                    // link of step k-2 (its head exchange ran in the previous iteration)
+                    if (k >= 2 && k - 2 < nsteps) {
+                        const unsigned i = wid * 32 + lane;
+                        link_batch(S, cbase + (uint64_t)(k - 2) * kStep + 32u * wid, lo, S.prep[((k - 2) % 3u) * kStep + i],
+                                   S.oldh[((k - 2) & 1u) * kStep + i]);
                     }
                     if (!priming) {
-                        // stage 3: search of step k-2
-                        if (k >= 2 && k - 2 < nsteps) {
-                            const uint32_t q = (k - 2) * kStep + wid * 32 + lane;
+                        // search of step k-3
+                        if (k >= 3 && k - 3 < nsteps) {
+                            const uint32_t q = (k - 3) * kStep + wid * 32 + lane;
                             if (q < n) S.res[res_slot(q)] = search_position(S, cfg, cbase + q, cend, lo);
                         }
-                        // stage 4: resolve the batches whose successor was searched before this iteration
-                        if (k >= 3) {
+                        if (k >= 4) {
+                            // resolve the batches whose successor was searched before this iteration
                             const uint32_t from = resolved_after(k - 1, n), upto = resolved_after(k, n);
+                            for (uint32_t q0 = from + 64u * wid; q0 < upto; q0 += 64u * kSearchWarps)
+                                resolve_pair(S, cfg, n, q0);
+                        }
+                        if (k >= 6) {
+                            // emit the batches the thin parse chained in the previous iteration
+                            const uint32_t from = resolved_after(k - 3, n), upto = resolved_after(k - 2, n);
                             for (uint32_t q0 = from + 32u * wid; q0 < upto; q0 += 32u * kSearchWarps)
-                                resolve_batch(S, cfg, n, q0);
+                                emit_batch(S, a, sym_base, n, q0);
                         }
                     }
                 }
