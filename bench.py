@@ -278,7 +278,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("lz77_kernel_dram_bytes_per_launch")
+            # DRAM bytes per input byte from the committed ncu --set full capture, scaled to this launch
+            traffic = json.load(open(tpath))["lz77_kernel_dram_bytes_per_input_byte"] * n
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "lz77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

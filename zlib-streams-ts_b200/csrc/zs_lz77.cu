@@ -170,7 +170,9 @@ __device__ __forceinline__ uint32_t prep_batch(const Smem& S, const LzArgs& a, u
     const bool valid = p < limit && p + 2 < a.data_end;
     unsigned h = 0;
     if (valid) h = hash3(win32(S, p));
-    // lanes with the same hash: kHashBits independent ballots
+    // lanes with the same hash: kHashBits independent ballots (measured faster than one MATCH.ANY,
+    // which iterates over the distinct values: 9.2 k vs 9.7 k cycles per step)
+#ifndef ZS_PREP_MATCH_ANY
     unsigned peers = __ballot_sync(ZS_FULL_MASK, valid);
 #pragma unroll
     for (int bit = 0; bit < (int)kHashBits; ++bit) {
@@ -178,6 +180,9 @@ __device__ __forceinline__ uint32_t prep_batch(const Smem& S, const LzArgs& a, u
         const unsigned bal = __ballot_sync(ZS_FULL_MASK, one);
         peers &= one ? bal : ~bal;
     }
+#else
+    const unsigned peers = __match_any_sync(ZS_FULL_MASK, valid ? h : 0x10000u + lane);
+#endif
     if (!valid) return 0u;
     const unsigned lower = peers & zs_lanemask_lt();
     uint32_t w = h | PREP_VALID;
