@@ -148,3 +148,53 @@ def test_window_wrap_and_long_matches(gpu_ctx, oracle):
     streams = [zlib.compress(pat, 9), zlib.compress(runs, 9), zlib.compress(pat + runs, 1)]
     r = _same_as_oracle(oracle, streams, 15, [len(pat), len(runs), len(pat) + len(runs)])
     assert (r.status == 1).all()
+
+
+def test_thread_per_stream_kernel_matches_oracle(gpu_ctx, oracle, fixtures64, monkeypatch):
+    # big batches (>= 16384 streams) take the thread-per-stream kernel; ZS_INFLATE_TPS forces it for
+    # the sizes used here: same verdicts, bytes and counters as the oracle
+    monkeypatch.setenv("ZS_INFLATE_TPS", "1")
+    rnd = random.Random(21)
+    text = make_text(1 << 20, 13)
+    streams, caps, datas = [], [], []
+    for i in range(1500):
+        n = rnd.choice((0, 1, 5, 100, 700, 4096, 9000))
+        d = rnd.randbytes(n) if i % 17 == 0 else text[i * 600: i * 600 + n]
+        lvl = rnd.choice((0, 1, 6, 9))
+        co = zlib.compressobj(lvl, 8, 31)
+        s = co.compress(d) + co.flush()
+        kind = i % 10
+        cap = len(d)
+        if kind == 7 and len(s) > 30:
+            s = s[: rnd.randrange(11, len(s) - 1)]                        # truncated
+        elif kind == 8 and len(s) > 30:
+            b = bytearray(s); b[rnd.randrange(10, len(s))] ^= 1 << rnd.randrange(8); s = bytes(b)   # corrupted
+        elif kind == 9 and n > 10:
+            cap = n // 2                                                   # output too small
+        streams.append(s); caps.append(cap); datas.append(d)
+    r = _same_as_oracle(oracle, streams, 31, caps)
+    good = [i for i in range(1500) if i % 10 < 7]
+    for i in good:
+        assert int(r.status[i]) == 1 and r.output(i) == datas[i] and int(r.checks[i]) == zlib.crc32(datas[i])
+    # zlib wrapper, raw with dictionary, and deflate64 through the same kernel
+    zs = [zlib.compress(text[i * 512: i * 512 + 3000], 6) for i in range(1100)]
+    r = _same_as_oracle(oracle, zs, 15, [3000] * 1100)
+    assert (r.status == 1).all()
+    dic = text[:20000]
+    raws, dicts = [], []
+    for i in range(1100):
+        co = zlib.compressobj(6, 8, -15, 8, 0, dic)
+        raws.append(co.compress(text[30000 + i * 100: 33000 + i * 100]) + co.flush())
+        dicts.append(dic if i % 2 == 0 else None)
+    r = _same_as_oracle(oracle, raws, -15, [3000] * 1100, dicts)
+    assert int(r.status[0]) == 1 and int(r.status[1]) == -3 and r.message(1) == "invalid distance too far back"
+    f64 = [f for f in fixtures64 if f["out_len"] < 200000]
+    streams = [f64[i % len(f64)]["data"] for i in range(1030)]
+    caps = [f64[i % len(f64)]["out_len"] + 8 for i in range(1030)]
+    r = _same_as_oracle(oracle, streams, -16, caps)
+    for i in range(1030):
+        f = f64[i % len(f64)]
+        assert int(r.status[i]) == 1 and int(r.checks[i]) == f["crc32"], f["name"]
+    kats = [bytes.fromhex("4b1cfdff07a3e5030000")] * 1024
+    r = _run(kats, -16, [70000] * 1024)
+    assert all(r.output(i) == b"a" * 66539 for i in (0, 511, 1023))

@@ -1,6 +1,7 @@
 // zs_api.cu -- the C ABI of include/zsgpu.h: context, batch deflate / inflate / checksum entry points
 // (device-pointer and host-buffer variants).  The streaming shim lives in zs_stream.cu.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -518,6 +519,7 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
     a.d_trailer = misc + n;
     a.d_flags = misc + 3 * (size_t)n;
     a.d_dict = d_dict; a.d_dict_rng = d_dict_rng;
+    a.force_tps = getenv("ZS_INFLATE_TPS") != nullptr;   // test hook: exercise the thread-per-stream kernel on small batches
     uint32_t* d_adler = misc + 4 * (size_t)n;
     uint32_t* d_crc = misc + 5 * (size_t)n;
     int rc = zs_launch_inflate(ctx, a);

@@ -260,7 +260,7 @@ int zs_launch_checksum_segments(zs_ctx* ctx, int kind, const uint8_t* d_buf, con
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;
     if (kind)
-        checksum_segments_kernel<1><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out);
+        ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<1><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
     else
         ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<0><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
     return ZS_OK;
@@ -271,7 +271,7 @@ int zs_launch_checksum_fold(zs_ctx* ctx, int kind, const uint32_t* d_part, const
     int rc = ensure_tables(ctx);
     if (rc != ZS_OK) return rc;
     if (kind)
-        checksum_fold_kernel<1><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result);
+        ZS_KERNEL(ctx, "checksum_fold_kernel", checksum_fold_kernel<1><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result));
     else
         ZS_KERNEL(ctx, "checksum_fold_kernel", checksum_fold_kernel<0><<<1, 1024, 0, ctx->stream>>>(d_part, d_off, n, init, d_result));
     return ZS_OK;
