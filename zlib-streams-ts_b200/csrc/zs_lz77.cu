@@ -161,15 +161,23 @@ __device__ __forceinline__ void stage_window(Smem& S, const LzArgs& a, uint64_t 
 
 __device__ __forceinline__ unsigned hash3(uint32_t w) { return ((w & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
 
+// Per-range constants, all 32-bit: stages address positions by their offset q inside the range.
+struct RangeCtx {
+    uint32_t cb;     // low 32 bits of the range's first absolute position: ring index = (cb + q) & 0xffff
+    uint32_t n;      // bytes in the range
+    uint32_t pre;    // bytes before the range that may be matched, capped at kMaxDist
+    uint32_t tail;   // bytes readable from the range start to the end of the input (saturating)
+};
+
 // ---- stage 1: prep (wide) -----------------------------------------------------------------------
-// 32 consecutive positions starting at b; positions >= limit (end of the range being inserted) or
-// without three readable bytes are not inserted.
-__device__ __forceinline__ uint32_t prep_batch(const Smem& S, const LzArgs& a, uint64_t b, uint64_t limit) {
+// 32 consecutive positions starting at offset q0; positions >= limit (end of the step being inserted)
+// or without three readable bytes are not inserted.
+__device__ __forceinline__ uint32_t prep_batch(const Smem& S, const RangeCtx& c, uint32_t q0, uint32_t limit) {
     const unsigned lane = zs_lane();
-    const uint64_t p = b + lane;
-    const bool valid = p < limit && p + 2 < a.data_end;
+    const uint32_t q = q0 + lane;
+    const bool valid = q < limit && q + 2 < c.tail;
     unsigned h = 0;
-    if (valid) h = hash3(win32(S, p));
+    if (valid) h = hash3(win32(S, c.cb + q));
     // lanes with the same hash: kHashBits independent ballots (measured faster than one MATCH.ANY,
     // which iterates over the distinct values: 9.2 k vs 9.7 k cycles per step)
 #ifndef ZS_PREP_MATCH_ANY
@@ -197,25 +205,26 @@ __device__ __forceinline__ uint32_t prep_batch(const Smem& S, const LzArgs& a, u
 // Only the head[] accesses are ordered (read the old head, then publish the batch's last position of
 // every hash); that is all the thin warp does.  Turning the old head into the prev[] link is
 // independent per position and is done by the wide warps one step later.
-__device__ __forceinline__ void head_exchange(Smem& S, uint64_t b, uint32_t w, uint16_t* oldh) {
+__device__ __forceinline__ void head_exchange(Smem& S, uint32_t p16, uint32_t w, uint16_t* oldh) {
     const unsigned h = w & 0x7fffu;
     unsigned old = 0;
     if ((w & PREP_VALID) && !(w & PREP_HAS_PRED)) old = S.head[h];
-    if (w & PREP_LAST) S.head[h] = (uint16_t)(b + zs_lane());
+    if (w & PREP_LAST) S.head[h] = (uint16_t)(p16 + zs_lane());
     oldh[zs_lane()] = (uint16_t)old;
     __syncwarp();  // orders this batch's head[] stores before the next batch's loads
 }
-__device__ __forceinline__ void link_batch(Smem& S, uint64_t b, uint64_t lo, uint32_t w, unsigned old) {
+__device__ __forceinline__ void link_batch(Smem& S, const RangeCtx& c, uint32_t q0, uint32_t w, unsigned old) {
     if (w & PREP_VALID) {
-        const uint64_t p = b + zs_lane();
-        uint64_t pred = p;
+        const uint32_t q = q0 + zs_lane();
+        const unsigned p16 = (c.cb + q) & 0xffffu;
+        unsigned pred = p16;
         if (w & PREP_HAS_PRED) {
-            pred = b + ((w >> 16) & 31u);
+            pred = (c.cb + q0 + ((w >> 16) & 31u)) & 0xffffu;
         } else {
-            const unsigned delta = ((unsigned)p - old) & 0xffffu;
-            if (delta != 0 && delta <= kMaxDist && p >= lo + delta) pred = p - delta;
+            const unsigned delta = (p16 - old) & 0xffffu;
+            if (delta != 0 && delta <= kMaxDist && delta <= q + c.pre) pred = (p16 - delta) & 0xffffu;
         }
-        S.prev[p & 32767u] = (uint16_t)pred;
+        S.prev[p16 & 32767u] = (uint16_t)pred;
     }
 }
 
@@ -239,17 +248,16 @@ __device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
 }
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
-__device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, uint64_t p, uint64_t chunk_end,
-                                                    uint64_t lo) {
-    const uint64_t room = chunk_end - p;
-    const unsigned max_len = room < 258 ? (unsigned)room : 258u;
-    const unsigned pi = (unsigned)p & (kRing - 1u);
+__device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q) {
+    const uint32_t room = c.n - q;
+    const unsigned max_len = room < 258u ? room : 258u;
+    const unsigned pi = (c.cb + q) & (kRing - 1u);
     const uint32_t pw0 = ring32(S, pi), pw1 = ring32(S, pi + 4);
     const uint32_t lit = (pw0 & 0xffu) << 24;
     if (max_len < 3) return lit;
     const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
-    const uint64_t back = p - lo;
-    const unsigned max_back = back < kMaxDist ? (unsigned)back : kMaxDist;
+    const uint32_t back = q + c.pre;
+    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
     unsigned best_len = 2, best_dist = 0;
     unsigned ci = pi, dist = 0;
     for (int chain = cfg.chain; chain > 0; --chain) {
@@ -444,20 +452,12 @@ __device__ __forceinline__ void emit_batch(const Smem& S, const LzArgs& a, uint6
 }
 
 // Pipeline schedule (k = iteration): prep of step k, head exchange of step k-1, link of step k-2,
-// search of step k-3; then, by position: resolve up to resolved_after(k), thin parse up to
-// resolved_after(k-1), emit up to resolved_after(k-2).
-// Searched frontier (exclusive, chunk-relative) at the start of iteration k.
-__device__ __forceinline__ uint32_t searched_at(uint32_t k, uint32_t n) {
-    if (k < 4) return 0;
-    const uint64_t f = (uint64_t)(k - 3) * kStep;
-    return f < n ? (uint32_t)f : n;
-}
-// Resolved frontier after iteration k: aligned pairs of batches (64 positions) whose successor
-// position has been searched.
-__device__ __forceinline__ uint32_t resolved_after(uint32_t k, uint32_t n) {
-    const uint32_t f = searched_at(k, n);
-    if (f == n) return n;
-    return f >= 64 ? (f - 1) & ~63u : 0;
+// search of step k-3; then, by position: resolve up to R(k), thin parse up to R(k-1), emit up to
+// R(k-2), where R(k) is the resolved frontier after iteration k: the aligned pairs of batches
+// (64 positions) whose successor position was searched before iteration k.
+__device__ __forceinline__ uint32_t resolved_frontier(uint32_t searched, uint32_t n) {
+    if (searched >= n) return n;
+    return searched >= 64 ? (searched - 1) & ~63u : 0;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
@@ -501,9 +501,17 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
             const uint64_t cbase = priming ? prime0 : a.org + a.in_off[c];
             const uint64_t cend = priming ? seg_start : a.org + a.in_off[c + 1];
             if (priming && cbase == cend) continue;
-            const uint32_t n = (uint32_t)(cend - cbase);
+            RangeCtx rc;
+            rc.cb = (uint32_t)cbase;
+            rc.n = (uint32_t)(cend - cbase);
+            {
+                const uint64_t pre = a.cross ? cbase - a.valid_lo : 0;
+                rc.pre = pre < kMaxDist ? (uint32_t)pre : kMaxDist;
+                const uint64_t tail = a.data_end - cbase;
+                rc.tail = tail < 0xffffffffull ? (uint32_t)tail : 0xffffffffu;
+            }
+            const uint32_t n = rc.n;
             const uint32_t nsteps = (n + kStep - 1) / kStep;
-            const uint64_t lo = a.cross ? a.valid_lo : cbase;
             const uint64_t sym_base = cbase - a.org;
             const uint32_t n_iter = priming ? nsteps + 2 : nsteps + 6;
             ParseState ps = {0, 0, 0, 0, 0, 0};
@@ -515,11 +523,20 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 }
                 __syncthreads();
             }
+            // per-iteration uniform state, kept incrementally (no multiplies / 64-bit math in the loop)
+            uint32_t q_prep = 0;                 // first position of the step being prepped (k * kStep)
+            unsigned s_prep = 0;                 // prep[] buffer of step k (k % 3)
+            uint32_t searched = 0;               // positions searched before this iteration
+            uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;   // resolved frontier after iteration k, k-1, k-2, k-3
 
             for (uint32_t k = 0; k < n_iter; ++k) {
 #ifdef ZS_LZ_PROF
                 const long long t_begin = clock64();
 #endif
+                r3 = r2; r2 = r1; r1 = r0;
+                r0 = resolved_frontier(searched, n);
+                const unsigned s_ins = s_prep == 0 ? 2u : s_prep - 1u;     // (k - 1) % 3
+                const unsigned s_link = s_ins == 0 ? 2u : s_ins - 1u;      // (k - 2) % 3
                 if (wid == kWarpInsert) {
                     // Bytes the next iteration reads (prep of step k+1, look-ahead of the search of step
                     // k-2) replace positions 64 KiB older, which nobody reads any more.  The global
@@ -529,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                     uint4 sv[kStageVec];
                     uint64_t stage_from = staged_end, stage_to = staged_end;
                     if (k < nsteps) {
-                        const uint64_t target = (cbase + (uint64_t)(k + 3) * kStep + kRingGuard + 15) & ~15ull;
+                        const uint64_t target = (cbase + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
                         if (target > staged_end) stage_to = target;
                     }
                     const uint64_t safe16 = (a.data_end + 15) & ~15ull;
@@ -540,11 +557,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                         if (pos < stage_to && pos < safe16) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + pos));
                     }
                     if (k >= 1 && k - 1 < nsteps) {
-                        const uint64_t sb = cbase + (uint64_t)(k - 1) * kStep;
-                        const uint32_t* pw = S.prep + ((k - 1) % 3u) * kStep;
+                        const uint32_t p16 = rc.cb + q_prep - kStep;
+                        const uint32_t* pw = S.prep + s_ins * kStep;
                         uint16_t* oh = S.oldh + ((k - 1) & 1u) * kStep;
 #pragma unroll 8
-                        for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, sb + 32u * u, pw[32 * u + lane], oh + 32 * u);
+                        for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, p16 + 32u * u, pw[32 * u + lane], oh + 32 * u);
                     }
 #pragma unroll
                     for (int v = 0; v < kStageVec; ++v) {
@@ -559,44 +576,41 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                     if (stage_to > stage_from + 512ull * kStageVec) stage_window(S, a, stage_from + 512ull * kStageVec, stage_to, lane, 32);
                 } else if (wid == kWarpParse) {
                     if (!priming && k >= 5) {
-                        const uint32_t upto = resolved_after(k - 1, n);
-                        while (ps.ppos < upto) {
-                            int np = (int)((upto - ps.ppos + 63) / 64);
+                        while (ps.ppos < r1) {
+                            int np = (int)((r1 - ps.ppos + 63) / 64);
                             if (np > kParseGroup) np = kParseGroup;
                             parse_group(S, a, ps, c, n, ps.ppos, np);
                             ps.ppos += 64u * np;
                         }
                     }
                 } else {
+                    const unsigned i = wid * 32 + lane;
                     // prep of step k
                     if (k < nsteps) {
-                        const uint64_t sb = cbase + (uint64_t)k * kStep;
-                        const uint64_t se = sb + kStep < cend ? sb + kStep : cend;
-                        S.prep[(k % 3u) * kStep + wid * 32 + lane] = prep_batch(S, a, sb + 32u * wid, se);
+                        const uint32_t se = q_prep + kStep < n ? q_prep + kStep : n;
+                        S.prep[s_prep * kStep + i] = prep_batch(S, rc, q_prep + 32u * wid, se);
                     }
                     // link of step k-2 (its head exchange ran in the previous iteration)
-                    if (k >= 2 && k - 2 < nsteps) {
-                        const unsigned i = wid * 32 + lane;
-                        link_batch(S, cbase + (uint64_t)(k - 2) * kStep + 32u * wid, lo, S.prep[((k - 2) % 3u) * kStep + i],
-                                   S.oldh[((k - 2) & 1u) * kStep + i]);
-                    }
+                    if (k >= 2 && k - 2 < nsteps)
+                        link_batch(S, rc, q_prep - 2u * kStep + 32u * wid, S.prep[s_link * kStep + i], S.oldh[(k & 1u) * kStep + i]);
                     if (!priming) {
                         // search of step k-3
                         if (k >= 3 && k - 3 < nsteps) {
-                            const uint32_t q = (k - 3) * kStep + wid * 32 + lane;
-                            if (q < n) S.res[res_slot(q)] = search_position(S, cfg, cbase + q, cend, lo);
+                            const uint32_t q = q_prep - 3u * kStep + i;
+                            if (q < n) S.res[res_slot(q)] = search_position(S, cfg, rc, q);
                         }
-                        if (k >= 4) {
-                            // resolve the batches whose successor was searched before this iteration
-                            const uint32_t from = resolved_after(k - 1, n), upto = resolved_after(k, n);
-                            for (uint32_t q0 = from + 64u * wid; q0 < upto; q0 += 64u * kSearchWarps)
-                                resolve_pair(S, cfg, n, q0);
-                        }
-                        if (k >= 6) {
-                            // emit the batches the thin parse chained in the previous iteration
-                            const uint32_t from = resolved_after(k - 3, n), upto = resolved_after(k - 2, n);
-                            for (uint32_t q0 = from + 32u * wid; q0 < upto; q0 += 32u * kSearchWarps)
+                        // The lower half of the wide warps resolves (one pair of batches each), the upper half
+                        // emits (one pair each): both are ~150 instructions per pair, so the halves stay balanced.
+                        constexpr unsigned kHalf = kSearchWarps / 2;
+                        if (wid < kHalf) {
+                            // resolve the pairs whose successor was searched before this iteration
+                            for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair(S, cfg, n, q0);
+                        } else {
+                            // emit the pairs the thin parse chained in the previous iteration
+                            for (uint32_t q0 = r3 + 64u * (wid - kHalf); q0 < r2; q0 += 64u * (kSearchWarps - kHalf)) {
                                 emit_batch(S, a, sym_base, n, q0);
+                                if (q0 + 32 < r2) emit_batch(S, a, sym_base, n, q0 + 32);
+                            }
                         }
                     }
                 }
@@ -612,9 +626,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 }
 #endif
                 if (k < nsteps) {
-                    const uint64_t target = (cbase + (uint64_t)(k + 3) * kStep + kRingGuard + 15) & ~15ull;
+                    const uint64_t target = (cbase + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
                     if (target > staged_end) staged_end = target;
                 }
+                // the search of step k-3 ran in this iteration
+                if (k >= 3) searched = searched + kStep < n ? searched + kStep : n;
+                q_prep += kStep;
+                s_prep = s_prep == 2 ? 0u : s_prep + 1u;
                 __syncthreads();
 #ifdef ZS_LZ_PROF
                 if (threadIdx.x == 0) atomicAdd(&g_prof[3], (unsigned long long)(clock64() - t_begin));
