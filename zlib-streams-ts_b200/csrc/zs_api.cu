@@ -136,6 +136,7 @@ void zs_ctx_destroy(zs_ctx* ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_res) cudaStreamDestroy(ctx->s_res);
     for (auto e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->prof) {
@@ -321,14 +322,20 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
                                    int level, int wrap, uint32_t flags, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
                                    uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
     constexpr int kMaxSlices = 16;
-    // slices of whole 16-chunk segments (the LZ77 kernel's segment size for large batches)
-    uint32_t slice_chunks = ((n_chunks / 8u) + 15u) & ~15u;
-    if (slice_chunks < 64) slice_chunks = 64;
+    // Same LZ77 segmentation as the single-shot call over the whole batch; a slice is a whole number
+    // of waves of segments (one segment per SM and wave), so that no SM idles inside a slice.
+    uint32_t seg = n_chunks / (4u * (uint32_t)ctx->sm_count);
+    seg = seg < 1 ? 1 : seg > 16 ? 16 : seg;
+    const uint32_t n_seg = (n_chunks + seg - 1) / seg;
+    const uint32_t wave = (uint32_t)ctx->sm_count;
+    const uint32_t waves_per_slice = (n_seg + wave * kMaxSlices - 1) / (wave * kMaxSlices);
+    const uint32_t slice_chunks = seg * wave * (waves_per_slice < 1 ? 1 : waves_per_slice);
     const int n_slices = (int)((n_chunks + slice_chunks - 1) / slice_chunks);
     if (n_slices > kMaxSlices) return bad_arg(ctx, "deflate: internal slicing error");
     if (!ctx->s_in) {
         ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_res, cudaStreamNonBlocking));
         for (auto& e : ctx->ev) ZS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     if (!ctx->h_pin) {
@@ -354,9 +361,7 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     ZS_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[48], ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev[48], 0));
     ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev[48], 0));
-    // same LZ77 segmentation as the single-shot call over the whole batch
-    uint32_t seg = n_chunks / (4u * (uint32_t)ctx->sm_count);
-    seg = seg < 1 ? 1 : seg > 16 ? 16 : seg;
+    ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_res, ctx->ev[48], 0));
     struct HintGuard { zs_ctx* c; ~HintGuard() { c->seg_hint = 0; } } guard{ctx};
     ctx->seg_hint = seg;
     for (int s = 0; s < n_slices; s++) {
@@ -373,9 +378,11 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
                                       d_obits + c0, want_checks ? d_cks + c0 : nullptr, d_res + s);
         if (rc != ZS_OK) return rc;
         ZS_CUDA_TRY(ctx, cudaEventRecord(ev_k[s], ctx->stream));
-        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ev_k[s], 0));
-        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(h_res + s, d_res + s, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->s_out));
-        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_r[s], ctx->s_out));
+        // The 24-byte results come back on their own stream: the bulk D2H copies below are issued as
+        // each result arrives and must not queue behind the waits for later slices.
+        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_res, ev_k[s], 0));
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(h_res + s, d_res + s, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->s_res));
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_r[s], ctx->s_res));
     }
     uint64_t host_off = 0;
     uint64_t base[kMaxSlices];

@@ -29,7 +29,7 @@ struct zs_ctx {
     int32_t* d_last_detail = nullptr;
     uint32_t last_detail_n = 0;
     // copy streams + events of the pipelined host-buffer path (zs_deflate_batch)
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_res = nullptr;   // host-buffer path: H2D, bulk D2H, small result readbacks
     uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
     cudaEvent_t ev[64] = {nullptr};
     // profiling (zs_ctx_profile)

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) histogram_kernel(HistArgs a) {
     for (unsigned i = threadIdx.x; i < 320; i += 256) h[i] = 0;
     __syncthreads();
     const uint32_t sym0 = a.blk_desc[gid * 4 + 0], nsym = a.blk_desc[gid * 4 + 1];
-    const uint32_t* sym = a.sym + a.in_off[chunk] + sym0;
+    const uint32_t* sym = a.sym + (int64_t)a.in_off[chunk] + (int32_t)sym0;   // sym0 may be negative, see close_block
     for (uint32_t i = threadIdx.x; i < nsym; i += 256) {
         const uint32_t s = sym[i];
         const unsigned dist = s >> 16, lc = s & 0xffffu;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
     }
     __syncthreads();
 
-    const uint32_t* sym = a.sym + cbase + sym0;
+    const uint32_t* sym = a.sym + (int64_t)cbase + (int32_t)sym0;   // sym0 may be negative (zs_lz77.cu, close_block)
     for (uint32_t tile = 0; tile < nsym; tile += kEncThreads) {
         const uint32_t i = tile + t;
         uint64_t v = 0;

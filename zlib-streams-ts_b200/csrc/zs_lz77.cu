@@ -72,7 +72,8 @@ constexpr unsigned kRingGuard = 288;   // ring[kRing + i] mirrors ring[i] so tha
 constexpr unsigned pow2_at_least(unsigned v) { unsigned r = 1; while (r < v) r <<= 1; return r; }
 constexpr unsigned kResRing = pow2_at_least(4 * kStep + 64);  // written by search, read by resolve and (three steps later) emit
 constexpr unsigned kMjRing = pow2_at_least(3 * kStep + 64);   // written by resolve, read by parse (one step later) and emit (two)
-constexpr unsigned kPbRing = pow2_at_least(2 * kSearchWarps + 4);  // per pair of batches (entry offset, first symbol index): parse -> emit
+constexpr unsigned kPbRing = pow2_at_least(2 * kSearchWarps + 4);
+constexpr unsigned kMaxSegChunks = 256;  // chunks per segment (boundary table in shared memory)  // per pair of batches (entry offset, first symbol index): parse -> emit
 
 struct LevelCfg { int lazy_fn, good, lazy, nice, chain; };
 // CONFIGURATION_TABLE, deflate.ts:86-103
@@ -93,6 +94,7 @@ struct Smem {
     uint2 pb[kPbRing];         // parse -> emit, per aligned pair of batches: (entry offset or 64 = nothing to emit, index of its first symbol)
     uint32_t res[kResRing];    // stage 3 -> 4,5: dist (15) | match len << 15 (9, 0 = none) | literal << 24
     uint2 mj[kMjRing];         // resolve -> parse, emit: (visited mask, packed exits/counts, see resolve) for a parse entering at this lane
+    uint32_t bnd[kMaxSegChunks + 1];  // chunk boundaries of the segment, as range offsets (bnd[0] = first data position)
     uint32_t seg;              // segment being processed
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
@@ -162,11 +164,18 @@ __device__ __forceinline__ void stage_window(Smem& S, const LzArgs& a, uint64_t 
 __device__ __forceinline__ unsigned hash3(uint32_t w) { return ((w & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
 
 // Per-range constants, all 32-bit: stages address positions by their offset q inside the range.
+// A range is one whole segment: the <= 32 KiB dictionary before its first chunk (inserted only)
+// followed by its chunks, back to back.  Chunk boundaries only matter to the search (matches stop
+// at the end of their chunk and, without priming, do not reach before its start) and to the parse
+// (blocks and symbol counts are per chunk).
 struct RangeCtx {
     uint32_t cb;     // low 32 bits of the range's first absolute position: ring index = (cb + q) & 0xffff
     uint32_t n;      // bytes in the range
     uint32_t pre;    // bytes before the range that may be matched, capped at kMaxDist
     uint32_t tail;   // bytes readable from the range start to the end of the input (saturating)
+    uint32_t q_data; // first position that is compressed (everything before is dictionary)
+    uint32_t nc;     // chunks in the segment
+    int cross;       // matches may reach before the chunk start
 };
 
 // ---- stage 1: prep (wide) -----------------------------------------------------------------------
@@ -248,15 +257,17 @@ __device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
 }
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
-__device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q) {
-    const uint32_t room = c.n - q;
+// [cs, ce) is the chunk that holds q.
+__device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
+                                                    uint32_t cs, uint32_t ce) {
+    const uint32_t room = ce - q;
     const unsigned max_len = room < 258u ? room : 258u;
     const unsigned pi = (c.cb + q) & (kRing - 1u);
     const uint32_t pw0 = ring32(S, pi), pw1 = ring32(S, pi + 4);
     const uint32_t lit = (pw0 & 0xffu) << 24;
     if (max_len < 3) return lit;
     const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
-    const uint32_t back = q + c.pre;
+    const uint32_t back = c.cross ? q + c.pre : q - cs;
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
     unsigned best_len = 2, best_dist = 0;
     unsigned ci = pi, dist = 0;
@@ -360,21 +371,30 @@ __device__ __forceinline__ void resolve_pair(Smem& S, const LevelCfg& cfg, uint3
 }
 
 // ---- stage 5: parse (thin) ---------------------------------------------------------------------------
+// Positions are range offsets and symbol indices count from the segment's first symbol: the symbols
+// of a segment are stored back to back from the slot of its first input byte, so a chunk boundary
+// inside a batch costs the emit stage nothing.  Blocks and their descriptors are per chunk.
 struct ParseState {
-    uint32_t ppos;       // next batch start, relative to the chunk
-    uint32_t skip;       // leading positions of that batch already covered by an emitted match
-    uint32_t nsym;       // symbols emitted in the chunk
-    uint32_t blk;        // blocks closed in the chunk
+    uint32_t ppos;       // next pair of batches, range offset
+    uint32_t skip;       // leading positions of that pair already covered by an emitted match
+    uint32_t nsym;       // symbols emitted in the segment
+    uint32_t blk;        // blocks closed in the current chunk
     uint32_t blk_sym0;   // first symbol of the open block
-    uint32_t blk_pos0;   // first input position of the open block
+    uint32_t blk_pos0;   // first input position of the open block (range offset)
+    uint32_t jc;         // current chunk of the segment
+    uint32_t cstart;     // its first position
+    uint32_t nb;         // its end = the next boundary (0xffffffff after the last chunk)
 };
 
-__device__ __forceinline__ void close_block(const LzArgs& a, ParseState& ps, uint32_t chunk, uint32_t pos_end) {
+// Block descriptor: first symbol (relative to the slot of the chunk's first byte: negative, as a
+// wrapped 32-bit value, when earlier chunks of the segment produced fewer symbols than bytes),
+// symbols, first input byte (relative to the chunk), input bytes.
+__device__ __forceinline__ void close_block(const LzArgs& a, const RangeCtx& rc, ParseState& ps, uint32_t c0, uint32_t pos_end) {
     if (ps.blk < a.max_bpc && zs_lane() == 0) {  // max_bpc is sized so that the test always holds
-        uint32_t* d = a.blk_desc + ((uint64_t)chunk * a.max_bpc + ps.blk) * 4;
-        d[0] = ps.blk_sym0;
+        uint32_t* d = a.blk_desc + ((uint64_t)(c0 + ps.jc) * a.max_bpc + ps.blk) * 4;
+        d[0] = ps.blk_sym0 - (ps.cstart - rc.q_data);
         d[1] = ps.nsym - ps.blk_sym0;
-        d[2] = ps.blk_pos0;
+        d[2] = ps.blk_pos0 - ps.cstart;
         d[3] = pos_end - ps.blk_pos0;
     }
     ps.blk++;
@@ -382,14 +402,31 @@ __device__ __forceinline__ void close_block(const LzArgs& a, ParseState& ps, uin
     ps.blk_pos0 = pos_end;
 }
 
+// The parse stands on the boundary ps.nb: the final (possibly empty) block of the chunk, next chunk.
+__device__ __forceinline__ void close_chunk(const Smem& S, const LzArgs& a, const RangeCtx& rc, ParseState& ps, uint32_t c0) {
+    close_block(a, rc, ps, c0, ps.nb);
+    if (zs_lane() == 0) a.chunk_nblk[c0 + ps.jc] = ps.blk < a.max_bpc ? ps.blk : a.max_bpc;
+    ps.jc++;
+    ps.cstart = ps.nb;
+    ps.nb = ps.jc < rc.nc ? S.bnd[ps.jc + 1] : 0xffffffffu;
+    ps.blk = 0;
+}
+
+__device__ __forceinline__ unsigned below(unsigned b) { return b >= 32u ? 0xffffffffu : (1u << b) - 1u; }
+
 // Thin parse: the serial chain only, one hop per aligned pair of batches (64 positions).  For a group
 // of up to kParseGroup pairs starting at qb the entry offset of every pair (0..63, or 64 = nothing
 // to emit) and the index of its first symbol go to the pb ring; the wide warps write the symbols one
-// step later (emit_batch).
+// step later (emit_batch).  Matches never cross a chunk boundary, so the chain lands on every
+// boundary; a boundary strictly inside a pair splits the hop (rare: once per chunk).
+// kBoundary = false is the chain without any boundary test, for groups no boundary can touch (every
+// instruction on this chain costs 15-25 cycles).
 constexpr int kParseGroup = 16;
-__device__ __forceinline__ void parse_group(Smem& S, const LzArgs& a, ParseState& ps, uint32_t chunk, uint32_t n,
+template <bool kBoundary>
+__device__ __forceinline__ void parse_group(Smem& S, const LzArgs& a, const RangeCtx& rc, ParseState& ps, uint32_t c0,
                                             uint32_t qb, int np) {
     const unsigned lane = zs_lane();
+    const uint32_t n = rc.n;
     unsigned ya[kParseGroup], yb[kParseGroup];   // mj[].y of this lane in the first / second batch of each pair
 #pragma unroll
     for (int u = 0; u < kParseGroup; ++u) {
@@ -401,20 +438,42 @@ __device__ __forceinline__ void parse_group(Smem& S, const LzArgs& a, ParseState
     for (int u = 0; u < kParseGroup; ++u) {
         if (u < np) {
             const uint32_t q0 = qb + 64u * u;
-            unsigned entry = 64u, cnt = 0, exit_rel = 0;
+            unsigned entry = 64u;
             const uint32_t first_sym = ps.nsym;
             if (ps.skip >= 64) {
                 ps.skip -= 64;
             } else {
+                unsigned s = ps.skip;
+                entry = s;
+                while (kBoundary && ps.nb < q0 + 64u) {
+                    // sub-hop [s, b): the symbols of the visited positions before the boundary
+                    const unsigned b = ps.nb - q0;
+                    unsigned c;
+                    if (s < 32u) {
+                        const uint2 m = S.mj[mj_slot(q0 + s)];
+                        c = __popc(m.x & below(b));
+                        if (b > 32u) {
+                            const unsigned xa = mj_exit(m.y) - 32u;   // < 32: the chain lands on b
+                            c += __popc(S.mj[mj_slot(q0 + 32u + xa)].x & below(b - 32u));
+                        }
+                    } else {
+                        c = __popc(S.mj[mj_slot(q0 + s)].x & below(b - 32u));
+                    }
+                    if (ps.nsym - ps.blk_sym0 + c > kSymLimit) close_block(a, rc, ps, c0, q0 + s);
+                    ps.nsym += c;
+                    close_chunk(S, a, rc, ps, c0);
+                    s = b;
+                }
                 // the serial chain: register shuffles only
-                const unsigned wa = __shfl_sync(ZS_FULL_MASK, ya[u], ps.skip & 31u);
-                const unsigned wb = __shfl_sync(ZS_FULL_MASK, yb[u], ps.skip & 31u);
-                entry = ps.skip;
-                if (ps.skip < 32) { cnt = mj_pair_count(wa); exit_rel = mj_pair_exit(wa); }
+                const unsigned wa = __shfl_sync(ZS_FULL_MASK, ya[u], s & 31u);
+                const unsigned wb = __shfl_sync(ZS_FULL_MASK, yb[u], s & 31u);
+                unsigned cnt, exit_rel;
+                if (s < 32) { cnt = mj_pair_count(wa); exit_rel = mj_pair_exit(wa); }
                 else { cnt = mj_count(wb); exit_rel = 32u + mj_exit(wb); }
-                if (ps.nsym - ps.blk_sym0 + cnt > kSymLimit) close_block(a, ps, chunk, q0 + entry);  // rare
+                if (ps.nsym - ps.blk_sym0 + cnt > kSymLimit) close_block(a, rc, ps, c0, q0 + s);  // rare
                 ps.nsym += cnt;
-                ps.skip = exit_rel >= 64u ? exit_rel - 64u : 0u;   // < 64 only where the chunk ends
+                ps.skip = exit_rel >= 64u ? exit_rel - 64u : 0u;   // < 64 only where the range ends
+                while (kBoundary && ps.nb <= q0 + exit_rel) close_chunk(S, a, rc, ps, c0);   // landed on a boundary
             }
             if (lane == 0) S.pb[(q0 >> 6) & (kPbRing - 1u)] = make_uint2(entry, first_sym);
         }
@@ -477,172 +536,189 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
         const uint32_t c0 = seg * a.seg_chunks;
         const uint32_t c1 = (c0 + a.seg_chunks < a.n_chunks) ? c0 + a.seg_chunks : a.n_chunks;
 
+        const uint32_t nc = c1 - c0;
+
         // fresh tables per segment: the output never depends on which CTA ran which segment
         {
             uint4* z = reinterpret_cast<uint4*>(S.head);
             const unsigned nz = (sizeof(S.head) + sizeof(S.prev)) / sizeof(uint4);
             for (unsigned i = threadIdx.x; i < nz; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         }
-        // Range 0 of a segment is the dictionary (deflateSetDictionary, deflate.ts:367-424): the
-        // <= 32 KiB before the first chunk go through prep + insert only.
-        const uint64_t seg_start = a.org + a.in_off[c0];
+        // The range starts with the dictionary (deflateSetDictionary, deflate.ts:367-424): the
+        // <= 32 KiB before the first chunk go through prep + insert + link only.
+        const uint64_t off0 = a.in_off[c0];
+        const uint64_t seg_start = a.org + off0;
+        const uint64_t seg_end = a.org + a.in_off[c1];
         uint64_t prime0 = seg_start;
         if (a.cross) {
             prime0 = seg_start > a.valid_lo + 32768 ? seg_start - 32768 : a.valid_lo;
             prime0 = (prime0 + 31) & ~31ull;
             if (prime0 > seg_start) prime0 = seg_start;
         }
+        RangeCtx rc;
+        rc.cb = (uint32_t)prime0;
+        rc.n = (uint32_t)(seg_end - prime0);
+        rc.q_data = (uint32_t)(seg_start - prime0);
+        rc.nc = nc;
+        rc.cross = a.cross;
+        {
+            const uint64_t pre = a.cross ? prime0 - a.valid_lo : 0;
+            rc.pre = pre < kMaxDist ? (uint32_t)pre : kMaxDist;
+            const uint64_t tail = a.data_end - prime0;
+            rc.tail = tail < 0xffffffffull ? (uint32_t)tail : 0xffffffffu;
+        }
+        for (unsigned j = threadIdx.x; j <= nc; j += kThreads) S.bnd[j] = (uint32_t)(a.in_off[c0 + j] - off0) + rc.q_data;
         uint64_t staged_end = prime0 & ~15ull;  // [staged_end - 64 KiB, staged_end) is in the ring
+        {   // look-ahead for the first two steps of the range
+            const uint64_t target = (prime0 + 2ull * kStep + kRingGuard + 15) & ~15ull;
+            stage_window(S, a, staged_end, target, threadIdx.x, kThreads);
+            staged_end = target;
+        }
         __syncthreads();
 
-        for (int64_t ci = (int64_t)c0 - 1; ci < (int64_t)c1; ++ci) {
-            const bool priming = ci < (int64_t)c0;
-            const uint32_t c = priming ? c0 : (uint32_t)ci;
-            const uint64_t cbase = priming ? prime0 : a.org + a.in_off[c];
-            const uint64_t cend = priming ? seg_start : a.org + a.in_off[c + 1];
-            if (priming && cbase == cend) continue;
-            RangeCtx rc;
-            rc.cb = (uint32_t)cbase;
-            rc.n = (uint32_t)(cend - cbase);
-            {
-                const uint64_t pre = a.cross ? cbase - a.valid_lo : 0;
-                rc.pre = pre < kMaxDist ? (uint32_t)pre : kMaxDist;
-                const uint64_t tail = a.data_end - cbase;
-                rc.tail = tail < 0xffffffffull ? (uint32_t)tail : 0xffffffffu;
-            }
-            const uint32_t n = rc.n;
-            const uint32_t nsteps = (n + kStep - 1) / kStep;
-            const uint64_t sym_base = cbase - a.org;
-            const uint32_t n_iter = priming ? nsteps + 2 : nsteps + 6;
-            ParseState ps = {0, 0, 0, 0, 0, 0};
-            {   // look-ahead for the first two steps of the range (no-op when already staged)
-                const uint64_t target = (cbase + 2ull * kStep + kRingGuard + 15) & ~15ull;
-                if (target > staged_end) {
-                    stage_window(S, a, staged_end, target, threadIdx.x, kThreads);
-                    staged_end = target;
-                }
-                __syncthreads();
-            }
-            // per-iteration uniform state, kept incrementally (no multiplies / 64-bit math in the loop)
-            uint32_t q_prep = 0;                 // first position of the step being prepped (k * kStep)
-            unsigned s_prep = 0;                 // prep[] buffer of step k (k % 3)
-            uint32_t searched = 0;               // positions searched before this iteration
-            uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;   // resolved frontier after iteration k, k-1, k-2, k-3
+        const uint32_t n = rc.n;
+        const uint32_t nsteps = (n + kStep - 1) / kStep;
+        const uint32_t n_iter = nsteps + 6;
+        const uint32_t qd64 = rc.q_data & ~63u;   // the pair of batches that holds the first data position
+        ParseState ps;
+        ps.ppos = qd64; ps.skip = rc.q_data - qd64; ps.nsym = 0; ps.blk = 0; ps.blk_sym0 = 0; ps.blk_pos0 = rc.q_data;
+        ps.jc = 0; ps.cstart = rc.q_data; ps.nb = S.bnd[1];
+        if (wid == kWarpParse)
+            while (ps.nb <= rc.q_data) close_chunk(S, a, rc, ps, c0);   // leading empty chunks
+        // search: the chunk that holds this warp's batch (only moves forward) and its bounds
+        unsigned js = 0;
+        uint32_t cs_w = rc.q_data, ce_w = S.bnd[1];
+        // per-iteration uniform state, kept incrementally (no multiplies / 64-bit math in the loop)
+        uint32_t q_prep = 0;                 // first position of the step being prepped (k * kStep)
+        unsigned s_prep = 0;                 // prep[] buffer of step k (k % 3)
+        uint32_t searched = 0;               // positions searched before this iteration
+        uint32_t r0 = qd64, r1 = qd64, r2 = qd64, r3 = qd64;   // resolved frontier after iteration k, k-1, k-2, k-3
 
-            for (uint32_t k = 0; k < n_iter; ++k) {
+        for (uint32_t k = 0; k < n_iter; ++k) {
 #ifdef ZS_LZ_PROF
-                const long long t_begin = clock64();
+            const long long t_begin = clock64();
 #endif
-                r3 = r2; r2 = r1; r1 = r0;
-                r0 = resolved_frontier(searched, n);
-                const unsigned s_ins = s_prep == 0 ? 2u : s_prep - 1u;     // (k - 1) % 3
-                const unsigned s_link = s_ins == 0 ? 2u : s_ins - 1u;      // (k - 2) % 3
-                if (wid == kWarpInsert) {
-                    // Bytes the next iteration reads (prep of step k+1, look-ahead of the search of step
-                    // k-2) replace positions 64 KiB older, which nobody reads any more.  The global
-                    // loads are issued first and stored last so that their latency hides behind the
-                    // table updates.
-                    constexpr int kStageVec = (kStep + 16 + 511) / 512;   // 16-byte vectors per lane and step
-                    uint4 sv[kStageVec];
-                    uint64_t stage_from = staged_end, stage_to = staged_end;
-                    if (k < nsteps) {
-                        const uint64_t target = (cbase + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
-                        if (target > staged_end) stage_to = target;
-                    }
-                    const uint64_t safe16 = (a.data_end + 15) & ~15ull;
-#pragma unroll
-                    for (int v = 0; v < kStageVec; ++v) {
-                        const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
-                        sv[v] = make_uint4(0, 0, 0, 0);
-                        if (pos < stage_to && pos < safe16) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + pos));
-                    }
-                    if (k >= 1 && k - 1 < nsteps) {
-                        const uint32_t p16 = rc.cb + q_prep - kStep;
-                        const uint32_t* pw = S.prep + s_ins * kStep;
-                        uint16_t* oh = S.oldh + ((k - 1) & 1u) * kStep;
-#pragma unroll 8
-                        for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, p16 + 32u * u, pw[32 * u + lane], oh + 32 * u);
-                    }
-#pragma unroll
-                    for (int v = 0; v < kStageVec; ++v) {
-                        const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
-                        if (pos < stage_to) {
-                            const unsigned idx = (unsigned)pos & (kRing - 1u);
-                            *reinterpret_cast<uint4*>(S.ring + idx) = sv[v];
-                            if (idx < kRingGuard) *reinterpret_cast<uint4*>(S.ring + kRing + idx) = sv[v];
-                        }
-                    }
-                    // anything beyond kStageVec vectors per lane (only after a short first range)
-                    if (stage_to > stage_from + 512ull * kStageVec) stage_window(S, a, stage_from + 512ull * kStageVec, stage_to, lane, 32);
-                } else if (wid == kWarpParse) {
-                    if (!priming && k >= 5) {
-                        while (ps.ppos < r1) {
-                            int np = (int)((r1 - ps.ppos + 63) / 64);
-                            if (np > kParseGroup) np = kParseGroup;
-                            parse_group(S, a, ps, c, n, ps.ppos, np);
-                            ps.ppos += 64u * np;
-                        }
-                    }
-                } else {
-                    const unsigned i = wid * 32 + lane;
-                    // prep of step k
-                    if (k < nsteps) {
-                        const uint32_t se = q_prep + kStep < n ? q_prep + kStep : n;
-                        S.prep[s_prep * kStep + i] = prep_batch(S, rc, q_prep + 32u * wid, se);
-                    }
-                    // link of step k-2 (its head exchange ran in the previous iteration)
-                    if (k >= 2 && k - 2 < nsteps)
-                        link_batch(S, rc, q_prep - 2u * kStep + 32u * wid, S.prep[s_link * kStep + i], S.oldh[(k & 1u) * kStep + i]);
-                    if (!priming) {
-                        // search of step k-3
-                        if (k >= 3 && k - 3 < nsteps) {
-                            const uint32_t q = q_prep - 3u * kStep + i;
-                            if (q < n) S.res[res_slot(q)] = search_position(S, cfg, rc, q);
-                        }
-                        // The lower half of the wide warps resolves (one pair of batches each), the upper half
-                        // emits (one pair each): both are ~150 instructions per pair, so the halves stay balanced.
-                        constexpr unsigned kHalf = kSearchWarps / 2;
-                        if (wid < kHalf) {
-                            // resolve the pairs whose successor was searched before this iteration
-                            for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair(S, cfg, n, q0);
-                        } else {
-                            // emit the pairs the thin parse chained in the previous iteration
-                            for (uint32_t q0 = r3 + 64u * (wid - kHalf); q0 < r2; q0 += 64u * (kSearchWarps - kHalf)) {
-                                emit_batch(S, a, sym_base, n, q0);
-                                if (q0 + 32 < r2) emit_batch(S, a, sym_base, n, q0 + 32);
-                            }
-                        }
-                    }
-                }
-#ifdef ZS_LZ_PROF
-                {
-                    const long long t_work = clock64() - t_begin;
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int role = wid == kWarpInsert ? 0 : wid == kWarpParse ? 1 : 2;
-                        atomicAdd(&g_prof[role], (unsigned long long)t_work);
-                        if (wid == 0) atomicAdd(&g_prof[4], 1ull);
-                    }
-                }
-#endif
+            r3 = r2; r2 = r1; r1 = r0;
+            r0 = resolved_frontier(searched, n);
+            if (r0 < qd64) r0 = qd64;
+            const unsigned s_ins = s_prep == 0 ? 2u : s_prep - 1u;     // (k - 1) % 3
+            const unsigned s_link = s_ins == 0 ? 2u : s_ins - 1u;      // (k - 2) % 3
+            if (wid == kWarpInsert) {
+                // Bytes the next iteration reads (prep of step k+1, look-ahead of the search of step
+                // k-2) replace positions 64 KiB older, which nobody reads any more.  The global
+                // loads are issued first and stored last so that their latency hides behind the
+                // table updates.
+                constexpr int kStageVec = (kStep + 16 + 511) / 512;   // 16-byte vectors per lane and step
+                uint4 sv[kStageVec];
+                uint64_t stage_from = staged_end, stage_to = staged_end;
                 if (k < nsteps) {
-                    const uint64_t target = (cbase + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
-                    if (target > staged_end) staged_end = target;
+                    const uint64_t target = (prime0 + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
+                    if (target > staged_end) stage_to = target;
                 }
-                // the search of step k-3 ran in this iteration
-                if (k >= 3) searched = searched + kStep < n ? searched + kStep : n;
-                q_prep += kStep;
-                s_prep = s_prep == 2 ? 0u : s_prep + 1u;
-                __syncthreads();
+                const uint64_t safe16 = (a.data_end + 15) & ~15ull;
+#pragma unroll
+                for (int v = 0; v < kStageVec; ++v) {
+                    const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
+                    sv[v] = make_uint4(0, 0, 0, 0);
+                    if (pos < stage_to && pos < safe16) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + pos));
+                }
+                if (k >= 1 && k - 1 < nsteps) {
+                    const uint32_t p16 = rc.cb + q_prep - kStep;
+                    const uint32_t* pw = S.prep + s_ins * kStep;
+                    uint16_t* oh = S.oldh + ((k - 1) & 1u) * kStep;
+#pragma unroll 8
+                    for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, p16 + 32u * u, pw[32 * u + lane], oh + 32 * u);
+                }
+#pragma unroll
+                for (int v = 0; v < kStageVec; ++v) {
+                    const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
+                    if (pos < stage_to) {
+                        const unsigned idx = (unsigned)pos & (kRing - 1u);
+                        *reinterpret_cast<uint4*>(S.ring + idx) = sv[v];
+                        if (idx < kRingGuard) *reinterpret_cast<uint4*>(S.ring + kRing + idx) = sv[v];
+                    }
+                }
+                // anything beyond kStageVec vectors per lane (never with the fixed 3-step look-ahead)
+                if (stage_to > stage_from + 512ull * kStageVec) stage_window(S, a, stage_from + 512ull * kStageVec, stage_to, lane, 32);
+            } else if (wid == kWarpParse) {
+                while (ps.ppos < r1) {
+                    int np = (int)((r1 - ps.ppos + 63) / 64);
+                    if (np > kParseGroup) np = kParseGroup;
+                    // a hop leaves its pair by at most 257 positions
+                    if (ps.nb > ps.ppos + 64u * (unsigned)np + 258u) parse_group<false>(S, a, rc, ps, c0, ps.ppos, np);
+                    else parse_group<true>(S, a, rc, ps, c0, ps.ppos, np);
+                    ps.ppos += 64u * np;
+                }
+            } else {
+                const unsigned i = wid * 32 + lane;
+                // prep of step k
+                if (k < nsteps) {
+                    const uint32_t se = q_prep + kStep < n ? q_prep + kStep : n;
+                    S.prep[s_prep * kStep + i] = prep_batch(S, rc, q_prep + 32u * wid, se);
+                }
+                // link of step k-2 (its head exchange ran in the previous iteration)
+                if (k >= 2 && k - 2 < nsteps)
+                    link_batch(S, rc, q_prep - 2u * kStep + 32u * wid, S.prep[s_link * kStep + i], S.oldh[(k & 1u) * kStep + i]);
+                // search of step k-3: data positions only (the tail of the dictionary inside the first
+                // data pair reads as literals nobody visits)
+                if (k >= 3 && k - 3 < nsteps) {
+                    const uint32_t qw = q_prep - 3u * kStep + 32u * wid;
+                    const uint32_t q = qw + lane;
+                    if (qw + 32u > qd64 && qw < n) {
+                        while (qw >= ce_w) { ++js; cs_w = ce_w; ce_w = S.bnd[js + 1]; }   // qw < n: terminates
+                        uint32_t r = 0;
+                        if (q >= rc.q_data && q < n) {
+                            uint32_t cs = cs_w, ce = ce_w;
+                            if (q >= ce) {   // a boundary inside the batch
+                                unsigned jl = js;
+                                do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
+                            }
+                            r = search_position(S, cfg, rc, q, cs, ce);
+                        }
+                        if (q < n) S.res[res_slot(q)] = r;
+                    }
+                }
+                // The lower half of the wide warps resolves (one pair of batches each), the upper half
+                // emits (one pair each): both are ~150 instructions per pair, so the halves stay balanced.
+                // (Claiming the pairs dynamically from a shared counter was measured: slower at level 1.)
+                constexpr unsigned kHalf = kSearchWarps / 2;
+                if (wid < kHalf) {
+                    // resolve the pairs whose successor was searched before this iteration
+                    for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair(S, cfg, n, q0);
+                } else {
+                    // emit the pairs the thin parse chained in the previous iteration
+                    for (uint32_t q0 = r3 + 64u * (wid - kHalf); q0 < r2; q0 += 64u * (kSearchWarps - kHalf)) {
+                        emit_batch(S, a, off0, n, q0);
+                        if (q0 + 32 < r2) emit_batch(S, a, off0, n, q0 + 32);
+                    }
+                }
+            }
 #ifdef ZS_LZ_PROF
-                if (threadIdx.x == 0) atomicAdd(&g_prof[3], (unsigned long long)(clock64() - t_begin));
+            {
+                const long long t_work = clock64() - t_begin;
+                __syncwarp();
+                if (lane == 0) {
+                    const int role = wid == kWarpInsert ? 0 : wid == kWarpParse ? 1 : 2;
+                    atomicAdd(&g_prof[role], (unsigned long long)t_work);
+                    if (wid == 0) atomicAdd(&g_prof[4], 1ull);
+                }
+            }
 #endif
+            if (k < nsteps) {
+                const uint64_t target = (prime0 + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
+                if (target > staged_end) staged_end = target;
             }
-            if (!priming && wid == kWarpParse) {
-                close_block(a, ps, c, n);  // the final (possibly empty) block of the chunk
-                if (lane == 0) a.chunk_nblk[c] = ps.blk < a.max_bpc ? ps.blk : a.max_bpc;
-            }
+            // the search of step k-3 ran in this iteration
+            if (k >= 3) searched = searched + kStep < n ? searched + kStep : n;
+            q_prep += kStep;
+            s_prep = s_prep == 2 ? 0u : s_prep + 1u;
+            __syncthreads();
+#ifdef ZS_LZ_PROF
+            if (threadIdx.x == 0) atomicAdd(&g_prof[3], (unsigned long long)(clock64() - t_begin));
+#endif
         }
+        if (wid == kWarpParse)
+            while (ps.jc < nc) close_chunk(S, a, rc, ps, c0);   // chunks that end with the range (and empty ones after it)
         __syncthreads();
     }
 }
@@ -668,17 +744,28 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     a.max_bpc = p.max_bpc;
     a.level = p.level;
     a.cross = (p.mode == ZS_MODE_STITCHED || (p.flags & ZS_FLAG_PRIME)) ? 1 : 0;
-    // segments: runs of consecutive chunks sharing one set of hash tables.  With cross-chunk
-    // matching a segment pays one 32 KiB insert-only priming pass; ~4 segments per SM keep the
-    // dynamic scheduler balanced, and small batches fall back to one chunk per segment.
+    // Segments: runs of consecutive chunks that go through the pipeline as one range, sharing one set
+    // of hash tables.  A segment pays the pipeline fill/drain (6 steps) and, with cross-chunk
+    // matching, one 32 KiB insert-only priming pass.
     uint32_t seg_chunks = 1;
     if (a.cross) {
+        // ~4 segments per SM keep the dynamic scheduler balanced; small batches fall back to one chunk
         seg_chunks = p.n_chunks / (4u * (uint32_t)ctx->sm_count);
         if (seg_chunks < 1) seg_chunks = 1;
         if (seg_chunks > 16) seg_chunks = 16;  // fixed for large batches: slicing a batch at multiples of 16 chunks
                                                // (the pipelined host path) then leaves the output unchanged
+    } else {
+        // Independent chunks: the segmentation cannot change the output (a search never looks before
+        // its chunk), so cut a whole number of waves of ~512 KiB segments.
+        uint64_t waves = p.in_len / ((uint64_t)ctx->sm_count * (512u << 10));
+        if (waves < 1) waves = 1;
+        const uint64_t want = waves * (uint64_t)ctx->sm_count;
+        uint64_t sc = (p.n_chunks + want - 1) / want;
+        if (sc < 1) sc = 1;
+        if (sc > kMaxSegChunks) sc = kMaxSegChunks;
+        seg_chunks = (uint32_t)sc;
     }
-    if (a.cross && p.seg_hint) seg_chunks = p.seg_hint;
+    if (a.cross && p.seg_hint) seg_chunks = p.seg_hint < kMaxSegChunks ? p.seg_hint : kMaxSegChunks;
     a.seg_chunks = seg_chunks;
     a.n_seg = (p.n_chunks + seg_chunks - 1) / seg_chunks;
     a.sym = p.d_sym;
