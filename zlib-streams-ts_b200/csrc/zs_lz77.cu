@@ -258,6 +258,7 @@ __device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
 // [cs, ce) is the chunk that holds q.
+template <bool kLazy>
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
                                                     uint32_t cs, uint32_t ce) {
     const uint32_t room = ce - q;
@@ -287,6 +288,13 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
             if (x) {
                 len = 4 + first_diff_byte(x);
             } else {
+                // Eight bytes match.  A candidate that cannot beat the best match is dropped after one
+                // more byte: without this the tail of a run, where every candidate ties, costs
+                // max_chain full compares per position (longest_match's scan_end test, deflate.ts:1063-1081).
+                // (Compiled into the lazy levels only: max_chain <= 32 bounds the damage at levels 1-3, and the
+                // test costs them 6 % through code generation alone.)
+                if (kLazy && best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) continue;   // + 257 stays inside the guard
+#ifdef ZS_OLD_EXT
                 len = 8;
                 while (len < max_len) {
                     const uint64_t y = ring64(S, ci + len) ^ ring64(S, pi + len);
@@ -299,6 +307,32 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
                 }
             }
         }
+#else
+                // 8 bytes per round; the two streams keep their own word alignment and the last word
+                // loaded is carried into the next round (2 + 2 loads per 8 bytes)
+                len = 8;
+                unsigned aa = (ci + 8u) & ~3u, ab = (pi + 8u) & ~3u;            // < kRing + 12: the guard mirrors 288 bytes
+                const unsigned sa = ((ci + 8u) & 3u) * 8u, sb = ((pi + 8u) & 3u) * 8u;
+                uint32_t a0 = *reinterpret_cast<const uint32_t*>(S.ring + aa);
+                uint32_t b0 = *reinterpret_cast<const uint32_t*>(S.ring + ab);
+                while (len < max_len) {
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 4);
+                    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 8);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 4);
+                    const uint32_t b2 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 8);
+                    const uint32_t yl = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+                    const uint32_t yh = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+                    if (yl | yh) {
+                        len += yl ? first_diff_byte(yl) : 4 + first_diff_byte(yh);
+                        break;
+                    }
+                    a0 = a2; b0 = b2;
+                    aa += 8; ab += 8;
+                    len += 8;
+                }
+            }
+        }
+#endif
         if (len > max_len) len = max_len;
         if (len > best_len) {
             best_len = len;
@@ -307,7 +341,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
         }
     }
     if (best_len < 3) return lit;
-    if (cfg.lazy_fn && best_len == 3 && best_dist > kTooFar) return lit;  // deflate.ts:1381-1387
+    if (kLazy && best_len == 3 && best_dist > kTooFar) return lit;  // deflate.ts:1381-1387
     return lit | (best_len << 15) | best_dist;
 }
 
@@ -324,6 +358,7 @@ __device__ __forceinline__ unsigned mj_pair_count(unsigned y) { return y >> 25; 
 
 // One batch of 32 positions starting at q0: greedy / lazy rule per position, then 5 rounds of
 // pointer doubling.  Needs the search result of position q0+32 (or q0+32 >= n).
+template <bool kLazy>
 __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0, unsigned& M,
                                             unsigned& J, bool& is_match) {
     const unsigned lane = zs_lane();
@@ -334,7 +369,7 @@ __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, 
     if (lane == 31) Ln = (q + 1 < n) ? ((S.res[res_slot(q + 1)] >> 15) & 0x1ffu) : 0u;
     // deflate_slow's lazy evaluation (deflate.ts:1372-1426): the match at q is dropped for a
     // literal when the match at q+1 is strictly longer and L < max_lazy
-    const bool deferred = cfg.lazy_fn && L >= 3 && L < (unsigned)cfg.lazy && Ln > L;
+    const bool deferred = kLazy && L >= 3 && L < (unsigned)cfg.lazy && Ln > L;
     is_match = L >= 3 && !deferred;
     // positions past the end of the chunk are terminal and never visited
     J = q < n ? lane + (is_match ? L : 1u) : 32u;
@@ -350,12 +385,13 @@ __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, 
 
 // An aligned pair of batches [q0, q0+64): both are resolved by the same warp and composed, so that
 // the thin parse needs one hop per 64 positions.
+template <bool kLazy>
 __device__ __forceinline__ void resolve_pair(Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0) {
     const unsigned lane = zs_lane();
     unsigned Ma, Ja, Mb, Jb;
     bool ma, mb;
-    resolve_one(S, cfg, n, q0, Ma, Ja, ma);
-    resolve_one(S, cfg, n, q0 + 32, Mb, Jb, mb);
+    resolve_one<kLazy>(S, cfg, n, q0, Ma, Ja, ma);
+    resolve_one<kLazy>(S, cfg, n, q0 + 32, Mb, Jb, mb);
     const unsigned ca = __popc(Ma), cb = __popc(Mb);
     // entering the pair at this lane of the first batch: where does the parse enter the second?
     const unsigned xa = Ja - 32u;
@@ -519,6 +555,8 @@ __device__ __forceinline__ uint32_t resolved_frontier(uint32_t searched, uint32_
     return searched >= 64 ? (searched - 1) & ~63u : 0;
 }
 
+// kLazy: levels 4-9 (deflate_slow's rules); levels 1-3 are the greedy instantiation.
+template <bool kLazy>
 __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -673,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-                            r = search_position(S, cfg, rc, q, cs, ce);
+                            r = search_position<kLazy>(S, cfg, rc, q, cs, ce);
                         }
                         if (q < n) S.res[res_slot(q)] = r;
                     }
@@ -684,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 constexpr unsigned kHalf = kSearchWarps / 2;
                 if (wid < kHalf) {
                     // resolve the pairs whose successor was searched before this iteration
-                    for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair(S, cfg, n, q0);
+                    for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair<kLazy>(S, cfg, n, q0);
                 } else {
                     // emit the pairs the thin parse chained in the previous iteration
                     for (uint32_t q0 = r3 + 64u * (wid - kHalf); q0 < r2; q0 += 64u * (kSearchWarps - kHalf)) {
@@ -728,7 +766,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
 int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     static bool attr_set = false;
     if (!attr_set) {
-        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(Smem)));
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)sizeof(Smem)));
         attr_set = true;
     }
@@ -783,7 +823,11 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     unsigned long long zero[16] = {0};
     cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
 #endif
-    ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+    if (a.level >= 4) {
+        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<true><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+    } else {
+        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<false><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+    }
 #ifdef ZS_LZ_PROF
     {
         unsigned long long pr[16];
