@@ -272,7 +272,13 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
     unsigned best_len = 2, best_dist = 0;
     unsigned ci = pi, dist = 0;
+#ifdef ZS_LZ_PROF_CHAIN
+    unsigned n_cand = 0;
+#endif
     for (int chain = cfg.chain; chain > 0; --chain) {
+#ifdef ZS_LZ_PROF_CHAIN
+        ++n_cand;
+#endif
         const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
         if (delta == 0) break;
         dist += delta;
@@ -293,21 +299,10 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
                 // max_chain full compares per position (longest_match's scan_end test, deflate.ts:1063-1081).
                 // (Compiled into the lazy levels only: max_chain <= 32 bounds the damage at levels 1-3, and the
                 // test costs them 6 % through code generation alone.)
-                if (kLazy && best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) continue;   // + 257 stays inside the guard
-#ifdef ZS_OLD_EXT
-                len = 8;
-                while (len < max_len) {
-                    const uint64_t y = ring64(S, ci + len) ^ ring64(S, pi + len);
-                    if (y) {
-                        const uint32_t yl = (uint32_t)y;
-                        len += yl ? first_diff_byte(yl) : 4 + first_diff_byte((uint32_t)(y >> 32));
-                        break;
-                    }
-                    len += 8;
+                if (kLazy && best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {   // + 257 stays inside the guard
+                    chain -= chain >> 2;   // counts as a tie, see below
+                    continue;
                 }
-            }
-        }
-#else
                 // 8 bytes per round; the two streams keep their own word alignment and the last word
                 // loaded is carried into the next round (2 + 2 loads per 8 bytes)
                 len = 8;
@@ -332,14 +327,33 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
                 }
             }
         }
-#endif
         if (len > max_len) len = max_len;
         if (len > best_len) {
+            // With a good match in hand the rest of the chain gets a quarter of the budget (the rule
+            // longest_match applies when the previous position's match was good, deflate.ts:1069-1071).
+            // If the match also extends backwards, q lies inside a longer match that started earlier:
+            // the reference never searches such a position (deflate_slow skips the bytes a match
+            // covers), the speculative search here cannot skip it but stops after a few more candidates.
+            if (kLazy && best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
+                chain >>= 2;
+                if (chain > 4 && S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)]) chain = 4;
+            }
             best_len = len;
             best_dist = dist;
             if (len >= nice) break;
+        } else if (kLazy && len == best_len) {
+            // A candidate that ties with the best match means periodic data (a run, a ramp): the rest
+            // of the chain is more of the same.  Every tie takes a quarter off the remaining budget,
+            // which bounds a chain of ties at ~4 log(max_chain) candidates.  (The reference never gets
+            // here: it does not search the positions a match covers.)
+            chain -= chain >> 2;
         }
     }
+#ifdef ZS_LZ_PROF_CHAIN   // with ZS_LZ_PROF: chain-walk statistics (perturbs the cycle counters)
+    atomicAdd(&g_prof[12], (unsigned long long)n_cand);
+    atomicMax(&g_prof[13], (unsigned long long)n_cand);
+    if (n_cand > 100) { atomicAdd(&g_prof[14], 1ull); g_prof[15] = ((unsigned long long)best_len << 32) | (q - cs); }
+#endif
     if (best_len < 3) return lit;
     if (kLazy && best_len == 3 && best_dist > kTooFar) return lit;  // deflate.ts:1381-1387
     return lit | (best_len << 15) | best_dist;
@@ -836,6 +850,8 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
         double st = pr[4] ? (double)pr[4] : 1.0;
         fprintf(stderr, "[lz77 prof] level %d steps %llu  cycles/step: insert %.0f parse %.0f wide(avg warp) %.0f step %.0f | insert: ldg-issued %.0f prep-loaded %.0f inserted %.0f | parse chain done %.0f\n",
                 p.level, pr[4], pr[0] / st, pr[1] / st, pr[2] / st / kSearchWarps, pr[3] / st, pr[8] / st, pr[9] / st, pr[10] / st, pr[11] / st);
+        fprintf(stderr, "[lz77 prof] chain-loop iterations: total %llu max %llu positions>100: %llu (last: best_len %llu at chunk offset %llu)\n",
+                pr[12], pr[13], pr[14], pr[15] >> 32, pr[15] & 0xffffffffull);
     }
 #endif
     return ZS_OK;
