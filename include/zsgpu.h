@@ -146,6 +146,17 @@ ZS_API int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, con
  * `dst_bit_off`.  The destination bits must be zero beforehand. */
 ZS_API int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits);
 
+/* The Huffman stage alone, for n blocks given by their symbol frequencies: build_tree / gen_bitlen /
+ * gen_codes (trees.ts:54-76,167-316), build_bl_tree (:416-432) and the stored / static / dynamic
+ * choice of _tr_flush_block (:544-583).  freq[n][320]: 286 literal/length counters at 0.., 30
+ * distance counters at 288.. (END_BLOCK is added by the engine); in_len[n]: input bytes of each
+ * block, for the stored-block test.  Outputs (each may be NULL): code[n][320] = code | length << 16
+ * of the chosen trees, type[n] (0 stored, 1 static, 2 dynamic), bits[n] = block size in bits
+ * without alignment padding.  Host buffers; this is what the parity tests compare with the oracle's
+ * build_tree. */
+ZS_API int zs_huffman_blocks(zs_ctx* ctx, const uint32_t* freq, const uint32_t* in_len, uint32_t n, uint32_t* code,
+                      uint32_t* type, uint64_t* bits);
+
 /* ---- inflate: replaces inflate_fast (inffast.ts:5), inflate_table (inftrees.ts:62) and the
  *      block/header/trailer modes of inflate() (inflate.ts:332-1100) for whole streams ---- */
 /*

@@ -288,3 +288,23 @@ def crc32_combine(c1: int, c2: int, len2: int) -> int:
 
 def adler32_combine(a1: int, a2: int, len2: int) -> int:
     return int(capi.load().zs_adler32_combine(a1, a2, len2))
+
+
+def huffman_blocks(freq, in_len, ctx: Context | None = None):
+    """Huffman stage alone (zs_huffman_blocks): freq uint32 [n, 320], in_len uint32 [n] (numpy, host).
+
+    Returns (code [n, 320] uint32 = code | length << 16, type [n] uint32, bits [n] uint64)."""
+    import numpy as np
+    freq = np.ascontiguousarray(freq, dtype=np.uint32)
+    in_len = np.ascontiguousarray(in_len, dtype=np.uint32)
+    n = freq.shape[0]
+    assert freq.shape == (n, 320) and in_len.shape == (n,)
+    ctx = ctx or default_context(0)
+    code = np.zeros((n, 320), dtype=np.uint32)
+    typ = np.zeros(n, dtype=np.uint32)
+    bits = np.zeros(n, dtype=np.uint64)
+    rc = capi.load().zs_huffman_blocks(ctx.handle, freq.ctypes.data, in_len.ctypes.data, n, code.ctypes.data,
+                                       typ.ctypes.data, bits.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"zs_huffman_blocks failed: {rc} {ctx.last_error()}")
+    return code, typ, bits

@@ -21,6 +21,7 @@
 //    whole 32-bit words (boundary words with atomicOr, the output having been zeroed).  Blocks
 //    land directly at their final bit offset: the stitch is fused into the encode.
 #include <cstdio>
+#include <vector>
 
 #include "zs_common.cuh"
 
@@ -749,6 +750,11 @@ __global__ void bit_concat_kernel(uint32_t* dst32, uint64_t dst_off, const uint8
 
 }  // namespace
 
+static int zs_launch_huff_build(zs_ctx* ctx, const HuffArgs& h, uint64_t nblk_slots) {
+    ZS_KERNEL(ctx, "huff_build_kernel", huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h));
+    return ZS_OK;
+}
+
 int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     const uint64_t nblk_slots = (uint64_t)p.n_chunks * p.max_bpc;
     if (nblk_slots == 0) return ZS_OK;
@@ -759,7 +765,10 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     HistArgs hs = {p.n_chunks, p.max_bpc, p.d_in_off, p.d_chunk_nblk, p.d_blk_desc, p.d_sym, p.d_blk_freq};
     ZS_KERNEL(ctx, "histogram_kernel", histogram_kernel<<<(unsigned)nblk_slots, 256, 0, ctx->stream>>>(hs));
     HuffArgs h = {p.n_chunks, p.max_bpc, p.d_chunk_nblk, p.d_blk_desc, p.d_blk_freq, p.d_blk_code, p.d_blk_hdr, p.d_blk_bits};
-    ZS_KERNEL(ctx, "huff_build_kernel", huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h));
+    {
+        const int rc = zs_launch_huff_build(ctx, h, nblk_slots);
+        if (rc != ZS_OK) return rc;
+    }
 
     LayoutArgs l;
     l.n_chunks = p.n_chunks; l.max_bpc = p.max_bpc; l.wrap = p.wrap; l.mode = p.mode; l.flags = p.flags;
@@ -796,4 +805,43 @@ int zs_launch_bit_concat(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, cons
     if (blocks > cap) blocks = cap;
     ZS_KERNEL(ctx, "bit_concat_kernel", bit_concat_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst32, off, d_src, n_bits));
     return ZS_OK;
+}
+
+// Host-buffer entry point for the Huffman stage alone (parity tests): every block is its own chunk.
+extern "C" int zs_huffman_blocks(zs_ctx* ctx, const uint32_t* freq, const uint32_t* in_len, uint32_t n, uint32_t* code,
+                                 uint32_t* type, uint64_t* bits) {
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (n == 0) return ZS_OK;
+    if (!freq || !in_len) return ZS_STREAM_ERROR;
+    uint32_t *d_freq = nullptr, *d_nblk = nullptr, *d_desc = nullptr, *d_code = nullptr, *d_hdr = nullptr;
+    uint64_t* d_bits = nullptr;
+    std::vector<uint32_t> ones(n, 1u), desc((size_t)n * 4, 0u), hdr((size_t)n * kHdrWords);
+    for (uint32_t i = 0; i < n; i++) desc[(size_t)i * 4 + 3] = in_len[i];
+    int rc = ZS_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == ZS_OK) { snprintf(ctx->err, sizeof(ctx->err), "huffman_blocks: %s", cudaGetErrorString(e)); rc = ZS_E_CUDA; } };
+    fail(cudaMalloc(&d_freq, (size_t)n * 320 * 4));
+    fail(cudaMalloc(&d_nblk, (size_t)n * 4));
+    fail(cudaMalloc(&d_desc, (size_t)n * 16));
+    fail(cudaMalloc(&d_code, (size_t)n * 320 * 4));
+    fail(cudaMalloc(&d_hdr, (size_t)n * kHdrWords * 4));
+    fail(cudaMalloc(&d_bits, (size_t)n * 8));
+    if (rc == ZS_OK) {
+        fail(cudaMemcpyAsync(d_freq, freq, (size_t)n * 320 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        fail(cudaMemcpyAsync(d_nblk, ones.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        fail(cudaMemcpyAsync(d_desc, desc.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+        fail(cudaMemsetAsync(d_code, 0, (size_t)n * 320 * 4, ctx->stream));
+    }
+    if (rc == ZS_OK) {
+        HuffArgs h = {n, 1u, d_nblk, d_desc, d_freq, d_code, d_hdr, d_bits};
+        rc = zs_launch_huff_build(ctx, h, n);
+    }
+    if (rc == ZS_OK) {
+        if (code) fail(cudaMemcpyAsync(code, d_code, (size_t)n * 320 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bits) fail(cudaMemcpyAsync(bits, d_bits, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        fail(cudaMemcpyAsync(hdr.data(), d_hdr, (size_t)n * kHdrWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        fail(cudaStreamSynchronize(ctx->stream));
+        if (type && rc == ZS_OK) for (uint32_t i = 0; i < n; i++) type[i] = hdr[(size_t)i * kHdrWords] & 0xffu;
+    }
+    cudaFree(d_freq); cudaFree(d_nblk); cudaFree(d_desc); cudaFree(d_code); cudaFree(d_hdr); cudaFree(d_bits);
+    return rc;
 }
