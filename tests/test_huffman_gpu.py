@@ -56,7 +56,10 @@ def _cases():
     return np.stack(cases)
 
 
-def test_code_lengths_and_codes_equal_reference(gpu_ctx, oracle):
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_code_lengths_and_codes_equal_reference(gpu_ctx, oracle, monkeypatch, kernel):
+    # both Huffman kernels (warp per block / thread per block; the engine picks by block count)
+    monkeypatch.setenv("ZS_HUFF_TPB" if kernel == "thread" else "ZS_HUFF_WARP", "1")
     B = pkg("batch")
     freq = _cases()
     in_len = np.full(freq.shape[0], 1 << 30, np.uint32) & 0xffff0000   # never "stored"

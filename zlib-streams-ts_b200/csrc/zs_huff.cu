@@ -21,6 +21,7 @@
 //    whole 32-bit words (boundary words with atomicOr, the output having been zeroed).  Blocks
 //    land directly at their final bit offset: the stitch is fused into the encode.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "zs_common.cuh"
@@ -33,19 +34,24 @@ constexpr uint32_t BT_STORED = 0, BT_STATIC = 1, BT_DYNAMIC = 2;
 
 __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// ---- Huffman construction (thread-private, local memory) ---------------------------------------
-struct Tree {
-    uint16_t freq[HEAP_SIZE];
-    uint16_t dad[HEAP_SIZE];
-    uint16_t len[HEAP_SIZE];
-    int max_code;
-};
-struct Heap {
-    uint16_t heap[HEAP_SIZE + 1];
-    uint8_t depth[HEAP_SIZE];
-    int heap_len, heap_max;
-    uint16_t bl_count[16];
-    uint32_t opt_len, static_len;
+// ---- Huffman construction: one warp per block, everything in shared memory ----------------------
+// The reference's heap (pqdownheap) is not a total order -- ties between equal (frequency, depth)
+// pairs are decided by where the entries sit in the heap -- so reproducing its code lengths means
+// running the same heap, serially.  Lane 0 does that on a compact layout: a heap entry carries its
+// own key (frequency << 16 | depth << 10 | node), so a sift step is one 8-byte shared-memory load of
+// the two children and one store, instead of six scattered loads.  Everything around the heap is
+// lane-parallel: compaction of the non-zero symbols, leaf depths (every lane climbs dad[] from its
+// leaves), bit-length counts, the opt_len / static_len sums, canonical code assignment (one lane per
+// code length) and the coalesced stores of the code table.
+constexpr int kHuffWarps = 8;
+struct HuffWs {
+    uint32_t heap[HEAP_SIZE + 3];   // [1 .. heap_len] the heap, [heap_max ..] nodes in extraction order; later: code staging
+    uint16_t dad[HEAP_SIZE + 3];
+    uint8_t len[HEAP_SIZE + 3];     // serial gen_bitlen only: lengths of all nodes
+    uint8_t llen[288], dlen[32], blen[32];   // final code lengths of the three trees
+    uint32_t bl_count[16];
+    uint32_t bl_freq[20];
+    uint16_t lnext[16], dnext[16], bnext[16];
 };
 
 __device__ __forceinline__ unsigned static_llen(unsigned n) { return n < 144 ? 8u : n < 256 ? 9u : n < 280 ? 7u : 8u; }
@@ -62,112 +68,178 @@ __device__ __forceinline__ unsigned extra_bits(int kind, unsigned n) {
     return bl_xbits(n);
 }
 
-__device__ __forceinline__ bool smaller(const Tree& t, const Heap& h, int n, int m) {
-    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && h.depth[n] <= h.depth[m]);
-}
+__device__ __forceinline__ unsigned he_key(uint32_t e) { return e >> 10; }    // (frequency, depth)
+__device__ __forceinline__ unsigned he_node(uint32_t e) { return e & 1023u; }
 
-// pqdownheap, trees.ts:167-185
-__device__ void sift_down(const Tree& t, Heap& h, int k) {
-    const int v = h.heap[k];
+// pqdownheap, trees.ts:167-185.  smaller(n, m) of the reference is key(n) <= key(m).
+__device__ __forceinline__ void sift_down(uint32_t* heap, int heap_len, int k) {
+    const uint32_t v = heap[k];
     int j = k << 1;
-    while (j <= h.heap_len) {
-        if (j < h.heap_len && smaller(t, h, h.heap[j + 1], h.heap[j])) j++;
-        if (smaller(t, h, v, h.heap[j])) break;
-        h.heap[k] = h.heap[j];
+    while (j <= heap_len) {
+        const uint2 c = *reinterpret_cast<const uint2*>(heap + j);   // children j, j+1 (j is even; heap[] has a spare slot)
+        uint32_t e = c.x;
+        if (j < heap_len && he_key(c.y) <= he_key(c.x)) { e = c.y; j++; }
+        if (he_key(v) <= he_key(e)) break;
+        heap[k] = e;
         k = j;
         j <<= 1;
     }
-    h.heap[k] = (uint16_t)v;
+    heap[k] = v;
 }
 
-// gen_bitlen, trees.ts:187-259
-__device__ void gen_bitlen(Tree& t, Heap& h, int kind, int max_length) {
-    int hh, n, m, bits, overflow = 0;
-    for (bits = 0; bits <= 15; bits++) h.bl_count[bits] = 0;
-    t.len[h.heap[h.heap_max]] = 0;
-    for (hh = h.heap_max + 1; hh < HEAP_SIZE; hh++) {
-        n = h.heap[hh];
-        bits = t.len[t.dad[n]] + 1;
-        if (bits > max_length) { bits = max_length; overflow++; }
-        t.len[n] = (uint16_t)bits;
-        if (n > t.max_code) continue;
-        h.bl_count[bits]++;
-        const unsigned xb = extra_bits(kind, (unsigned)n);
-        const uint32_t f = t.freq[n];
-        h.opt_len += f * ((uint32_t)bits + xb);
-        if (kind == 0) h.static_len += f * (static_llen((unsigned)n) + xb);
-        else if (kind == 1) h.static_len += f * (5u + xb);
+// build_tree (trees.ts:261-316) + gen_bitlen (:187-259) for one tree, by one warp.  freq_of(n) gives
+// the 16-bit frequency of symbol n.  Results: out_len[0 .. elems), w.bl_count, next codes, max_code;
+// opt_len / static_len are advanced exactly as the reference does.
+template <int KIND, typename FreqFn>
+__device__ void build_tree_warp(HuffWs& w, FreqFn freq_of, uint8_t* out_len, uint16_t* next_out, int& max_code_out,
+                                uint32_t& opt_len, uint32_t& static_len) {
+    constexpr int elems = KIND == 0 ? L_CODES : KIND == 1 ? D_CODES : BL_CODES;
+    constexpr int max_length = KIND == 2 ? 7 : 15;
+    const unsigned lane = zs_lane();
+    // the non-zero symbols, in symbol order, become heap[1 .. heap_len]
+    int heap_len = 0, max_code = -1;
+    for (int base = 0; base < elems; base += 32) {
+        const int n = base + (int)lane;
+        const unsigned f = n < elems ? (freq_of(n) & 0xffffu) : 0u;
+        const unsigned bal = __ballot_sync(ZS_FULL_MASK, f != 0);
+        if (f != 0) w.heap[heap_len + 1 + __popc(bal & zs_lanemask_lt())] = (f << 16) | (unsigned)n;
+        if (n < elems) out_len[n] = 0;
+        if (bal) max_code = base + 31 - __clz(bal);
+        heap_len += __popc(bal);
     }
-    if (overflow == 0) return;
-    do {
-        bits = max_length - 1;
-        while (h.bl_count[bits] == 0) bits--;
-        h.bl_count[bits]--;
-        h.bl_count[bits + 1] += 2;
-        h.bl_count[max_length]--;
-        overflow -= 2;
-    } while (overflow > 0);
-    for (bits = max_length; bits != 0; bits--) {
-        n = h.bl_count[bits];
-        while (n != 0) {
-            m = h.heap[--hh];
-            if (m > t.max_code) continue;
-            if (t.len[m] != (unsigned)bits) {
-                h.opt_len += (uint32_t)(((int)bits - (int)t.len[m]) * (int)t.freq[m]);
-                t.len[m] = (uint16_t)bits;
-            }
-            n--;
+    if (lane < 16) w.bl_count[lane] = 0;
+    // force at least two codes of non-zero frequency (trees.ts:280-288)
+    unsigned phantom = 0;   // bit n: symbol n was given frequency 1
+    while (heap_len < 2) {
+        const int node = max_code < 2 ? ++max_code : 0;
+        if (lane == 0) w.heap[heap_len + 1] = (1u << 16) | (unsigned)node;
+        heap_len++;
+        phantom |= 1u << node;
+        opt_len--;
+        if (KIND == 0) static_len -= static_llen((unsigned)node);
+        else if (KIND == 1) static_len -= 5u;
+    }
+    __syncwarp();
+    int heap_max = HEAP_SIZE;
+    if (lane == 0) {
+        uint32_t* heap = w.heap;
+        for (int n = heap_len / 2; n >= 1; n--) sift_down(heap, heap_len, n);
+        int node = elems, hl = heap_len;
+        do {
+            const uint32_t en = heap[1];
+            heap[1] = heap[hl--];
+            sift_down(heap, hl, 1);
+            const uint32_t em = heap[1];
+            heap[--heap_max] = en;
+            heap[--heap_max] = em;
+            const unsigned f = ((en >> 16) + (em >> 16)) & 0xffffu;   // 16-bit counters like the reference's
+            const unsigned dn = (en >> 10) & 63u, dm = (em >> 10) & 63u;
+            const unsigned d = (dn >= dm ? dn : dm) + 1u;
+            w.dad[he_node(en)] = w.dad[he_node(em)] = (uint16_t)node;
+            heap[1] = (f << 16) | (d << 10) | (unsigned)node++;
+            sift_down(heap, hl, 1);
+        } while (hl >= 2);
+        heap[--heap_max] = heap[1];
+    }
+    heap_max = HEAP_SIZE - (2 * (heap_len - 1) + 1);   // what lane 0 ended with
+    __syncwarp();
+    const unsigned root = he_node(w.heap[heap_max]);
+    // leaf depths: every lane climbs dad[] from its own leaves
+    bool overflow = false;
+    for (int base = 0; base <= max_code; base += 32) {
+        const int n = base + (int)lane;
+        if (n <= max_code && ((freq_of(n) & 0xffffu) != 0 || (n < 3 && ((phantom >> n) & 1u)))) {
+            unsigned d = 0, x = (unsigned)n;
+            while (x != root) { x = w.dad[x]; d++; }
+            if (d > (unsigned)max_length) overflow = true;
+            else { out_len[n] = (uint8_t)d; atomicAdd(&w.bl_count[d], 1u); }
         }
     }
-}
-
-// build_tree, trees.ts:261-316 (gen_codes is applied by the caller, which needs only bl_count)
-__device__ void build_tree(Tree& t, Heap& h, int kind) {
-    const int elems = kind == 0 ? L_CODES : kind == 1 ? D_CODES : BL_CODES;
-    const int max_length = kind == 2 ? 7 : 15;
-    int n, m, node, max_code = -1;
-    h.heap_len = 0;
-    h.heap_max = HEAP_SIZE;
-    for (n = 0; n < elems; n++) {
-        if (t.freq[n] != 0) { h.heap[++h.heap_len] = (uint16_t)(max_code = n); h.depth[n] = 0; }
-        else t.len[n] = 0;
+    overflow = __any_sync(ZS_FULL_MASK, overflow);
+    __syncwarp();
+    if (overflow) {
+        // the reference's clamp-and-repair, serially, in its own order (rare: needs a tree deeper than
+        // max_length)
+        if (lane == 0) {
+            for (int b = 0; b < 16; b++) w.bl_count[b] = 0;
+            int over = 0, h;
+            w.len[root] = 0;
+            for (h = heap_max + 1; h < HEAP_SIZE; h++) {
+                const int n = (int)he_node(w.heap[h]);
+                int bits = w.len[w.dad[n]] + 1;
+                if (bits > max_length) { bits = max_length; over++; }
+                w.len[n] = (uint8_t)bits;
+                if (n > max_code) continue;
+                w.bl_count[bits]++;
+            }
+            do {
+                int bits = max_length - 1;
+                while (w.bl_count[bits] == 0) bits--;
+                w.bl_count[bits]--;
+                w.bl_count[bits + 1] += 2;
+                w.bl_count[max_length]--;
+                over -= 2;
+            } while (over > 0);
+            for (int bits = max_length; bits != 0; bits--) {
+                int n = (int)w.bl_count[bits];
+                while (n != 0) {
+                    const int m = (int)he_node(w.heap[--h]);
+                    if (m > max_code) continue;
+                    w.len[m] = (uint8_t)bits;
+                    n--;
+                }
+            }
+            for (int n = 0; n <= max_code; n++) out_len[n] = 0;
+            for (h = heap_max; h < HEAP_SIZE; h++) {
+                const int n = (int)he_node(w.heap[h]);
+                if (n <= max_code) out_len[n] = w.len[n];
+            }
+        }
+        __syncwarp();
     }
-    while (h.heap_len < 2) {
-        node = h.heap[++h.heap_len] = (uint16_t)(max_code < 2 ? ++max_code : 0);
-        t.freq[node] = 1;
-        h.depth[node] = 0;
-        h.opt_len--;
-        if (kind == 0) h.static_len -= static_llen((unsigned)node);
-        else if (kind == 1) h.static_len -= 5u;
+    // opt_len / static_len: sums over the leaves (the reference accumulates the same terms while it
+    // assigns and repairs the lengths)
+    uint32_t so = 0, ss = 0;
+    for (int base = 0; base <= max_code; base += 32) {
+        const int n = base + (int)lane;
+        if (n <= max_code) {
+            const unsigned l = out_len[n];
+            if (l) {
+                const uint32_t f = (n < 3 && ((phantom >> n) & 1u)) ? 1u : (freq_of(n) & 0xffffu);
+                const unsigned xb = extra_bits(KIND, (unsigned)n);
+                so += f * (l + xb);
+                if (KIND == 0) ss += f * (static_llen((unsigned)n) + xb);
+                else if (KIND == 1) ss += f * (5u + xb);
+            }
+        }
     }
-    t.max_code = max_code;
-    for (n = h.heap_len / 2; n >= 1; n--) sift_down(t, h, n);
-    node = elems;
-    do {
-        n = h.heap[1];
-        h.heap[1] = h.heap[h.heap_len--];
-        sift_down(t, h, 1);
-        m = h.heap[1];
-        h.heap[--h.heap_max] = (uint16_t)n;
-        h.heap[--h.heap_max] = (uint16_t)m;
-        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
-        h.depth[node] = (uint8_t)((h.depth[n] >= h.depth[m] ? h.depth[n] : h.depth[m]) + 1);
-        t.dad[n] = t.dad[m] = (uint16_t)node;
-        h.heap[1] = (uint16_t)node++;
-        sift_down(t, h, 1);
-    } while (h.heap_len >= 2);
-    h.heap[--h.heap_max] = h.heap[1];
-    gen_bitlen(t, h, kind, max_length);
+    for (int o = 16; o; o >>= 1) { so += __shfl_xor_sync(ZS_FULL_MASK, so, o); ss += __shfl_xor_sync(ZS_FULL_MASK, ss, o); }
+    opt_len += so;
+    static_len += ss;
+    // gen_codes, trees.ts:54-76: next_code per length
+    if (lane == 0) {
+        unsigned c = 0;
+        next_out[0] = 0;
+        for (int b = 1; b <= 15; b++) { c = (c + w.bl_count[b - 1]) << 1; next_out[b] = (uint16_t)c; }
+    }
+    __syncwarp();
+    max_code_out = max_code;
 }
 
-// gen_codes, trees.ts:54-76: next_code per length from bl_count
-__device__ __forceinline__ void next_codes(const uint16_t* bl_count, uint16_t* next) {
-    unsigned c = 0;
-    next[0] = 0;
-    for (int b = 1; b <= 15; b++) { c = (c + bl_count[b - 1]) << 1; next[b] = (uint16_t)c; }
+// Canonical codes in symbol order: lane b owns code length b and walks the symbols.
+__device__ __forceinline__ void assign_codes(const uint8_t* len, int max_code, const uint16_t* next, uint32_t* code_out, int elems) {
+    const unsigned lane = zs_lane();
+    for (int n = (int)lane; n < elems; n += 32) code_out[n] = 0;
+    __syncwarp();
+    if (lane >= 1 && lane <= 15) {
+        unsigned c = next[lane];
+        for (int n = 0; n <= max_code; n++)
+            if (len[n] == lane) code_out[n] = zs_bitrev(c++, lane) | (lane << 16);
+    }
+    __syncwarp();
 }
 
-// bit blob writer for the dynamic header (thread-private, writes 32-bit words to global memory)
+// bit blob writer for the dynamic header (lane 0, writes 32-bit words to global memory)
 struct BlobWriter {
     uint32_t* w;
     uint64_t acc;
@@ -183,8 +255,8 @@ struct BlobWriter {
 };
 
 // scan_tree (count = true, trees.ts:318-363) / send_tree (count = false, trees.ts:365-414)
-__device__ void walk_tree(const uint16_t* len, int max_code, bool count, uint16_t* bl_freq,
-                          const uint16_t* bl_code, const uint16_t* bl_len, BlobWriter* bw) {
+__device__ void walk_tree(const uint8_t* len, int max_code, bool count, uint32_t* bl_freq,
+                          const uint32_t* bl_code, BlobWriter* bw) {
     int prevlen = -1, curlen, nextlen = len[0], cnt = 0, max_count = 7, min_count = 4;
     if (nextlen == 0) { max_count = 138; min_count = 3; }
     for (int n = 0; n <= max_code; n++) {
@@ -192,21 +264,21 @@ __device__ void walk_tree(const uint16_t* len, int max_code, bool count, uint16_
         nextlen = n + 1 <= max_code ? len[n + 1] : 0xffff;  // the reference plants a 0xffff guard
         if (++cnt < max_count && curlen == nextlen) continue;
         if (cnt < min_count) {
-            if (count) bl_freq[curlen] += (uint16_t)cnt;
-            else do bw->put(bl_code[curlen], bl_len[curlen]); while (--cnt != 0);
+            if (count) bl_freq[curlen] += (uint32_t)cnt;
+            else do bw->put(bl_code[curlen] & 0xffffu, bl_code[curlen] >> 16); while (--cnt != 0);
         } else if (curlen != 0) {
             if (curlen != prevlen) {
                 if (count) bl_freq[curlen]++;
-                else { bw->put(bl_code[curlen], bl_len[curlen]); cnt--; }
+                else { bw->put(bl_code[curlen] & 0xffffu, bl_code[curlen] >> 16); cnt--; }
             }
             if (count) bl_freq[16]++;
-            else { bw->put(bl_code[16], bl_len[16]); bw->put((unsigned)(cnt - 3), 2); }
+            else { bw->put(bl_code[16] & 0xffffu, bl_code[16] >> 16); bw->put((unsigned)(cnt - 3), 2); }
         } else if (cnt <= 10) {
             if (count) bl_freq[17]++;
-            else { bw->put(bl_code[17], bl_len[17]); bw->put((unsigned)(cnt - 3), 3); }
+            else { bw->put(bl_code[17] & 0xffffu, bl_code[17] >> 16); bw->put((unsigned)(cnt - 3), 3); }
         } else {
             if (count) bl_freq[18]++;
-            else { bw->put(bl_code[18], bl_len[18]); bw->put((unsigned)(cnt - 11), 7); }
+            else { bw->put(bl_code[18] & 0xffffu, bl_code[18] >> 16); bw->put((unsigned)(cnt - 11), 7); }
         }
         cnt = 0;
         prevlen = curlen;
@@ -261,8 +333,241 @@ struct HuffArgs {
     uint64_t* blk_bits;
 };
 
+// _tr_flush_block's decision (trees.ts:544-583) for every block; one warp per block.
+__global__ void __launch_bounds__(32 * kHuffWarps) huff_build_kernel(HuffArgs a) {
+    __shared__ __align__(16) HuffWs ws[kHuffWarps];
+    const unsigned lane = zs_lane(), wid = threadIdx.x >> 5;
+    const uint64_t gid = (uint64_t)blockIdx.x * kHuffWarps + wid;
+    const uint64_t total = (uint64_t)a.n_chunks * a.max_bpc;
+    if (gid >= total) return;
+    const uint32_t chunk = (uint32_t)(gid / a.max_bpc), j = (uint32_t)(gid % a.max_bpc);
+    if (j >= a.chunk_nblk[chunk]) return;
+    HuffWs& w = ws[wid];
+    const uint32_t* freq = a.blk_freq + gid * 320;
+    const uint32_t in_len = a.blk_desc[gid * 4 + 3];
+
+    uint32_t opt_len = 0, static_len = 0;
+    int l_max, d_max, b_max;
+    // END_BLOCK always has frequency 1 (init_block, trees.ts:100)
+    build_tree_warp<0>(w, [&](int n) { return n == 256 ? 1u : freq[n]; }, w.llen, w.lnext, l_max, opt_len, static_len);
+    build_tree_warp<1>(w, [&](int n) { return freq[288 + n]; }, w.dlen, w.dnext, d_max, opt_len, static_len);
+    // build_bl_tree, trees.ts:416-432
+    if (lane < 20) w.bl_freq[lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        walk_tree(w.llen, l_max, true, w.bl_freq, nullptr, nullptr);
+        walk_tree(w.dlen, d_max, true, w.bl_freq, nullptr, nullptr);
+    }
+    __syncwarp();
+    build_tree_warp<2>(w, [&](int n) { return w.bl_freq[n]; }, w.blen, w.bnext, b_max, opt_len, static_len);
+    int max_blindex;
+    for (max_blindex = BL_CODES - 1; max_blindex >= 3; max_blindex--)
+        if (w.blen[c_bl_order[max_blindex]] != 0) break;
+    opt_len += 3u * ((uint32_t)max_blindex + 1u) + 5u + 5u + 4u;
+    uint32_t opt_lenb = (opt_len + 3u + 7u) >> 3;
+    const uint32_t static_lenb = (static_len + 3u + 7u) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+
+    uint32_t* code = a.blk_code + gid * 320;
+    uint32_t* hdr = a.blk_hdr + gid * kHdrWords;
+    uint64_t bits;
+    if (in_len + 4u <= opt_lenb && in_len <= 65535u) {
+        bits = 3ull + 32ull + 8ull * in_len;  // plus alignment padding, resolved by the layout
+        if (lane == 0) hdr[0] = BT_STORED;
+    } else if (static_lenb == opt_lenb) {
+        bits = 3ull + static_len;
+        for (unsigned n = lane; n < 320u; n += 32) {
+            uint32_t c = 0;
+            if (n < (unsigned)L_CODES) { const unsigned l = static_llen(n); c = zs_bitrev(static_lcode(n), l) | (l << 16); }
+            else if (n >= 288u && n < 288u + D_CODES) c = zs_bitrev(n - 288u, 5) | (5u << 16);
+            code[n] = c;
+        }
+        if (lane == 0) hdr[0] = BT_STATIC;
+    } else {
+        bits = 3ull + opt_len;
+        uint32_t* stage = w.heap;               // the heap is done: [0, 320) code table, [320, 340) bit-length codes
+        assign_codes(w.llen, l_max, w.lnext, stage, 288);
+        assign_codes(w.dlen, d_max, w.dnext, stage + 288, 32);
+        assign_codes(w.blen, b_max, w.bnext, stage + 320, 20);
+        for (unsigned n = lane; n < 320u; n += 32) code[n] = stage[n];
+        if (lane == 0) {
+            // send_all_trees, trees.ts:434-447
+            const uint32_t* bcode = stage + 320;
+            BlobWriter bw = {hdr + 1, 0, 0, 0, 0};
+            bw.put((unsigned)(l_max + 1 - 257), 5);
+            bw.put((unsigned)(d_max + 1 - 1), 5);
+            bw.put((unsigned)(max_blindex + 1 - 4), 4);
+            for (int r = 0; r <= max_blindex; r++) bw.put(w.blen[c_bl_order[r]], 3);
+            walk_tree(w.llen, l_max, false, nullptr, bcode, &bw);
+            walk_tree(w.dlen, d_max, false, nullptr, bcode, &bw);
+            bw.finish();
+            hdr[0] = BT_DYNAMIC | (bw.total << 8);
+        }
+    }
+    if (lane == 0) a.blk_bits[gid] = bits;
+}
+
+// ---- Huffman construction, thread per block (batches of very many small blocks) --------------------
+// The same algorithm with every array in thread-private local memory.  One warp per block retires
+// ~35 k serial instructions per block with one lane, which is issue-bound once a batch holds far
+// more blocks than the GPU has warps (4 KiB records: 131 072 blocks); there, 32 blocks per warp in
+// lockstep win (measured: 1.8 ms against 4.1 ms), while for 16 384 blocks of incompressible data the
+// shared-memory version above is 2.2x faster (1.4 ms against 3.1 ms).
+struct TpbTree {
+    uint16_t freq[HEAP_SIZE];
+    uint16_t dad[HEAP_SIZE];
+    uint16_t len[HEAP_SIZE];
+    int max_code;
+};
+struct TpbHeap {
+    uint16_t heap[HEAP_SIZE + 1];
+    uint8_t depth[HEAP_SIZE];
+    int heap_len, heap_max;
+    uint16_t bl_count[16];
+    uint32_t opt_len, static_len;
+};
+
+__device__ __forceinline__ bool tpb_smaller(const TpbTree& t, const TpbHeap& h, int n, int m) {
+    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && h.depth[n] <= h.depth[m]);
+}
+
+// pqdownheap, trees.ts:167-185
+__device__ void tpb_sift_down(const TpbTree& t, TpbHeap& h, int k) {
+    const int v = h.heap[k];
+    int j = k << 1;
+    while (j <= h.heap_len) {
+        if (j < h.heap_len && tpb_smaller(t, h, h.heap[j + 1], h.heap[j])) j++;
+        if (tpb_smaller(t, h, v, h.heap[j])) break;
+        h.heap[k] = h.heap[j];
+        k = j;
+        j <<= 1;
+    }
+    h.heap[k] = (uint16_t)v;
+}
+
+// tpb_gen_bitlen, trees.ts:187-259
+__device__ void tpb_gen_bitlen(TpbTree& t, TpbHeap& h, int kind, int max_length) {
+    int hh, n, m, bits, overflow = 0;
+    for (bits = 0; bits <= 15; bits++) h.bl_count[bits] = 0;
+    t.len[h.heap[h.heap_max]] = 0;
+    for (hh = h.heap_max + 1; hh < HEAP_SIZE; hh++) {
+        n = h.heap[hh];
+        bits = t.len[t.dad[n]] + 1;
+        if (bits > max_length) { bits = max_length; overflow++; }
+        t.len[n] = (uint16_t)bits;
+        if (n > t.max_code) continue;
+        h.bl_count[bits]++;
+        const unsigned xb = extra_bits(kind, (unsigned)n);
+        const uint32_t f = t.freq[n];
+        h.opt_len += f * ((uint32_t)bits + xb);
+        if (kind == 0) h.static_len += f * (static_llen((unsigned)n) + xb);
+        else if (kind == 1) h.static_len += f * (5u + xb);
+    }
+    if (overflow == 0) return;
+    do {
+        bits = max_length - 1;
+        while (h.bl_count[bits] == 0) bits--;
+        h.bl_count[bits]--;
+        h.bl_count[bits + 1] += 2;
+        h.bl_count[max_length]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (bits = max_length; bits != 0; bits--) {
+        n = h.bl_count[bits];
+        while (n != 0) {
+            m = h.heap[--hh];
+            if (m > t.max_code) continue;
+            if (t.len[m] != (unsigned)bits) {
+                h.opt_len += (uint32_t)(((int)bits - (int)t.len[m]) * (int)t.freq[m]);
+                t.len[m] = (uint16_t)bits;
+            }
+            n--;
+        }
+    }
+}
+
+// tpb_build_tree, trees.ts:261-316 (gen_codes is applied by the caller, which needs only bl_count)
+__device__ void tpb_build_tree(TpbTree& t, TpbHeap& h, int kind) {
+    const int elems = kind == 0 ? L_CODES : kind == 1 ? D_CODES : BL_CODES;
+    const int max_length = kind == 2 ? 7 : 15;
+    int n, m, node, max_code = -1;
+    h.heap_len = 0;
+    h.heap_max = HEAP_SIZE;
+    for (n = 0; n < elems; n++) {
+        if (t.freq[n] != 0) { h.heap[++h.heap_len] = (uint16_t)(max_code = n); h.depth[n] = 0; }
+        else t.len[n] = 0;
+    }
+    while (h.heap_len < 2) {
+        node = h.heap[++h.heap_len] = (uint16_t)(max_code < 2 ? ++max_code : 0);
+        t.freq[node] = 1;
+        h.depth[node] = 0;
+        h.opt_len--;
+        if (kind == 0) h.static_len -= static_llen((unsigned)node);
+        else if (kind == 1) h.static_len -= 5u;
+    }
+    t.max_code = max_code;
+    for (n = h.heap_len / 2; n >= 1; n--) tpb_sift_down(t, h, n);
+    node = elems;
+    do {
+        n = h.heap[1];
+        h.heap[1] = h.heap[h.heap_len--];
+        tpb_sift_down(t, h, 1);
+        m = h.heap[1];
+        h.heap[--h.heap_max] = (uint16_t)n;
+        h.heap[--h.heap_max] = (uint16_t)m;
+        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
+        h.depth[node] = (uint8_t)((h.depth[n] >= h.depth[m] ? h.depth[n] : h.depth[m]) + 1);
+        t.dad[n] = t.dad[m] = (uint16_t)node;
+        h.heap[1] = (uint16_t)node++;
+        tpb_sift_down(t, h, 1);
+    } while (h.heap_len >= 2);
+    h.heap[--h.heap_max] = h.heap[1];
+    tpb_gen_bitlen(t, h, kind, max_length);
+}
+
+// gen_codes, trees.ts:54-76: next_code per length from bl_count
+__device__ __forceinline__ void tpb_next_codes(const uint16_t* bl_count, uint16_t* next) {
+    unsigned c = 0;
+    next[0] = 0;
+    for (int b = 1; b <= 15; b++) { c = (c + bl_count[b - 1]) << 1; next[b] = (uint16_t)c; }
+}
+
+// scan_tree (count = true, trees.ts:318-363) / send_tree (count = false, trees.ts:365-414)
+__device__ void tpb_walk_tree(const uint16_t* len, int max_code, bool count, uint16_t* bl_freq,
+                          const uint16_t* bl_code, const uint16_t* bl_len, BlobWriter* bw) {
+    int prevlen = -1, curlen, nextlen = len[0], cnt = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) { max_count = 138; min_count = 3; }
+    for (int n = 0; n <= max_code; n++) {
+        curlen = nextlen;
+        nextlen = n + 1 <= max_code ? len[n + 1] : 0xffff;  // the reference plants a 0xffff guard
+        if (++cnt < max_count && curlen == nextlen) continue;
+        if (cnt < min_count) {
+            if (count) bl_freq[curlen] += (uint16_t)cnt;
+            else do bw->put(bl_code[curlen], bl_len[curlen]); while (--cnt != 0);
+        } else if (curlen != 0) {
+            if (curlen != prevlen) {
+                if (count) bl_freq[curlen]++;
+                else { bw->put(bl_code[curlen], bl_len[curlen]); cnt--; }
+            }
+            if (count) bl_freq[16]++;
+            else { bw->put(bl_code[16], bl_len[16]); bw->put((unsigned)(cnt - 3), 2); }
+        } else if (cnt <= 10) {
+            if (count) bl_freq[17]++;
+            else { bw->put(bl_code[17], bl_len[17]); bw->put((unsigned)(cnt - 3), 3); }
+        } else {
+            if (count) bl_freq[18]++;
+            else { bw->put(bl_code[18], bl_len[18]); bw->put((unsigned)(cnt - 11), 7); }
+        }
+        cnt = 0;
+        prevlen = curlen;
+        if (nextlen == 0) { max_count = 138; min_count = 3; }
+        else if (curlen == nextlen) { max_count = 6; min_count = 3; }
+        else { max_count = 7; min_count = 4; }
+    }
+}
+
 // _tr_flush_block's decision (trees.ts:544-583) for every block; one thread per block.
-__global__ void __launch_bounds__(64) huff_build_kernel(HuffArgs a) {
+__global__ void __launch_bounds__(64) tpb_huff_build_kernel(HuffArgs a) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)a.n_chunks * a.max_bpc;
     if (gid >= total) return;
@@ -271,23 +576,23 @@ __global__ void __launch_bounds__(64) huff_build_kernel(HuffArgs a) {
     const uint32_t* freq = a.blk_freq + gid * 320;
     const uint32_t in_len = a.blk_desc[gid * 4 + 3];
 
-    Tree lt, dt, bt;
-    Heap h;
+    TpbTree lt, dt, bt;
+    TpbHeap h;
     h.opt_len = h.static_len = 0;
     for (int n = 0; n < L_CODES; n++) lt.freq[n] = (uint16_t)freq[n];
     lt.freq[256] = 1;  // END_BLOCK, init_block trees.ts:100
     for (int n = 0; n < D_CODES; n++) dt.freq[n] = (uint16_t)freq[288 + n];
-    build_tree(lt, h, 0);
+    tpb_build_tree(lt, h, 0);
     uint16_t lnext[16], dnext[16], bnext[16];
-    next_codes(h.bl_count, lnext);
-    build_tree(dt, h, 1);
-    next_codes(h.bl_count, dnext);
+    tpb_next_codes(h.bl_count, lnext);
+    tpb_build_tree(dt, h, 1);
+    tpb_next_codes(h.bl_count, dnext);
     // build_bl_tree, trees.ts:416-432
     for (int n = 0; n < BL_CODES; n++) bt.freq[n] = 0;
-    walk_tree(lt.len, lt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
-    walk_tree(dt.len, dt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
-    build_tree(bt, h, 2);
-    next_codes(h.bl_count, bnext);
+    tpb_walk_tree(lt.len, lt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
+    tpb_walk_tree(dt.len, dt.max_code, true, bt.freq, nullptr, nullptr, nullptr);
+    tpb_build_tree(bt, h, 2);
+    tpb_next_codes(h.bl_count, bnext);
     int max_blindex;
     for (max_blindex = BL_CODES - 1; max_blindex >= 3; max_blindex--)
         if (bt.len[c_bl_order[max_blindex]] != 0) break;
@@ -336,8 +641,8 @@ __global__ void __launch_bounds__(64) huff_build_kernel(HuffArgs a) {
         bw.put((unsigned)(dt.max_code + 1 - 1), 5);
         bw.put((unsigned)(max_blindex + 1 - 4), 4);
         for (int r = 0; r <= max_blindex; r++) bw.put(blen[c_bl_order[r]], 3);
-        walk_tree(lt.len, lt.max_code, false, nullptr, bcode, blen, &bw);
-        walk_tree(dt.len, dt.max_code, false, nullptr, bcode, blen, &bw);
+        tpb_walk_tree(lt.len, lt.max_code, false, nullptr, bcode, blen, &bw);
+        tpb_walk_tree(dt.len, dt.max_code, false, nullptr, bcode, blen, &bw);
         bw.finish();
         hdr[0] = type | (bw.total << 8);
     }
@@ -751,7 +1056,14 @@ __global__ void bit_concat_kernel(uint32_t* dst32, uint64_t dst_off, const uint8
 }  // namespace
 
 static int zs_launch_huff_build(zs_ctx* ctx, const HuffArgs& h, uint64_t nblk_slots) {
-    ZS_KERNEL(ctx, "huff_build_kernel", huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h));
+    // see the comment at tpb_huff_build_kernel; the environment variables are test hooks
+    const bool tpb = getenv("ZS_HUFF_TPB") ? true : getenv("ZS_HUFF_WARP") ? false : nblk_slots > 49152;
+    if (tpb) {
+        ZS_KERNEL(ctx, "huff_build_kernel", tpb_huff_build_kernel<<<(unsigned)((nblk_slots + 63) / 64), 64, 0, ctx->stream>>>(h));
+    } else {
+        ZS_KERNEL(ctx, "huff_build_kernel",
+                  huff_build_kernel<<<(unsigned)((nblk_slots + kHuffWarps - 1) / kHuffWarps), 32 * kHuffWarps, 0, ctx->stream>>>(h));
+    }
     return ZS_OK;
 }
 
