@@ -703,51 +703,84 @@ __device__ __forceinline__ uint64_t chunk_len_at(uint64_t start, uint64_t P, uin
     return P + 3 + stored_pad(start + P + 3) + (Rf >> 1);
 }
 
-// One warp resolves the start of every chunk.  INDEPENDENT: byte offsets of whole streams
-// (wrapper header + body + trailer).  STITCHED: bit offsets inside the single stream.
-__global__ void __launch_bounds__(32) layout_scan_kernel(LayoutArgs a) {
-    const unsigned lane = zs_lane();
+// One CTA resolves the start of every chunk.  INDEPENDENT: byte offsets of whole streams (wrapper
+// header + body + trailer) -- a plain prefix sum.  STITCHED: bit offsets inside the single stream,
+// where a chunk's length depends on the bit its first stored block starts at.  Only the start
+// modulo 8 matters, and a chunk that holds a stored block ends at a residue that does not depend on
+// where it started (everything after the padding is fixed), so the start residues are a segmented
+// scan -- "reset to a constant" for chunks with a stored block, "add P mod 8" for the others --
+// followed by an ordinary prefix sum of the lengths.  1024 chunks per round.
+constexpr int kScanThreads = 1024;
+// residue-scan element: bit 3 = reset, bits 0..2 = value; a then b
+__device__ __forceinline__ unsigned res_combine(unsigned a, unsigned b) {
+    return (b & 8u) ? b : ((a & 8u) | (((a & 7u) + (b & 7u)) & 7u));
+}
+__global__ void __launch_bounds__(kScanThreads) layout_scan_kernel(LayoutArgs a) {
+    __shared__ unsigned s_res[32];
+    __shared__ uint64_t s_len[32];
+    __shared__ uint64_t s_tile_len;
+    const unsigned lane = zs_lane(), wid = threadIdx.x >> 5;
     const uint64_t H = a.wrap == ZS_WRAP_ZLIB ? 2 : a.wrap == ZS_WRAP_GZIP ? 10 : 0;
     const uint64_t T = a.wrap == ZS_WRAP_ZLIB ? 4 : a.wrap == ZS_WRAP_GZIP ? 8 : 0;
     const bool stitched = a.mode == ZS_MODE_STITCHED;
     uint64_t pos = 0;  // INDEPENDENT: bytes; STITCHED: bits
     if (stitched && !(a.flags & ZS_FLAG_NOT_FIRST)) pos = 8 * H;
-    for (uint32_t base = 0; base < a.n_chunks; base += 32) {
-        const uint32_t c = base + lane;
+    for (uint32_t base = 0; base < a.n_chunks; base += kScanThreads) {
+        const uint32_t c = base + threadIdx.x;
         const bool live = c < a.n_chunks;
         const uint64_t P = live ? a.chunk_pr[2 * c] : 0, Rf = live ? a.chunk_pr[2 * c + 1] : 0;
-        const unsigned cnt = a.n_chunks - base < 32 ? a.n_chunks - base : 32;
-        uint64_t my_start, my_bits;
-        if (!stitched) {
-            my_bits = live ? chunk_len_at(0, P, Rf) : 0;
-            uint64_t sz = live ? H + ((my_bits + 7) >> 3) + T : 0, incl = sz;
+        unsigned start_res = 0;
+        if (stitched) {
+            const unsigned e = !live ? 0u : (Rf & 1u) ? (8u | (unsigned)((Rf >> 1) & 7u)) : (unsigned)(P & 7u);
+            unsigned x = e;
             for (int o = 1; o < 32; o <<= 1) {
-                uint64_t v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
-                if ((int)lane >= o) incl += v;
+                const unsigned v = __shfl_up_sync(ZS_FULL_MASK, x, o);
+                if ((int)lane >= o) x = res_combine(v, x);
             }
-            my_start = pos + incl - sz;
-            pos += __shfl_sync(ZS_FULL_MASK, incl, 31);
-        } else if (__ballot_sync(ZS_FULL_MASK, (Rf & 1u) != 0) == 0) {
-            my_bits = P;
-            uint64_t incl = P;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint64_t v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
-                if ((int)lane >= o) incl += v;
+            if (lane == 31) s_res[wid] = x;
+            unsigned ex = __shfl_up_sync(ZS_FULL_MASK, x, 1);
+            if (lane == 0) ex = 0;   // identity
+            __syncthreads();
+            if (wid == 0) {
+                unsigned t = s_res[lane], incl = t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
+                    if ((int)lane >= o) incl = res_combine(v, incl);
+                }
+                unsigned wex = __shfl_up_sync(ZS_FULL_MASK, incl, 1);
+                if (lane == 0) wex = 0;
+                s_res[lane] = wex;
             }
-            my_start = pos + incl - P;
-            pos += __shfl_sync(ZS_FULL_MASK, incl, 31);
-        } else {
-            my_start = 0; my_bits = 0;
-            for (unsigned i = 0; i < cnt; i++) {
-                const uint64_t Pi = __shfl_sync(ZS_FULL_MASK, P, i), Ri = __shfl_sync(ZS_FULL_MASK, Rf, i);
-                const uint64_t len = chunk_len_at(pos, Pi, Ri);
-                if (lane == i) { my_start = pos; my_bits = len; }
-                pos += len;
-            }
+            __syncthreads();
+            const unsigned carry = 8u | (unsigned)(pos & 7u);
+            start_res = res_combine(res_combine(carry, s_res[wid]), ex) & 7u;
         }
+        const uint64_t my_bits = live ? chunk_len_at(start_res, P, Rf) : 0;
+        const uint64_t sz = stitched ? my_bits : (live ? H + ((my_bits + 7) >> 3) + T : 0);
+        uint64_t incl = sz;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t v = __shfl_up_sync(ZS_FULL_MASK, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) s_len[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const uint64_t t = s_len[lane];
+            uint64_t wi = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t v = __shfl_up_sync(ZS_FULL_MASK, wi, o);
+                if ((int)lane >= o) wi += v;
+            }
+            s_len[lane] = wi - t;
+            if (lane == 31) s_tile_len = wi;
+        }
+        __syncthreads();
+        const uint64_t my_start = pos + s_len[wid] + incl - sz;
         if (live) { a.out_off[c] = my_start; a.out_bits[c] = my_bits; }
+        pos += s_tile_len;
+        __syncthreads();   // s_len / s_res are rewritten by the next round
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         uint64_t total_bits, total_bytes;
         if (stitched) {
             total_bits = pos;
@@ -1089,7 +1122,7 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     l.result = p.d_result; l.error = p.d_error; l.check_total = p.d_check_total;
     const unsigned cgrid = (p.n_chunks + 127) / 128;
     ZS_KERNEL(ctx, "layout_chunks_kernel", layout_chunks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l));
-    ZS_KERNEL(ctx, "layout_scan_kernel", layout_scan_kernel<<<1, 32, 0, ctx->stream>>>(l));
+    ZS_KERNEL(ctx, "layout_scan_kernel", layout_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(l));
     ZS_KERNEL(ctx, "layout_blocks_kernel", layout_blocks_kernel<<<cgrid, 128, 0, ctx->stream>>>(l));
 
     ZS_KERNEL(ctx, "zero_output_kernel", zero_output_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p.d_out, p.d_result, p.d_error, p.out_cap));
