@@ -66,6 +66,17 @@ extern "C" {
 #define ZS_FLAG_SYNC 8u      /* STITCHED: end every chunk with an empty stored block (Z_SYNC_FLUSH
                                 marker, deflate.ts:945-946) so chunks start byte aligned */
 
+/* strategy (last argument of deflateInit2_, src/mod/common/constants.ts): bits 8..10 of the flags.
+ * FILTERED drops matches of length <= 5 at the lazy levels (deflate.ts:1381-1387), HUFFMAN_ONLY emits
+ * literals only (deflate_huff, :1525), RLE matches at distance 1 only (deflate_rle, :1450), FIXED never
+ * builds dynamic trees (trees.ts:559). */
+#define ZS_STRATEGY_DEFAULT 0
+#define ZS_STRATEGY_FILTERED 1
+#define ZS_STRATEGY_HUFFMAN_ONLY 2
+#define ZS_STRATEGY_RLE 3
+#define ZS_STRATEGY_FIXED 4
+#define ZS_FLAG_STRATEGY(s) (((uint32_t)(s) & 7u) << 8)
+
 typedef struct zs_ctx zs_ctx;
 
 #if defined(__GNUC__)
@@ -122,7 +133,8 @@ typedef struct zs_deflate_result {
  * Chunk i is d_in[d_in_off[i] .. d_in_off[i+1]).  If d_in_off is NULL the input is cut into
  * `chunk_size`-byte chunks (the last one short) and n_chunks must equal ceil(in_len/chunk_size)
  * (or 1 when in_len == 0).  `history` bytes before d_in[0] are readable and may be matched against
- * (STITCHED continuation parts / PRIME).  level 1..9 (-1 = 6), CONFIGURATION_TABLE deflate.ts:86.
+ * (STITCHED continuation parts / PRIME).  level 0..9 (-1 = 6), CONFIGURATION_TABLE deflate.ts:86;
+ * level 0 stores every chunk as stored blocks (deflate_stored, deflate.ts:1140).
  * Outputs (device): d_out, d_out_off[n_chunks+1] = byte offsets of the streams (INDEPENDENT) or
  * bit offsets of the chunk bit-streams (STITCHED); d_out_bits[n_chunks] = compressed bit length of
  * each chunk; d_checks[n_chunks] (may be NULL) = per-chunk adler32/crc32; d_result = summary.
@@ -209,6 +221,11 @@ ZS_API int zs_stream_deflate_init(zs_ctx* ctx, zs_stream* strm, int level, int m
 ZS_API int zs_stream_deflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len);
 ZS_API int zs_stream_deflate(zs_stream* strm, int flush);
 ZS_API int zs_stream_deflate_end(zs_stream* strm);
+/* deflateReset / deflateResetKeep (deflate.ts:444-495), deflateParams (:553-595), deflatePending /
+ * deflateUsed (:505-526; the engine never keeps a partial byte between calls: bits = 0). */
+ZS_API int zs_stream_deflate_reset(zs_stream* strm);
+ZS_API int zs_stream_deflate_params(zs_stream* strm, int level, int strategy);
+ZS_API int zs_stream_deflate_pending(zs_stream* strm, uint32_t* pending, int* bits);
 ZS_API int zs_stream_inflate_init(zs_ctx* ctx, zs_stream* strm, int window_bits);
 ZS_API int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len);
 ZS_API int zs_stream_inflate(zs_stream* strm, int flush);

@@ -39,6 +39,7 @@ struct zo_inflate_stream {
     uint32_t adler;
     int data_type;
     int inited;
+    uint32_t blocks[3];   /* test aid: stored / fixed / dynamic blocks seen since the last reset */
     /* InflateState, inflate/utils.ts:11-50 */
     int mode, last, wrap, havedict, flags;
     unsigned dmax;
@@ -697,6 +698,7 @@ int zo_inflate(zo_inflate_stream* s, int flush) {
             NEEDBITS(3);
             s->last = (int)BITS(1);
             DROPBITS(1);
+            if (BITS(2) < 3) s->blocks[BITS(2)]++;
             switch (BITS(2)) {
                 case 0: s->mode = M_STORED; break;
                 case 1:
@@ -991,6 +993,9 @@ inf_leave: /* inflate.ts:1059-1100 */
     return ret;
 }
 
+static uint32_t last_blocks[3];
+void zo_inflate_last_blocks(uint32_t* counts) { memcpy(counts, last_blocks, sizeof(last_blocks)); }
+
 int zo_inflate_oneshot(const uint8_t* in, size_t in_len, int window_bits, const uint8_t* dict,
                        size_t dict_len, uint8_t* out, size_t out_cap, size_t* out_len, size_t* in_used,
                        uint32_t* check) {
@@ -1013,6 +1018,7 @@ int zo_inflate_oneshot(const uint8_t* in, size_t in_len, int window_bits, const 
     if (out_len) *out_len = (size_t)s->total_out;
     if (in_used) *in_used = (size_t)s->total_in;
     if (check) *check = s->adler;
+    memcpy(last_blocks, s->blocks, sizeof(last_blocks));
     zo_inflate_free(s);
     return ret;
 }

@@ -138,6 +138,15 @@ def inflate(data, window_bits: int = 15, out_cap: int | None = None, dictionary=
     return ret, bytes(out[: ol.value]) if ol.value else b"", used.value, ck.value
 
 
+def block_types(data, window_bits: int = -15):
+    """Set of block types (0 stored, 1 fixed, 2 dynamic) of a complete stream."""
+    ret, out, used, _ = inflate(data, window_bits)
+    assert ret == Z_STREAM_END, ret
+    counts = (C.c_uint32 * 3)()
+    lib().zo_inflate_last_blocks(counts)
+    return {t for t in range(3) if counts[t]}
+
+
 def deflate(data, level: int = 6, wrap: int = 1, dictionary=None, flush: int = Z_FINISH) -> bytes:
     """One-shot deflateInit2_(level, 8, wbits(wrap), 8, 0) [+ dictionary] + deflate(flush)."""
     p, n, k = _buf(data)

@@ -82,6 +82,10 @@ int zo_inflate_oneshot(const uint8_t* in, size_t in_len, int window_bits, const 
                        size_t dict_len, uint8_t* out, size_t out_cap, size_t* out_len,
                        size_t* in_used, uint32_t* check);
 
+/* Test aid: how many stored / fixed / dynamic blocks the last zo_inflate_oneshot call walked through
+ * (counts[3]); not thread safe. */
+void zo_inflate_last_blocks(uint32_t* counts);
+
 /* ---- deflate: deflate/deflate.ts, trees.ts, deflate/utils.ts ---------------------------- */
 
 /* Upper bound of deflateBound for windowBits 15 / memLevel 8, deflate.ts:615-674.

@@ -290,6 +290,11 @@ def adler32_combine(a1: int, a2: int, len2: int) -> int:
     return int(capi.load().zs_adler32_combine(a1, a2, len2))
 
 
+def flag_strategy(strategy: int) -> int:
+    """ZS_FLAG_STRATEGY: the strategy argument of deflateInit2_ carried in the batch flags."""
+    return (strategy & 7) << 8
+
+
 def huffman_blocks(freq, in_len, ctx: Context | None = None):
     """Huffman stage alone (zs_huffman_blocks): freq uint32 [n, 320], in_len uint32 [n] (numpy, host).
 

@@ -78,6 +78,9 @@ _PROTOTYPES = {
     "zs_stream_deflate_set_dictionary": (C.c_int, [C.POINTER(ZStream), C.c_void_p, C.c_uint32]),
     "zs_stream_deflate": (C.c_int, [C.POINTER(ZStream), C.c_int]),
     "zs_stream_deflate_end": (C.c_int, [C.POINTER(ZStream)]),
+    "zs_stream_deflate_reset": (C.c_int, [C.POINTER(ZStream)]),
+    "zs_stream_deflate_params": (C.c_int, [C.POINTER(ZStream), C.c_int, C.c_int]),
+    "zs_stream_deflate_pending": (C.c_int, [C.POINTER(ZStream), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
     "zs_stream_inflate_init": (C.c_int, [C.c_void_p, C.POINTER(ZStream), C.c_int]),
     "zs_stream_inflate_set_dictionary": (C.c_int, [C.POINTER(ZStream), C.c_void_p, C.c_uint32]),
     "zs_stream_inflate": (C.c_int, [C.POINTER(ZStream), C.c_int]),

@@ -243,7 +243,9 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     if (!ctx) return ZS_STREAM_ERROR;
     if (level == -1) level = 6;
     // argument rules of deflateInit2_ (deflate.ts:263-297) that apply to the batch form
-    if (level < 1 || level > 9) return bad_arg(ctx, "deflate: level must be 1..9 (level 0 / stored is out of scope)");
+    if (level < 0 || level > 9) return bad_arg(ctx, "deflate: level must be 0..9");
+    const int strategy = (int)((flags >> 8) & 7u);
+    if (strategy > ZS_STRATEGY_FIXED) return bad_arg(ctx, "deflate: unknown strategy");
     if (wrap < 0 || wrap > 2 || (mode != ZS_MODE_INDEPENDENT && mode != ZS_MODE_STITCHED))
         return bad_arg(ctx, "deflate: bad wrap or mode");
     if (!d_out || !d_result || (in_len && !d_in) || n_chunks == 0) return bad_arg(ctx, "deflate: null buffer or zero chunks");
@@ -265,7 +267,7 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     memset(&p, 0, sizeof(p));
     p.d_in = d_in; p.in_len = in_len; p.history = history; p.n_chunks = n_chunks; p.max_chunk = max_chunk;
     p.max_bpc = max_chunk / 16351u + 2u;
-    p.level = level; p.wrap = wrap; p.mode = mode; p.flags = flags;
+    p.level = level; p.wrap = wrap; p.mode = mode; p.flags = flags; p.strategy = strategy;
     p.seg_hint = ctx->seg_hint;
     const size_t slots = (size_t)n_chunks * p.max_bpc;
 

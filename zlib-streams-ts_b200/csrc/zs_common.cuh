@@ -170,6 +170,7 @@ struct zs_deflate_plan {
     uint32_t max_bpc;         // block descriptor slots per chunk
     uint32_t seg_hint;        // 0 or the LZ77 segment size to use (chunks)
     int level, wrap, mode;
+    int strategy;             // ZS_STRATEGY_*
     uint32_t flags;
     // scratch
     uint32_t* d_sym;          // [in_len] packed symbols

@@ -331,6 +331,7 @@ struct HuffArgs {
     uint32_t* blk_code;
     uint32_t* blk_hdr;
     uint64_t* blk_bits;
+    int force;   // 0: the reference's choice; 1: stored blocks only (level 0); 2: never dynamic (Z_FIXED, trees.ts:559-568)
 };
 
 // _tr_flush_block's decision (trees.ts:544-583) for every block; one warp per block.
@@ -345,6 +346,10 @@ __global__ void __launch_bounds__(32 * kHuffWarps) huff_build_kernel(HuffArgs a)
     HuffWs& w = ws[wid];
     const uint32_t* freq = a.blk_freq + gid * 320;
     const uint32_t in_len = a.blk_desc[gid * 4 + 3];
+    if (a.force == 1) {   // deflate_stored: no trees at all
+        if (lane == 0) { a.blk_hdr[gid * kHdrWords] = BT_STORED; a.blk_bits[gid] = 3ull + 32ull + 8ull * in_len; }
+        return;
+    }
 
     uint32_t opt_len = 0, static_len = 0;
     int l_max, d_max, b_max;
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(32 * kHuffWarps) huff_build_kernel(HuffArgs a)
     opt_len += 3u * ((uint32_t)max_blindex + 1u) + 5u + 5u + 4u;
     uint32_t opt_lenb = (opt_len + 3u + 7u) >> 3;
     const uint32_t static_lenb = (static_len + 3u + 7u) >> 3;
-    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (static_lenb <= opt_lenb || a.force == 2) opt_lenb = static_lenb;
 
     uint32_t* code = a.blk_code + gid * 320;
     uint32_t* hdr = a.blk_hdr + gid * kHdrWords;
@@ -575,6 +580,11 @@ __global__ void __launch_bounds__(64) tpb_huff_build_kernel(HuffArgs a) {
     if (j >= a.chunk_nblk[chunk]) return;
     const uint32_t* freq = a.blk_freq + gid * 320;
     const uint32_t in_len = a.blk_desc[gid * 4 + 3];
+    if (a.force == 1) {   // deflate_stored: no trees at all
+        a.blk_hdr[gid * kHdrWords] = BT_STORED;
+        a.blk_bits[gid] = 3ull + 32ull + 8ull * in_len;
+        return;
+    }
 
     TpbTree lt, dt, bt;
     TpbHeap h;
@@ -599,7 +609,7 @@ __global__ void __launch_bounds__(64) tpb_huff_build_kernel(HuffArgs a) {
     h.opt_len += 3u * ((uint32_t)max_blindex + 1u) + 5u + 5u + 4u;
     uint32_t opt_lenb = (h.opt_len + 3u + 7u) >> 3;
     const uint32_t static_lenb = (h.static_len + 3u + 7u) >> 3;
-    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (static_lenb <= opt_lenb || a.force == 2) opt_lenb = static_lenb;
 
     uint32_t* code = a.blk_code + gid * 320;
     uint32_t* hdr = a.blk_hdr + gid * kHdrWords;
@@ -1109,7 +1119,8 @@ int zs_launch_huffman(zs_ctx* ctx, const zs_deflate_plan& p) {
     }
     HistArgs hs = {p.n_chunks, p.max_bpc, p.d_in_off, p.d_chunk_nblk, p.d_blk_desc, p.d_sym, p.d_blk_freq};
     ZS_KERNEL(ctx, "histogram_kernel", histogram_kernel<<<(unsigned)nblk_slots, 256, 0, ctx->stream>>>(hs));
-    HuffArgs h = {p.n_chunks, p.max_bpc, p.d_chunk_nblk, p.d_blk_desc, p.d_blk_freq, p.d_blk_code, p.d_blk_hdr, p.d_blk_bits};
+    HuffArgs h = {p.n_chunks, p.max_bpc, p.d_chunk_nblk, p.d_blk_desc, p.d_blk_freq, p.d_blk_code, p.d_blk_hdr, p.d_blk_bits,
+                  p.level == 0 ? 1 : p.strategy == ZS_STRATEGY_FIXED ? 2 : 0};
     {
         const int rc = zs_launch_huff_build(ctx, h, nblk_slots);
         if (rc != ZS_OK) return rc;
@@ -1177,7 +1188,7 @@ extern "C" int zs_huffman_blocks(zs_ctx* ctx, const uint32_t* freq, const uint32
         fail(cudaMemsetAsync(d_code, 0, (size_t)n * 320 * 4, ctx->stream));
     }
     if (rc == ZS_OK) {
-        HuffArgs h = {n, 1u, d_nblk, d_desc, d_freq, d_code, d_hdr, d_bits};
+        HuffArgs h = {n, 1u, d_nblk, d_desc, d_freq, d_code, d_hdr, d_bits, 0};
         rc = zs_launch_huff_build(ctx, h, n);
     }
     if (rc == ZS_OK) {

@@ -107,6 +107,7 @@ struct LzArgs {
     const uint64_t* in_off;    // [n_chunks+1] relative to org
     uint32_t n_chunks, seg_chunks, n_seg, max_bpc;
     int level;
+    int strategy;              // ZS_STRATEGY_* (FILTERED and RLE act here)
     int cross;                 // 1: matches may reach before the chunk start (PRIME / STITCHED)
     uint32_t* sym;
     uint32_t* chunk_nblk;
@@ -176,6 +177,7 @@ struct RangeCtx {
     uint32_t q_data; // first position that is compressed (everything before is dictionary)
     uint32_t nc;     // chunks in the segment
     int cross;       // matches may reach before the chunk start
+    unsigned min_len;  // shortest match worth emitting: 3, or 6 with Z_FILTERED at the lazy levels (deflate.ts:1381-1387)
 };
 
 // ---- stage 1: prep (wide) -----------------------------------------------------------------------
@@ -258,7 +260,8 @@ __device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
 // [cs, ce) is the chunk that holds q.
-template <bool kLazy>
+// kMode: 0 greedy levels (1-3), 1 lazy levels (4-9), 2 Z_RLE
+template <int kMode>
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
                                                     uint32_t cs, uint32_t ce) {
     const uint32_t room = ce - q;
@@ -267,6 +270,22 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     const uint32_t pw0 = ring32(S, pi), pw1 = ring32(S, pi + 4);
     const uint32_t lit = (pw0 & 0xffu) << 24;
     if (max_len < 3) return lit;
+    constexpr bool kLazy = kMode == 1;
+    if (kMode == 2) {
+        // deflate_rle (deflate.ts:1450-1523): the only candidate is the previous byte; the match is the
+        // rest of the run it starts
+        const uint32_t back = c.cross ? q + c.pre : q - cs;
+        if (back == 0) return lit;
+        const uint32_t pat = (uint32_t)S.ring[(pi - 1u) & (kRing - 1u)] * 0x01010101u;
+        unsigned len = 0;
+        while (len < max_len) {
+            const uint32_t x = ring32(S, pi + len) ^ pat;
+            if (x) { len += first_diff_byte(x); break; }
+            len += 4;
+        }
+        if (len > max_len) len = max_len;
+        return len >= 3 ? (lit | (len << 15) | 1u) : lit;
+    }
     const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
     const uint32_t back = c.cross ? q + c.pre : q - cs;
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
@@ -354,7 +373,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     atomicMax(&g_prof[13], (unsigned long long)n_cand);
     if (n_cand > 100) { atomicAdd(&g_prof[14], 1ull); g_prof[15] = ((unsigned long long)best_len << 32) | (q - cs); }
 #endif
-    if (best_len < 3) return lit;
+    if (best_len < c.min_len) return lit;
     if (kLazy && best_len == 3 && best_dist > kTooFar) return lit;  // deflate.ts:1381-1387
     return lit | (best_len << 15) | best_dist;
 }
@@ -372,7 +391,7 @@ __device__ __forceinline__ unsigned mj_pair_count(unsigned y) { return y >> 25; 
 
 // One batch of 32 positions starting at q0: greedy / lazy rule per position, then 5 rounds of
 // pointer doubling.  Needs the search result of position q0+32 (or q0+32 >= n).
-template <bool kLazy>
+template <int kMode>
 __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0, unsigned& M,
                                             unsigned& J, bool& is_match) {
     const unsigned lane = zs_lane();
@@ -383,7 +402,7 @@ __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, 
     if (lane == 31) Ln = (q + 1 < n) ? ((S.res[res_slot(q + 1)] >> 15) & 0x1ffu) : 0u;
     // deflate_slow's lazy evaluation (deflate.ts:1372-1426): the match at q is dropped for a
     // literal when the match at q+1 is strictly longer and L < max_lazy
-    const bool deferred = kLazy && L >= 3 && L < (unsigned)cfg.lazy && Ln > L;
+    const bool deferred = kMode == 1 && L >= 3 && L < (unsigned)cfg.lazy && Ln > L;
     is_match = L >= 3 && !deferred;
     // positions past the end of the chunk are terminal and never visited
     J = q < n ? lane + (is_match ? L : 1u) : 32u;
@@ -399,13 +418,13 @@ __device__ __forceinline__ void resolve_one(const Smem& S, const LevelCfg& cfg, 
 
 // An aligned pair of batches [q0, q0+64): both are resolved by the same warp and composed, so that
 // the thin parse needs one hop per 64 positions.
-template <bool kLazy>
+template <int kMode>
 __device__ __forceinline__ void resolve_pair(Smem& S, const LevelCfg& cfg, uint32_t n, uint32_t q0) {
     const unsigned lane = zs_lane();
     unsigned Ma, Ja, Mb, Jb;
     bool ma, mb;
-    resolve_one<kLazy>(S, cfg, n, q0, Ma, Ja, ma);
-    resolve_one<kLazy>(S, cfg, n, q0 + 32, Mb, Jb, mb);
+    resolve_one<kMode>(S, cfg, n, q0, Ma, Ja, ma);
+    resolve_one<kMode>(S, cfg, n, q0 + 32, Mb, Jb, mb);
     const unsigned ca = __popc(Ma), cb = __popc(Mb);
     // entering the pair at this lane of the first batch: where does the parse enter the second?
     const unsigned xa = Ja - 32u;
@@ -569,8 +588,8 @@ __device__ __forceinline__ uint32_t resolved_frontier(uint32_t searched, uint32_
     return searched >= 64 ? (searched - 1) & ~63u : 0;
 }
 
-// kLazy: levels 4-9 (deflate_slow's rules); levels 1-3 are the greedy instantiation.
-template <bool kLazy>
+// kMode 1: levels 4-9 (deflate_slow's rules); 0: levels 1-3, greedy; 2: Z_RLE, greedy with distance 1 only.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -613,6 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
         rc.q_data = (uint32_t)(seg_start - prime0);
         rc.nc = nc;
         rc.cross = a.cross;
+        rc.min_len = (kMode == 1 && a.strategy == ZS_STRATEGY_FILTERED) ? 6u : 3u;
         {
             const uint64_t pre = a.cross ? prime0 - a.valid_lo : 0;
             rc.pre = pre < kMaxDist ? (uint32_t)pre : kMaxDist;
@@ -725,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-                            r = search_position<kLazy>(S, cfg, rc, q, cs, ce);
+                            r = search_position<kMode>(S, cfg, rc, q, cs, ce);
                         }
                         if (q < n) S.res[res_slot(q)] = r;
                     }
@@ -736,7 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 constexpr unsigned kHalf = kSearchWarps / 2;
                 if (wid < kHalf) {
                     // resolve the pairs whose successor was searched before this iteration
-                    for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair<kLazy>(S, cfg, n, q0);
+                    for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair<kMode>(S, cfg, n, q0);
                 } else {
                     // emit the pairs the thin parse chained in the previous iteration
                     for (uint32_t q0 = r3 + 64u * (wid - kHalf); q0 < r2; q0 += 64u * (kSearchWarps - kHalf)) {
@@ -775,15 +795,38 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
     }
 }
 
+// Level 0 (deflate_stored, deflate.ts:1140-1279) and Z_HUFFMAN_ONLY (deflate_huff, :1525-1560) need no
+// match finder: the blocks of a chunk are cut at fixed input lengths -- 65535 bytes per stored block,
+// kSymLimit literals per Huffman block -- and, for HUFFMAN_ONLY, symbol i of a chunk is its i-th byte.
+__global__ void plain_blocks_kernel(LzArgs a, uint32_t per_block, int with_symbols) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+    const uint32_t n = (uint32_t)(a.in_off[c + 1] - a.in_off[c]);
+    uint32_t nb = (n + per_block - 1) / per_block;
+    if (nb == 0) nb = 1;   // an empty chunk still ends with a (final) block
+    if (nb > a.max_bpc) nb = a.max_bpc;
+    for (uint32_t j = 0; j < nb; j++) {
+        uint32_t* d = a.blk_desc + ((uint64_t)c * a.max_bpc + j) * 4;
+        const uint32_t b0 = j * per_block, len = n - b0 < per_block ? n - b0 : per_block;
+        d[0] = with_symbols ? b0 : 0u;
+        d[1] = with_symbols ? len : 0u;
+        d[2] = b0;
+        d[3] = len;
+    }
+    a.chunk_nblk[c] = nb;
+}
+__global__ void literal_symbols_kernel(const uint8_t* in, uint32_t* sym, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) sym[i] = in[i];
+}
+
 }  // namespace
 
 int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     static bool attr_set = false;
     if (!attr_set) {
-        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(Smem)));
-        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(Smem)));
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_set = true;
     }
     LzArgs a;
@@ -797,6 +840,7 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     a.n_chunks = p.n_chunks;
     a.max_bpc = p.max_bpc;
     a.level = p.level;
+    a.strategy = p.strategy;
     a.cross = (p.mode == ZS_MODE_STITCHED || (p.flags & ZS_FLAG_PRIME)) ? 1 : 0;
     // Segments: runs of consecutive chunks that go through the pipeline as one range, sharing one set
     // of hash tables.  A segment pays the pipeline fill/drain (6 steps) and, with cross-chunk
@@ -830,6 +874,15 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
 #ifdef ZS_LZ_PROF
     if (getenv("ZS_LZ_DEBUG")) a.debug = atoi(getenv("ZS_LZ_DEBUG"));
 #endif
+    if (p.level == 0 || p.strategy == ZS_STRATEGY_HUFFMAN_ONLY) {
+        const bool stored = p.level == 0;
+        ZS_KERNEL(ctx, "plain_blocks_kernel",
+                  plain_blocks_kernel<<<(p.n_chunks + 127) / 128, 128, 0, ctx->stream>>>(a, stored ? 65535u : kSymLimit, stored ? 0 : 1));
+        if (!stored && p.in_len)
+            ZS_KERNEL(ctx, "literal_symbols_kernel",
+                      literal_symbols_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p.d_in, p.d_sym, p.in_len));
+        return ZS_OK;
+    }
     ZS_CUDA_TRY(ctx, cudaMemsetAsync(p.d_seg_counter, 0, sizeof(uint32_t), ctx->stream));
     unsigned grid = a.n_seg < (unsigned)ctx->sm_count ? a.n_seg : (unsigned)ctx->sm_count;
     if (grid == 0) return ZS_OK;
@@ -837,10 +890,12 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     unsigned long long zero[16] = {0};
     cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
 #endif
-    if (a.level >= 4) {
-        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<true><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+    if (a.strategy == ZS_STRATEGY_RLE) {
+        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<2><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+    } else if (a.level >= 4) {
+        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<1><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
     } else {
-        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<false><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
+        ZS_KERNEL(ctx, "lz77_kernel", lz77_kernel<0><<<grid, kThreads, sizeof(Smem), ctx->stream>>>(a));
     }
 #ifdef ZS_LZ_PROF
     {

@@ -45,7 +45,7 @@ constexpr size_t kPartThreshold = 16u << 20;
 struct DeflateState {
     uint32_t magic = 0x44464c54;  // 'DFLT'
     zs_ctx* ctx = nullptr;
-    int level = 6, wrap = 1, status = ST_INIT, last_flush = -2;
+    int level = 6, strategy = 0, wrap = 1, status = ST_INIT, last_flush = -2;
     std::vector<uint8_t> hist;      // last <= 32 KiB already compressed (or the preset dictionary)
     std::vector<uint8_t> in;        // buffered, not yet compressed
     std::vector<uint8_t> out;       // compressed, not yet delivered
@@ -109,7 +109,7 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
         st->header_done = true;
     }
     const bool whole = !st->any_part && finish && !st->header_done;  // the GPU frames a single-part stream completely
-    uint32_t flags = ZS_FLAG_SYNC;
+    uint32_t flags = ZS_FLAG_SYNC | ZS_FLAG_STRATEGY(st->strategy);
     if (st->header_done || st->any_part) flags |= ZS_FLAG_NOT_FIRST;
     if (!finish) flags |= ZS_FLAG_NOT_LAST;
     const uint32_t chunk = n >= (148u * 4u * 262144u) ? 262144u : 65536u;
@@ -197,14 +197,10 @@ int zs_stream_deflate_init(zs_ctx* ctx, zs_stream* strm, int level, int method, 
     if (mem_level < 1 || mem_level > 9 || method != 8 || window_bits < 8 || window_bits > 15 || level < 0 || level > 9 ||
         strategy < 0 || strategy > 4 || (window_bits == 8 && wrap != 1))
         return ZS_STREAM_ERROR;
-    if (level == 0 || strategy != 0) {
-        // deflate_stored / Z_FILTERED / Z_HUFFMAN_ONLY / Z_RLE / Z_FIXED are outside the GPU hot path
-        strm->msg = "level 0 and non-default strategies are not implemented by the GPU engine";
-        return ZS_STREAM_ERROR;
-    }
     DeflateState* st = new DeflateState();
     st->ctx = ctx;
     st->level = level;
+    st->strategy = strategy;
     st->wrap = wrap;
     st->status = ST_INIT;
     strm->state = st;
@@ -284,6 +280,58 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
     }
     drain(strm, st->out, st->out_pos);
     if (flush == ZS_FINISH && st->status == ST_FINISH && st->out_pos >= st->out.size()) return ZS_STREAM_END;
+    return ZS_OK;
+}
+
+// deflateResetKeep / deflateReset, deflate.ts:444-495: same parameters, fresh stream
+int zs_stream_deflate_reset(zs_stream* strm) {
+    DeflateState* st = dstate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    st->hist.clear(); st->in.clear(); st->out.clear();
+    st->out_pos = 0;
+    st->header_done = st->any_part = st->trailer_done = st->have_dict = false;
+    st->check = st->dict_id = 0;
+    st->total_in_len = 0;
+    st->status = ST_INIT;
+    st->last_flush = -2;
+    strm->total_in = strm->total_out = 0;
+    strm->msg = "";
+    strm->data_type = 2;
+    strm->adler = st->wrap == 2 ? 0u : 1u;
+    return ZS_OK;
+}
+
+// deflateParams, deflate.ts:553-595.  What has been buffered is compressed with the old parameters
+// first (the reference does this with deflate(strm, Z_BLOCK)); like there, Z_BUF_ERROR means that the
+// output buffer could not take everything and the call must be repeated after draining.
+int zs_stream_deflate_params(zs_stream* strm, int level, int strategy) {
+    DeflateState* st = dstate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    if (level == -1) level = 6;
+    if (level < 0 || level > 9 || strategy < 0 || strategy > 4) return ZS_STREAM_ERROR;
+    const bool lazy_old = st->level >= 4, lazy_new = level >= 4;
+    const bool func_changes = (st->level == 0) != (level == 0) || lazy_old != lazy_new;
+    if ((strategy != st->strategy || func_changes) && st->last_flush != -2) {
+        const int err = zs_stream_deflate(strm, ZS_BLOCK);
+        if (err == ZS_STREAM_ERROR) return err;
+        if (strm->avail_in || !st->in.empty() || st->out_pos < st->out.size()) return ZS_BUF_ERROR;
+    }
+    st->level = level;
+    st->strategy = strategy;
+    return ZS_OK;
+}
+
+// deflatePending (deflate.ts:505-516): bytes produced but not yet delivered; the engine never holds a
+// partial byte back between calls (every part ends byte aligned), so `bits` is always 0, as is
+// deflateUsed's answer (deflate.ts:518-526) for the last byte.
+int zs_stream_deflate_pending(zs_stream* strm, uint32_t* pending, int* bits) {
+    DeflateState* st = dstate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    if (pending) {
+        const size_t n = st->out.size() - st->out_pos;
+        *pending = n > 0xffffffffull ? 0xffffffffu : (uint32_t)n;
+    }
+    if (bits) *bits = 0;
     return ZS_OK;
 }
 

@@ -22,6 +22,13 @@ from .capi import (Z_BLOCK, Z_BUF_ERROR, Z_DATA_ERROR, Z_FINISH, Z_FULL_FLUSH, Z
 Z_DEFLATED = 8
 Z_DEFAULT_COMPRESSION = -1
 Z_DEFAULT_STRATEGY = 0
+Z_FILTERED = 1
+Z_HUFFMAN_ONLY = 2
+Z_RLE = 3
+Z_FIXED = 4
+Z_NO_COMPRESSION = 0
+Z_BEST_SPEED = 1
+Z_BEST_COMPRESSION = 9
 DEF_WBITS = 15
 DEF_MEM_LEVEL = 8
 
@@ -138,6 +145,60 @@ def deflateEnd(strm: Stream) -> int:
     rc = capi.load().zs_stream_deflate_end(C.byref(strm._state[1]))
     strm._state = None
     return rc
+
+
+class Ref:
+    """The reference's out-parameter box ({ _value: number })."""
+
+    def __init__(self, value: int = 0):
+        self._value = value
+
+
+def deflateResetKeep(strm: Stream) -> int:
+    """deflate.ts:444-487"""
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    zs = strm._state[1]
+    rc = capi.load().zs_stream_deflate_reset(C.byref(zs))
+    strm.total_in = strm.total_out = 0
+    strm.msg = ""
+    strm._adler = zs.adler
+    strm._data_type = zs.data_type
+    return rc
+
+
+deflateReset = deflateResetKeep   # deflate.ts:489-495: ResetKeep + lm_init; the engine keeps no match state
+
+
+def deflateParams(strm: Stream, level: int, strategy: int) -> int:
+    """deflate.ts:553-595.  Pending input is compressed with the old parameters first; Z_BUF_ERROR
+    asks the caller to drain the output and call again, as in the reference."""
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    lib = capi.load()
+    return _call(strm, lambda zs, _f: lib.zs_stream_deflate_params(zs, level, strategy), 0)
+
+
+def deflatePending(strm: Stream, pending: Ref | None = None, bits: Ref | None = None) -> int:
+    """deflate.ts:505-516"""
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    p, b = C.c_uint32(0), C.c_int(0)
+    rc = capi.load().zs_stream_deflate_pending(C.byref(strm._state[1]), C.byref(p), C.byref(b))
+    if pending is not None:
+        pending._value = p.value
+    if bits is not None:
+        bits._value = b.value
+    return rc
+
+
+def deflateUsed(strm: Stream, bits: Ref | None = None) -> int:
+    """deflate.ts:518-526: bits used in the last byte written (every part ends byte aligned: 0)."""
+    if not _kind(strm, "deflate"):
+        return Z_STREAM_ERROR
+    if bits is not None:
+        bits._value = 0
+    return Z_OK
 
 
 def deflateBound(strm, sourceLen: int) -> int:
