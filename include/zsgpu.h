@@ -191,8 +191,7 @@ ZS_API int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_o
                      uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks,
                      int32_t* status, const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total);
 
-/* Message the reference would leave in strm.msg for a (status, detail) pair; detail codes are
- * returned in the high bits of nothing -- see zs_inflate_detail_dev. */
+/* Message the reference would leave in strm.msg for a detail code (see zs_inflate_last_details). */
 ZS_API const char* zs_inflate_message(int detail);
 /* Optional: per-stream detail code (index into the reference's message strings) of the last
  * zs_inflate_batch[_dev] call on this context, copied to the host array `detail[n]`. */
@@ -226,10 +225,37 @@ ZS_API int zs_stream_deflate_end(zs_stream* strm);
 ZS_API int zs_stream_deflate_reset(zs_stream* strm);
 ZS_API int zs_stream_deflate_params(zs_stream* strm, int level, int strategy);
 ZS_API int zs_stream_deflate_pending(zs_stream* strm, uint32_t* pending, int* bits);
+/* gzip header fields: GzipHeader of src/mod/common/types.ts:137-151 (zlib's gz_header).
+ * deflate side (deflateSetHeader, deflate.ts:497; written by deflate(), :803-921): extra / name /
+ * comment are present when their pointer is not NULL (name and comment zero-terminated, extra_len
+ * bytes of extra); hcrc != 0 adds the header CRC16; the fields are copied by the call.
+ * inflate side (inflateGetHeader, inflate.ts; filled by inflate(), :423-580): the caller's struct is
+ * filled while the header is parsed -- up to extra_max / name_max / comm_max bytes into the buffers
+ * that are not NULL -- and done becomes 1 (header complete) or -1 (not a gzip stream).  The struct
+ * must stay valid until then. */
+typedef struct zs_gz_header {
+    int32_t text;
+    uint32_t time;
+    int32_t xflags;
+    int32_t os;
+    uint8_t* extra;
+    uint32_t extra_max;
+    uint32_t extra_len;
+    uint8_t* name;
+    uint32_t name_max;
+    uint8_t* comment;
+    uint32_t comm_max;
+    int32_t hcrc;
+    int32_t done;
+} zs_gz_header;
+ZS_API int zs_stream_deflate_set_header(zs_stream* strm, const zs_gz_header* head);
+ZS_API int zs_stream_inflate_get_header(zs_stream* strm, zs_gz_header* head);
 ZS_API int zs_stream_inflate_init(zs_ctx* ctx, zs_stream* strm, int window_bits);
 ZS_API int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint32_t dict_len);
 ZS_API int zs_stream_inflate(zs_stream* strm, int flush);
 ZS_API int zs_stream_inflate_reset(zs_stream* strm);
+/* inflateReset2, inflate.ts:138-172 */
+ZS_API int zs_stream_inflate_reset2(zs_stream* strm, int window_bits);
 ZS_API int zs_stream_inflate_end(zs_stream* strm);
 
 #ifdef __cplusplus

@@ -161,3 +161,74 @@ def test_params_pending_reset(gpu_ctx):
     assert feed(a, Z.Z_FINISH) == Z.Z_STREAM_END
     assert zlib.decompress(bytes(out)) == a
     assert Z.deflateEnd(s) == Z.Z_OK
+
+
+def test_gzip_header_fields(gpu_ctx):
+    """deflateSetHeader / inflateGetHeader (scope row f3; test-deflate-gzip-header.ts, test/inflate/test-header.ts):
+    the header written for the caller's fields is what C zlib (gzip module semantics) and our own
+    inflateGetHeader read back."""
+    import gzip, io
+    Z = pkg("zlib_api")
+    data = make_text(40000, 9)
+    for hcrc in (0, 1):
+        s = Z.createDeflateStream()
+        assert Z.deflateInit2_(s, 6, Z.Z_DEFLATED, 31, 8, 0) == Z.Z_OK
+        head = Z.GzipHeader(text=1, time=0x5f3759df, os=3, extra=b"\x01\x02abcd", name=b"file.txt", comment=b"a comment", hcrc=hcrc)
+        assert Z.deflateSetHeader(s, head) == Z.Z_OK
+        out = bytearray()
+        s.next_in, s.next_in_index, s.avail_in = data, 0, len(data)
+        while True:
+            buf = bytearray(4096)
+            s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+            r = Z.deflate(s, Z.Z_FINISH)
+            out += buf[: s.next_out_index]
+            if r == Z.Z_STREAM_END:
+                break
+            assert r == Z.Z_OK
+        assert Z.deflateEnd(s) == Z.Z_OK
+        out = bytes(out)
+        assert out[:4] == bytes([0x1f, 0x8b, 8, 1 + 2 * hcrc + 4 + 8 + 16]) and out[9] == 3
+        assert int.from_bytes(out[4:8], "little") == 0x5f3759df
+        g = gzip.GzipFile(fileobj=io.BytesIO(out))
+        assert g.read() == data and g.mtime == 0x5f3759df
+        assert zlib.decompress(out, 31) == data
+        # and back through inflateGetHeader, fed in small pieces
+        t = Z.createInflateStream()
+        assert Z.inflateInit2_(t, 31) == Z.Z_OK
+        got_head = Z.GzipHeader(extra_max=64, name_max=64, comm_max=64)
+        assert Z.inflateGetHeader(t, got_head) == Z.Z_OK and got_head._done == 0
+        res = bytearray()
+        pos, r = 0, Z.Z_OK
+        while r != Z.Z_STREAM_END:
+            piece = out[pos: pos + 7]
+            t.next_in, t.next_in_index, t.avail_in = piece, 0, len(piece)
+            buf = bytearray(65536)
+            t.next_out, t.next_out_index, t.avail_out = buf, 0, len(buf)
+            r = Z.inflate(t, Z.Z_NO_FLUSH)
+            assert r in (Z.Z_OK, Z.Z_STREAM_END, Z.Z_BUF_ERROR), (r, t.msg)
+            res += buf[: t.next_out_index]
+            pos += len(piece) - t.avail_in
+        assert bytes(res) == data
+        assert got_head._done == 1 and got_head._text == 1 and got_head._time == 0x5f3759df and got_head._os == 3
+        assert got_head._extra == b"\x01\x02abcd" and got_head._extra_len == 6
+        assert got_head._name == b"file.txt" and got_head._comment == b"a comment" and got_head._hcrc == hcrc
+        assert Z.inflateEnd(t) == Z.Z_OK
+    # not a gzip stream: Z_STREAM_ERROR for zlib-only windowBits, done = -1 under auto-detection
+    t = Z.createInflateStream()
+    assert Z.inflateInit2_(t, 15) == Z.Z_OK
+    assert Z.inflateGetHeader(t, Z.GzipHeader()) == Z.Z_STREAM_ERROR
+    assert Z.inflateReset2(t, 47) == Z.Z_OK
+    h = Z.GzipHeader()
+    assert Z.inflateGetHeader(t, h) == Z.Z_OK
+    z = zlib.compress(data)
+    t.next_in, t.next_in_index, t.avail_in = z, 0, len(z)
+    buf = bytearray(len(data) + 64)
+    t.next_out, t.next_out_index, t.avail_out = buf, 0, len(buf)
+    assert Z.inflate(t, Z.Z_FINISH) == Z.Z_STREAM_END and bytes(buf[: t.next_out_index]) == data
+    assert h._done == -1
+    assert Z.inflateEnd(t) == Z.Z_OK
+    # deflateSetHeader needs a gzip stream
+    s = Z.createDeflateStream()
+    assert Z.deflateInit(s, 6) == Z.Z_OK
+    assert Z.deflateSetHeader(s, Z.GzipHeader()) == Z.Z_STREAM_ERROR
+    assert Z.deflateEnd(s) == Z.Z_OK

@@ -81,12 +81,23 @@ _PROTOTYPES = {
     "zs_stream_deflate_reset": (C.c_int, [C.POINTER(ZStream)]),
     "zs_stream_deflate_params": (C.c_int, [C.POINTER(ZStream), C.c_int, C.c_int]),
     "zs_stream_deflate_pending": (C.c_int, [C.POINTER(ZStream), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
+    "zs_stream_deflate_set_header": (C.c_int, [C.POINTER(ZStream), C.c_void_p]),
+    "zs_stream_inflate_get_header": (C.c_int, [C.POINTER(ZStream), C.c_void_p]),
     "zs_stream_inflate_init": (C.c_int, [C.c_void_p, C.POINTER(ZStream), C.c_int]),
     "zs_stream_inflate_set_dictionary": (C.c_int, [C.POINTER(ZStream), C.c_void_p, C.c_uint32]),
     "zs_stream_inflate": (C.c_int, [C.POINTER(ZStream), C.c_int]),
     "zs_stream_inflate_reset": (C.c_int, [C.POINTER(ZStream)]),
+    "zs_stream_inflate_reset2": (C.c_int, [C.POINTER(ZStream), C.c_int]),
     "zs_stream_inflate_end": (C.c_int, [C.POINTER(ZStream)]),
 }
+
+class GzHeader(C.Structure):
+    """zs_gz_header of include/zsgpu.h"""
+    _fields_ = [("text", C.c_int32), ("time", C.c_uint32), ("xflags", C.c_int32), ("os", C.c_int32),
+                ("extra", C.c_void_p), ("extra_max", C.c_uint32), ("extra_len", C.c_uint32),
+                ("name", C.c_void_p), ("name_max", C.c_uint32), ("comment", C.c_void_p), ("comm_max", C.c_uint32),
+                ("hcrc", C.c_int32), ("done", C.c_int32)]
+
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

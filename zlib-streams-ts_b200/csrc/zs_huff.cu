@@ -1019,14 +1019,17 @@ __global__ void frame_kernel(EncodeArgs a) {
     if (first) {
         if (a.wrap == ZS_WRAP_ZLIB) {
             unsigned header = (8u + (7u << 4)) << 8;
-            unsigned lf = a.level < 2 ? 0u : a.level < 6 ? 1u : a.level == 6 ? 2u : 3u;
+            // level_flags, deflate.ts:757-765
+            const int strategy = (int)((a.flags >> 8) & 7u);
+            unsigned lf = (strategy >= ZS_STRATEGY_HUFFMAN_ONLY || a.level < 2) ? 0u : a.level < 6 ? 1u : a.level == 6 ? 2u : 3u;
             header |= lf << 6;
             header += 31u - header % 31u;
             hp[0] = (uint8_t)(header >> 8); hp[1] = (uint8_t)header;
         } else if (a.wrap == ZS_WRAP_GZIP) {
             hp[0] = 0x1f; hp[1] = 0x8b; hp[2] = 8;
             for (int k = 3; k < 8; k++) hp[k] = 0;
-            hp[8] = a.level == 9 ? 2 : a.level < 2 ? 4 : 0;
+            const int strategy = (int)((a.flags >> 8) & 7u);
+            hp[8] = a.level == 9 ? 2 : (strategy >= ZS_STRATEGY_HUFFMAN_ONLY || a.level < 2) ? 4 : 0;   // XFL, deflate.ts:796
             hp[9] = 255;  // OS_CODE of the reference, deflate/constants.ts:30
         }
     }

@@ -53,6 +53,11 @@ struct DeflateState {
     bool header_done = false, any_part = false, trailer_done = false, have_dict = false;
     uint32_t check = 0, dict_id = 0;
     uint64_t total_in_len = 0;
+    // deflateSetHeader: a copy of the caller's gzip header fields
+    bool gz_custom = false, gz_has_extra = false, gz_has_name = false, gz_has_comment = false;
+    int gz_text = 0, gz_os = 0, gz_hcrc = 0;
+    uint32_t gz_time = 0;
+    std::vector<uint8_t> gz_extra, gz_name, gz_comment;
     DevBuf d_in, d_out, d_res;
 };
 
@@ -70,6 +75,7 @@ struct InflateState {
     int fail_code = 0;
     const char* fail_msg = "";
     uint32_t check = 0;
+    zs_gz_header* gzhead = nullptr;   // inflateGetHeader
 };
 
 int rank_of(int f) { return f * 2 - (f > 4 ? 9 : 0); }  // RANK, deflate.ts:105
@@ -92,6 +98,39 @@ void put_le32(std::vector<uint8_t>& v, uint32_t x) {
     v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 24));
 }
 
+// crc32 of a few header bytes on the host (framing only; payload checksums are computed on the GPU)
+uint32_t host_crc32(const uint8_t* p, size_t n) {
+    uint32_t c = 0xffffffffu;
+    for (size_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+    }
+    return c ^ 0xffffffffu;
+}
+
+// The gzip header with the caller's fields, deflate.ts:803-921.
+void put_gzip_header(DeflateState* st) {
+    std::vector<uint8_t> h;
+    h.push_back(0x1f); h.push_back(0x8b); h.push_back(8);
+    h.push_back((uint8_t)((st->gz_text ? 1 : 0) + (st->gz_hcrc ? 2 : 0) + (st->gz_has_extra ? 4 : 0) +
+                          (st->gz_has_name ? 8 : 0) + (st->gz_has_comment ? 16 : 0)));
+    for (int k = 0; k < 4; k++) h.push_back((uint8_t)(st->gz_time >> (8 * k)));
+    h.push_back((uint8_t)(st->level == 9 ? 2 : (st->strategy >= 2 || st->level < 2) ? 4 : 0));
+    h.push_back((uint8_t)st->gz_os);
+    if (st->gz_has_extra) {
+        const uint32_t n = (uint32_t)st->gz_extra.size() & 0xffffu;
+        h.push_back((uint8_t)n); h.push_back((uint8_t)(n >> 8));
+        h.insert(h.end(), st->gz_extra.begin(), st->gz_extra.begin() + n);
+    }
+    if (st->gz_has_name) h.insert(h.end(), st->gz_name.begin(), st->gz_name.end());        // with the terminator
+    if (st->gz_has_comment) h.insert(h.end(), st->gz_comment.begin(), st->gz_comment.end());
+    if (st->gz_hcrc) {
+        const uint32_t c = host_crc32(h.data(), h.size());
+        h.push_back((uint8_t)c); h.push_back((uint8_t)(c >> 8));
+    }
+    st->out.insert(st->out.end(), h.begin(), h.end());
+}
+
 // Compress everything buffered as one part.  `finish` makes it the last part of the stream.
 int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     zs_ctx* ctx = st->ctx;
@@ -99,13 +138,17 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     // zlib header with a preset dictionary carries FDICT + DICTID: host framing (deflate.ts:754-777)
     if (!st->header_done && st->wrap == ZS_WRAP_ZLIB && st->have_dict) {
         unsigned header = (8u + (7u << 4)) << 8;
-        unsigned lf = st->level < 2 ? 0u : st->level < 6 ? 1u : st->level == 6 ? 2u : 3u;
+        unsigned lf = (st->strategy >= 2 || st->level < 2) ? 0u : st->level < 6 ? 1u : st->level == 6 ? 2u : 3u;
         header |= lf << 6;
         header |= 0x20;
         header += 31u - header % 31u;
         st->out.push_back((uint8_t)(header >> 8));
         st->out.push_back((uint8_t)header);
         put_be32(st->out, st->dict_id);
+        st->header_done = true;
+    }
+    if (!st->header_done && st->wrap == ZS_WRAP_GZIP && st->gz_custom) {
+        put_gzip_header(st);
         st->header_done = true;
     }
     const bool whole = !st->any_part && finish && !st->header_done;  // the GPU frames a single-part stream completely
@@ -335,6 +378,23 @@ int zs_stream_deflate_pending(zs_stream* strm, uint32_t* pending, int* bits) {
     return ZS_OK;
 }
 
+// deflateSetHeader, deflate.ts:497-503
+int zs_stream_deflate_set_header(zs_stream* strm, const zs_gz_header* head) {
+    DeflateState* st = dstate(strm);
+    if (!st || st->wrap != 2 || !head) return ZS_STREAM_ERROR;
+    st->gz_custom = true;
+    st->gz_text = head->text; st->gz_time = head->time; st->gz_os = head->os; st->gz_hcrc = head->hcrc;
+    st->gz_has_extra = head->extra != nullptr;
+    st->gz_has_name = head->name != nullptr;
+    st->gz_has_comment = head->comment != nullptr;
+    st->gz_extra.clear(); st->gz_name.clear(); st->gz_comment.clear();
+    if (head->extra) st->gz_extra.assign(head->extra, head->extra + (head->extra_len & 0xffffu));
+    auto zstr = [](const uint8_t* p, std::vector<uint8_t>& v) { size_t n = 0; while (p[n]) n++; v.assign(p, p + n + 1); };
+    if (head->name) zstr(head->name, st->gz_name);
+    if (head->comment) zstr(head->comment, st->gz_comment);
+    return ZS_OK;
+}
+
 int zs_stream_deflate_end(zs_stream* strm) {
     DeflateState* st = dstate(strm);
     if (!st) return ZS_STREAM_ERROR;
@@ -387,6 +447,50 @@ int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint3
     st->have_dict = true;
     st->next_attempt = 0;
     return ZS_OK;
+}
+
+// inflateGetHeader: fill the caller's struct from the buffered start of the stream (host framing; the
+// kernel parses and checks the header on its own, inflate.ts:423-580).
+static void fill_gz_header(InflateState* st) {
+    zs_gz_header* g = st->gzhead;
+    if (!g || g->done != 0) return;
+    const std::vector<uint8_t>& b = st->in;
+    if (b.size() < 2) return;
+    if (!(b[0] == 0x1f && b[1] == 0x8b)) { g->done = -1; return; }   // a zlib stream (windowBits 32+), inflate.ts:404
+    if (b.size() < 10) return;
+    const unsigned flg = b[3];
+    size_t p = 10;
+    size_t xoff = 0, xlen = 0, noff = 0, nlen = 0, coff = 0, clen = 0;
+    if (flg & 4) {
+        if (b.size() < p + 2) return;
+        xlen = b[p] | (b[p + 1] << 8);
+        p += 2;
+        if (b.size() < p + xlen) return;
+        xoff = p; p += xlen;
+    }
+    if (flg & 8) {
+        noff = p;
+        while (p < b.size() && b[p]) p++;
+        if (p >= b.size()) return;
+        nlen = ++p - noff;
+    }
+    if (flg & 16) {
+        coff = p;
+        while (p < b.size() && b[p]) p++;
+        if (p >= b.size()) return;
+        clen = ++p - coff;
+    }
+    if (flg & 2) { if (b.size() < p + 2) return; }
+    g->text = (flg >> 0) & 1;
+    g->time = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+    g->xflags = b[8];
+    g->os = b[9];
+    g->hcrc = (flg >> 1) & 1;
+    g->extra_len = (uint32_t)xlen;
+    if ((flg & 4) && g->extra) memcpy(g->extra, b.data() + xoff, xlen < g->extra_max ? xlen : g->extra_max);
+    if (g->name) { if (flg & 8) memcpy(g->name, b.data() + noff, nlen < g->name_max ? nlen : g->name_max); else if (g->name_max) g->name[0] = 0; }
+    if (g->comment) { if (flg & 16) memcpy(g->comment, b.data() + coff, clen < g->comm_max ? clen : g->comm_max); else if (g->comm_max) g->comment[0] = 0; }
+    g->done = 1;
 }
 
 static int inflate_attempt(zs_stream* strm, InflateState* st) {
@@ -469,6 +573,7 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
             strm->avail_in = 0;
         }
         if (st->need_dict) return ZS_NEED_DICT;
+        fill_gz_header(st);
         const bool due = flush == ZS_FINISH || st->in.size() >= st->next_attempt;
         if (due && !st->in.empty()) {
             int rc = inflate_attempt(strm, st);
@@ -513,6 +618,17 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
     return ZS_OK;
 }
 
+// inflateGetHeader, inflate.ts (state._gzhead = head; head.done = 0)
+int zs_stream_inflate_get_header(zs_stream* strm, zs_gz_header* head) {
+    InflateState* st = istate(strm);
+    if (!st || !head) return ZS_STREAM_ERROR;
+    const int wb = st->window_bits;
+    if (wb < 16) return ZS_STREAM_ERROR;   // (state._wrap & 2) == 0: raw or zlib-only
+    st->gzhead = head;
+    head->done = 0;
+    return ZS_OK;
+}
+
 int zs_stream_inflate_reset(zs_stream* strm) {
     InflateState* st = istate(strm);
     if (!st) return ZS_STREAM_ERROR;
@@ -522,9 +638,30 @@ int zs_stream_inflate_reset(zs_stream* strm) {
     st->delivered = 0;
     st->next_attempt = 0;
     st->done = st->failed = st->need_dict = st->have_dict = false;
+    st->gzhead = nullptr;   // inflateResetKeep drops the header request
     strm->total_in = strm->total_out = 0;
     strm->msg = "";
     return ZS_OK;
+}
+
+// inflateReset2, inflate.ts:138-172: new windowBits, then inflateReset
+int zs_stream_inflate_reset2(zs_stream* strm, int window_bits) {
+    InflateState* st = istate(strm);
+    if (!st) return ZS_STREAM_ERROR;
+    int wb = window_bits;
+    if (wb < 0) {
+        if (wb < -16) return ZS_STREAM_ERROR;
+        wb = -wb;
+        if (wb < 8) return ZS_STREAM_ERROR;
+    } else {
+        if (wb < 48) wb &= 15;
+        if (wb && (wb < 8 || wb > 15)) return ZS_STREAM_ERROR;
+    }
+    st->window_bits = window_bits;
+    st->leftover.clear();
+    const int rc = zs_stream_inflate_reset(strm);
+    strm->adler = (window_bits > 0 && ((window_bits >> 4) + 5) & 1) ? 1u : 0u;
+    return rc;
 }
 
 int zs_stream_inflate_end(zs_stream* strm) {

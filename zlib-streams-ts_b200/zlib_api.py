@@ -49,6 +49,7 @@ class Stream:
         self._data_type = 0
         self._adler = 0
         self._state = None      # ("deflate" | "inflate", ZStream)
+        self._gzhead = None     # inflateGetHeader request
         self._keep = None
 
 
@@ -145,6 +146,81 @@ def deflateEnd(strm: Stream) -> int:
     rc = capi.load().zs_stream_deflate_end(C.byref(strm._state[1]))
     strm._state = None
     return rc
+
+
+class GzipHeader:
+    """GzipHeader of src/mod/common/types.ts:137-151."""
+
+    def __init__(self, text=0, time=0, xflags=0, os=0, extra=None, extra_len=0, name=None, comment=None, hcrc=0,
+                 extra_max=0, name_max=0, comm_max=0):
+        self._text, self._time, self._xflags, self._os = text, time, xflags, os
+        self._extra, self._extra_len, self._extra_max = extra, extra_len if extra_len else (len(extra) if extra else 0), extra_max
+        self._name, self._name_max = name, name_max
+        self._comment, self._comm_max = comment, comm_max
+        self._hcrc = hcrc
+        self._done = 0
+
+
+def deflateSetHeader(strm: Stream, head: GzipHeader) -> int:
+    """deflate.ts:497-503"""
+    if not _kind(strm, "deflate") or head is None:
+        return Z_STREAM_ERROR
+    g = capi.GzHeader()
+    keep = []
+
+    def buf(b, terminate):
+        if b is None:
+            return None
+        raw = bytes(b)
+        if terminate and (not raw or raw[-1] != 0):
+            raw = raw.split(b"\0")[0] + b"\0"
+        a = (C.c_ubyte * max(len(raw), 1)).from_buffer_copy(raw or b"\0")
+        keep.append(a)
+        return C.addressof(a)
+
+    g.text, g.time, g.xflags, g.os, g.hcrc = int(bool(head._text)), head._time & 0xffffffff, head._xflags, head._os & 0xff, int(bool(head._hcrc))
+    g.extra = buf(head._extra, False)
+    g.extra_len = head._extra_len
+    g.name = buf(head._name, True)
+    g.comment = buf(head._comment, True)
+    return capi.load().zs_stream_deflate_set_header(C.byref(strm._state[1]), C.byref(g))
+
+
+def inflateGetHeader(strm: Stream, head: GzipHeader) -> int:
+    """inflate.ts (inflateGetHeader): `head` is filled while inflate() walks the gzip header."""
+    if not _kind(strm, "inflate") or head is None:
+        return Z_STREAM_ERROR
+    g = capi.GzHeader()
+    bufs = {}
+    for field, cap in (("extra", head._extra_max), ("name", head._name_max), ("comment", head._comm_max)):
+        if cap:
+            bufs[field] = (C.c_ubyte * cap)()
+            setattr(g, field, C.addressof(bufs[field]))
+    g.extra_max, g.name_max, g.comm_max = head._extra_max, head._name_max, head._comm_max
+    rc = capi.load().zs_stream_inflate_get_header(C.byref(strm._state[1]), C.byref(g))
+    if rc == Z_OK:
+        head._done = 0
+        strm._gzhead = (head, g, bufs)
+    return rc
+
+
+def _sync_gzhead(strm: Stream):
+    gz = getattr(strm, "_gzhead", None)
+    if not gz:
+        return
+    head, g, bufs = gz
+    if g.done == 0 or head._done != 0:
+        return
+    head._done = g.done
+    if g.done == 1:
+        head._text, head._time, head._xflags, head._os, head._hcrc = g.text, g.time, g.xflags, g.os, g.hcrc
+        head._extra_len = g.extra_len
+        if "extra" in bufs:
+            head._extra = bytes(bufs["extra"][: min(g.extra_len, head._extra_max)])
+        if "name" in bufs:
+            head._name = bytes(bufs["name"]).split(b"\0")[0]
+        if "comment" in bufs:
+            head._comment = bytes(bufs["comment"]).split(b"\0")[0]
 
 
 class Ref:
@@ -246,7 +322,9 @@ def inflate(strm: Stream, flush: int) -> int:
         return Z_STREAM_ERROR
     if strm.next_out is None or (strm.next_in is None and strm.avail_in != 0):
         return Z_STREAM_ERROR
-    return _call(strm, capi.load().zs_stream_inflate, flush)
+    rc = _call(strm, capi.load().zs_stream_inflate, flush)
+    _sync_gzhead(strm)
+    return rc
 
 
 def inflateReset(strm: Stream) -> int:
@@ -256,6 +334,24 @@ def inflateReset(strm: Stream) -> int:
     rc = capi.load().zs_stream_inflate_reset(C.byref(zs))
     strm.total_in = strm.total_out = 0
     strm.msg = ""
+    strm._gzhead = None
+    return rc
+
+
+inflateResetKeep = inflateReset   # inflate.ts:96-122: the engine has no window to keep
+
+
+def inflateReset2(strm: Stream, windowBits: int) -> int:
+    """inflate.ts:138-172"""
+    if not _kind(strm, "inflate"):
+        return Z_STREAM_ERROR
+    zs = strm._state[1]
+    rc = capi.load().zs_stream_inflate_reset2(C.byref(zs), windowBits)
+    if rc == Z_OK:
+        strm.total_in = strm.total_out = 0
+        strm.msg = ""
+        strm._adler = zs.adler
+        strm._gzhead = None
     return rc
 
 
