@@ -451,6 +451,99 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             // LEN..MATCH / LIT (inflate.ts:840-1005, inffast.ts:31-214), one symbol per trip
             const unsigned lmask = (1u << lenbits) - 1u, dmask = (1u << distbits) - 1u;
             for (;;) {
+                // ---- fast path: the role of inflate_fast (inffast.ts:5-228).  While at least 12 input bytes and
+                // room for the longest match remain, symbols are decoded without the per-symbol end-of-buffer
+                // tests; anything unusual -- end of block, an invalid code, a distance that reaches the
+                // dictionary or beyond -- is left, unconsumed, to the careful loop below, which reproduces the
+                // reference's verdicts.  (deflate64 keeps to the careful loop: its matches can be 64 KiB long.)
+                if (!d64) {
+                    uint64_t in_left = br.end - br.pos, out_left = cap - op;
+                    uint32_t in_rem = in_left > 0xffffffffull ? 0xffffffffu : (uint32_t)in_left;
+                    uint32_t out_rem = out_left > 0xffffffffull ? 0xffffffffu : (uint32_t)out_left;
+                    uint8_t* wp = out + op;
+                    uint32_t made = 0;     // bytes written by the fast path since `op` was last updated
+                    // input window: the next 128 bytes, one aligned word per lane (a coalesced load); a refill is
+                    // a register shuffle.  woff = offset of the next unread byte inside the window.
+                    uint64_t win_base = br.pos & ~3ull;
+                    uint32_t woff = (uint32_t)(br.pos & 3u);
+                    uint32_t inw = 0;
+                    bool have_win = false;
+                    // one refill: up to 32 bits; the first one after an unaligned position only completes the word
+#define ZS_FAST_REFILL()                                                                                   \
+    do {                                                                                                   \
+        if (!have_win || woff >= 128u) {                                                                   \
+            if (have_win) { win_base += 128; woff -= 128u; }                                               \
+            const uint64_t wa = win_base + 4ull * lane;                                                    \
+            inw = wa < br.safe_end ? __ldg(reinterpret_cast<const unsigned*>(br.base + wa)) : 0u;          \
+            have_win = true;                                                                               \
+        }                                                                                                  \
+        const uint32_t w_ = __shfl_sync(ZS_FULL_MASK, inw, woff >> 2);                                     \
+        const unsigned mis_ = woff & 3u, take_ = 4u - mis_;                                                \
+        br.hold |= (uint64_t)(w_ >> (8u * mis_)) << br.bits;                                               \
+        br.bits += 8u * take_; woff += take_; in_rem -= take_;                                             \
+    } while (0)
+                    // a symbol pulls at most 11 bytes: two refills of 32 bits plus one that completes a word
+                    while (in_rem >= 12u && out_rem >= 258u) {
+                        if (br.bits <= 32) ZS_FAST_REFILL();
+                        if (br.bits <= 32) ZS_FAST_REFILL();   // after an alignment refill of < 4 bytes
+                        uint32_t here = lcode[(unsigned)br.hold & lmask];
+                        unsigned used = E_BITS(here);
+                        if (E_OP(here) && (E_OP(here) & 0xf0u) == 0) {  // second-level table
+                            const uint32_t first = here;
+                            here = lcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                            used = E_BITS(first) + E_BITS(here);
+                        }
+                        const unsigned lop = E_OP(here);
+                        if (lop == 0) {  // literal
+                            br.drop(used);
+                            if (lane == 0) wp[made] = (uint8_t)E_VAL(here);
+                            made++; out_rem--;
+                            continue;
+                        }
+                        if (lop & 0x60u) break;   // end of block / invalid code
+                        // length + distance: <= 15 + 5 + 15 + 13 bits; the state is restored if the pair is unusual
+                        const uint64_t hold0 = br.hold;
+                        const unsigned bits0 = br.bits;
+                        const uint64_t wb0 = win_base;
+                        const uint32_t woff0 = woff;
+                        unsigned xb = lop & 15u;
+                        const unsigned len = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
+                        br.drop(used + xb);
+                        if (br.bits <= 32) ZS_FAST_REFILL();
+                        if (br.bits <= 32) ZS_FAST_REFILL();   // after an alignment refill of < 4 bytes
+                        here = dcode[(unsigned)br.hold & dmask];
+                        used = E_BITS(here);
+                        if ((E_OP(here) & 0xf0u) == 0) {
+                            const uint32_t first = here;
+                            here = dcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                            used = E_BITS(first) + E_BITS(here);
+                        }
+                        xb = E_OP(here) & 15u;
+                        const unsigned dist = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
+                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made) {
+                            // invalid distance code, or a distance into the dictionary / too far back: undo the pair
+                            br.hold = hold0; br.bits = bits0;
+                            win_base = wb0; woff = woff0;
+                            break;
+                        }
+                        br.drop(used + xb);
+                        // copy: the source is periodic with period dist, so every byte comes from before wp + made
+                        __syncwarp();
+                        const uint8_t* sp = wp + made - dist;
+                        uint8_t* dp = wp + made;
+                        if (dist >= len) {
+                            for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j];
+                        } else {
+                            for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j % dist];
+                        }
+                        __syncwarp();
+                        made += len; out_rem -= len;
+                    }
+#undef ZS_FAST_REFILL
+                    br.pos = win_base + woff;
+                    op += made;
+                }
+                // ---- careful path: one symbol with every test of inflate() (also reached for the tail of a buffer)
                 br.refill();
                 uint32_t here = lcode[(unsigned)br.hold & lmask];
                 unsigned used = E_BITS(here);
