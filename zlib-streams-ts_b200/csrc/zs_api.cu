@@ -528,7 +528,8 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
     a.d_trailer = misc + n;
     a.d_flags = misc + 3 * (size_t)n;
     a.d_dict = d_dict; a.d_dict_rng = d_dict_rng;
-    a.force_tps = getenv("ZS_INFLATE_TPS") != nullptr;   // test hook: exercise the thread-per-stream kernel on small batches
+    // test hooks: force the thread-per-stream (1) or the warp-per-stream (-1) kernel
+    a.force_tps = getenv("ZS_INFLATE_TPS") ? 1 : getenv("ZS_INFLATE_WARP") ? -1 : 0;
     uint32_t* d_adler = misc + 4 * (size_t)n;
     uint32_t* d_crc = misc + 5 * (size_t)n;
     int rc = zs_launch_inflate(ctx, a);

@@ -152,7 +152,7 @@ struct zs_inflate_args {
     uint32_t* d_flags;    // [n]: 1 = has zlib trailer (adler), 2 = has gzip trailer (crc)
     const uint8_t* d_dict;
     const uint64_t* d_dict_rng;
-    int force_tps;        // tests: take the thread-per-stream kernel for any batch of >= 32 streams
+    int force_tps;        // tests: 1 = thread-per-stream kernel for any batch of >= 32 streams, -1 = never
 };
 int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a);
 int zs_launch_inflate_verify(zs_ctx* ctx, uint32_t n, const uint32_t* d_adler, const uint32_t* d_crc,

@@ -453,8 +453,8 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             for (;;) {
                 // ---- fast path: the role of inflate_fast (inffast.ts:5-228).  While at least 12 input bytes and
                 // room for the longest match remain, symbols are decoded without the per-symbol end-of-buffer
-                // tests; anything unusual -- end of block, an invalid code, a distance that reaches the
-                // dictionary or beyond -- is left, unconsumed, to the careful loop below, which reproduces the
+                // tests; anything unusual -- end of block, an invalid code, a distance beyond the dictionary --
+                // is left, unconsumed, to the careful loop below, which reproduces the
                 // reference's verdicts.  (deflate64 keeps to the careful loop: its matches can be 64 KiB long.)
                 if (!d64) {
                     uint64_t in_left = br.end - br.pos, out_left = cap - op;
@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         }
                         xb = E_OP(here) & 15u;
                         const unsigned dist = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
-                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made) {
-                            // invalid distance code, or a distance into the dictionary / too far back: undo the pair
+                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made + dict_len) {
+                            // invalid distance code or a distance too far back: undo the pair
                             br.hold = hold0; br.bits = bits0;
                             win_base = wb0; woff = woff0;
                             break;
@@ -531,7 +531,14 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         __syncwarp();
                         const uint8_t* sp = wp + made - dist;
                         uint8_t* dp = wp + made;
-                        if (dist >= len) {
+                        if ((uint64_t)dist > op + made) {
+                            // the match starts in the preset dictionary (inflate.ts:951-975)
+                            const int64_t s0 = (int64_t)(op + made) - (int64_t)dist;
+                            for (unsigned j = lane; j < len; j += 32) {
+                                const int64_t si = s0 + (int64_t)(dist >= len ? j : j % dist);
+                                dp[j] = si >= 0 ? out[si] : __ldg(dict + dict_len + si);
+                            }
+                        } else if (dist >= len) {
                             for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j];
                         } else {
                             for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j % dist];
@@ -664,7 +671,10 @@ int zs_launch_inflate_tps(zs_ctx* ctx, const zs_inflate_args& a);  // zs_inflate
 // warp each (cooperative copies, big lookup tables: 21.6 vs 7.3 GB/s on 8 K x 64 KiB streams).
 int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a) {
     if (a.n == 0) return ZS_OK;
-    if (a.n >= 16384 || (a.force_tps && a.n >= 32)) return zs_launch_inflate_tps(ctx, a);
+    // thread per stream needs >= 32 k streams to fill the GPU (1024 warps); measured (tools/infmatrix.py):
+    // 28-29 GB/s from 32768 streams up whatever the record size, 16-18 GB/s at 16384, where a warp per
+    // stream gives 14 (4 KiB records) to 21 GB/s (64 KiB)
+    if (a.force_tps >= 0 && (a.n >= 32768 || (a.force_tps > 0 && a.n >= 32))) return zs_launch_inflate_tps(ctx, a);
     unsigned ctas = (a.n + kWarps - 1) / kWarps;
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;
