@@ -121,7 +121,11 @@ napi_value Process(napi_env env, napi_callback_info info) {
     uint32_t ii = (uint32_t)i32(env, a[4]), ai = (uint32_t)i32(env, a[5]), oi = (uint32_t)i32(env, a[7]), ao = (uint32_t)i32(env, a[8]);
     s->next_in = in ? in + ii : nullptr; s->avail_in = ai;
     s->next_out = out ? out + oi : nullptr; s->avail_out = ao;
-    int rc = i32(env, a[1]) == 0 ? zs_stream_deflate(s, i32(env, a[2])) : zs_stream_inflate(s, i32(env, a[2]));
+    // which: 0 deflate, 1 inflate, 2 deflateParams (flush carries level + 1 | strategy << 8; it may have to
+    // flush pending input through the same buffers, deflate.ts:572-579)
+    const int which = i32(env, a[1]), f = i32(env, a[2]);
+    int rc = which == 0 ? zs_stream_deflate(s, f) : which == 1 ? zs_stream_inflate(s, f)
+                        : zs_stream_deflate_params(s, (f & 0xff) - 1, f >> 8);
     napi_value arr; napi_create_array_with_length(env, 6, &arr);
     double vals[6] = {(double)rc, (double)(ai - s->avail_in), (double)(ao - s->avail_out), (double)s->total_in,
                       (double)s->total_out, (double)s->adler};
@@ -149,11 +153,44 @@ napi_value InflateReset(napi_env env, napi_callback_info info) {
     return num(env, zs_stream_inflate_reset(strm_of(env, a[0])));
 }
 
+// control(h, op, a) -> rc      op 0 deflateReset, 2 inflateReset2(windowBits)
+napi_value Control(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3]; napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+    zs_stream* s = strm_of(env, a[0]);
+    switch (i32(env, a[1])) {
+        case 0: return num(env, zs_stream_deflate_reset(s));
+        case 2: return num(env, zs_stream_inflate_reset2(s, i32(env, a[2])));
+    }
+    return num(env, ZS_STREAM_ERROR);
+}
+// deflatePending(h) -> [rc, pending, bits]                               zs_stream_deflate_pending
+napi_value DeflatePending(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+    uint32_t pending = 0; int bits = 0;
+    int rc = zs_stream_deflate_pending(strm_of(env, a[0]), &pending, &bits);
+    napi_value arr; napi_create_array_with_length(env, 3, &arr);
+    napi_set_element(env, arr, 0, num(env, rc)); napi_set_element(env, arr, 1, num(env, pending)); napi_set_element(env, arr, 2, num(env, bits));
+    return arr;
+}
+// deflateSetHeader(h, text, time, os, hcrc, extra|null, name|null, comment|null) -> rc   zs_stream_deflate_set_header
+// (name and comment arrive zero-terminated from the facade)
+napi_value DeflateSetHeader(napi_env env, napi_callback_info info) {
+    size_t argc = 8; napi_value a[8]; napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+    zs_gz_header g; memset(&g, 0, sizeof g);
+    g.text = i32(env, a[1]); g.time = (uint32_t)i32(env, a[2]); g.os = i32(env, a[3]); g.hcrc = i32(env, a[4]);
+    size_t n = 0;
+    if (u8(env, a[5], &g.extra, &n)) g.extra_len = (uint32_t)n;
+    u8(env, a[6], &g.name, &n);
+    u8(env, a[7], &g.comment, &n);
+    return num(env, zs_stream_deflate_set_header(strm_of(env, a[0]), &g));
+}
+
 napi_value Register(napi_env env, napi_value exports) {
     const struct { const char* name; napi_callback fn; } fns[] = {
         {"init", Init}, {"deflateBatch", DeflateBatch}, {"inflateBatch", InflateBatch}, {"checksum", Checksum},
         {"streamNew", StreamNew}, {"deflateInit2", DeflateInit2}, {"inflateInit2", InflateInit2}, {"process", Process},
-        {"end", End}, {"setDictionary", SetDictionary}, {"inflateReset", InflateReset}};
+        {"end", End}, {"setDictionary", SetDictionary}, {"inflateReset", InflateReset}, {"control", Control},
+        {"deflatePending", DeflatePending}, {"deflateSetHeader", DeflateSetHeader}};
     for (auto& f : fns) {
         napi_value v; napi_create_function(env, f.name, NAPI_AUTO_LENGTH, f.fn, nullptr, &v);
         napi_set_named_property(env, exports, f.name, v);

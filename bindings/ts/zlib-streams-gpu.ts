@@ -42,9 +42,9 @@ export function inflateInit2_(strm: Stream, windowBits: number): number {       
   if (rc === Z_OK) strm._state = { h, which: 1 } as Handle;
   return rc;
 }
-function process(strm: Stream, flush: number, which: 0 | 1): number {
+function process(strm: Stream, flush: number, which: 0 | 1 | 2): number {
   const st = strm && (strm._state as Handle);
-  if (!st || st.which !== which) return Z_STREAM_ERROR;
+  if (!st || st.which !== (which === 2 ? 0 : which)) return Z_STREAM_ERROR;
   const [rc, used, made, tin, tout, adler] = addon.process(st.h, which, flush, strm.next_in, strm.next_in_index,
     strm.avail_in, strm.next_out, strm.next_out_index, strm.avail_out);
   strm.next_in_index += used; strm.avail_in -= used; strm.next_out_index += made; strm.avail_out -= made;
@@ -73,6 +73,46 @@ export function inflateReset(strm: Stream): number {                            
   const st = strm && (strm._state as Handle);
   return st && st.which === 1 ? addon.inflateReset(st.h) : Z_STREAM_ERROR;
 }
+export function deflateReset(strm: Stream): number {                                                    // deflate.ts:489
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 0) return Z_STREAM_ERROR;
+  strm.total_in = strm.total_out = 0; strm.msg = "";
+  return addon.control(st.h, 0, 0);
+}
+export const deflateResetKeep = deflateReset;                                                           // deflate.ts:444
+export function deflateParams(strm: Stream, level: number, strategy: number): number {                  // deflate.ts:553
+  // pending input is flushed with the old parameters inside the call: same buffer handling as deflate()
+  return process(strm, ((level + 1) & 0xff) | (strategy << 8), 2);
+}
+export function deflatePending(strm: Stream, pending?: { _value: number }, bits?: { _value: number }): number {   // deflate.ts:505
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 0) return Z_STREAM_ERROR;
+  const [rc, p, b] = addon.deflatePending(st.h);
+  if (pending) pending._value = p;
+  if (bits) bits._value = b;
+  return rc;
+}
+export function deflateUsed(strm: Stream, bits?: { _value: number }): number {                           // deflate.ts:518
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 0) return Z_STREAM_ERROR;
+  if (bits) bits._value = 0;   // every part the engine emits ends byte aligned
+  return Z_OK;
+}
+export function deflateSetHeader(strm: Stream, head: { _text: number; _time: number; _os: number; _hcrc: number;
+    _extra?: Uint8Array | null; _extra_len?: number; _name?: Uint8Array | null; _comment?: Uint8Array | null }): number {   // deflate.ts:497
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 0) return Z_STREAM_ERROR;
+  const z = (b?: Uint8Array | null) => { if (!b) return null; const i = b.indexOf(0); const r = new Uint8Array((i < 0 ? b.length : i) + 1); r.set(b.subarray(0, r.length - 1)); return r; };
+  return addon.deflateSetHeader(st.h, head._text ? 1 : 0, head._time >>> 0, head._os & 0xff, head._hcrc ? 1 : 0,
+    head._extra ? head._extra.subarray(0, head._extra_len ?? head._extra.length) : null, z(head._name), z(head._comment));
+}
+export function inflateReset2(strm: Stream, windowBits: number): number {                                // inflate.ts:138
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 1) return Z_STREAM_ERROR;
+  strm.total_in = strm.total_out = 0; strm.msg = "";
+  return addon.control(st.h, 2, windowBits);
+}
+export const Z_FILTERED = 1, Z_HUFFMAN_ONLY = 2, Z_RLE = 3, Z_FIXED = 4, Z_DEFAULT_STRATEGY = 0;
 export function adler32(adler: number, buf?: Uint8Array, len?: number): number {                         // adler32.ts:4
   return buf === undefined || len === undefined ? 1 : addon.checksum(0, adler, buf.subarray(0, len));
 }
