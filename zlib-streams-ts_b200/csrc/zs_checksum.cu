@@ -2,9 +2,15 @@
 //
 // Results must be bit-exact with the reference's adler32 (src/mod/common/adler32.ts:4) and crc32
 // (src/mod/common/crc32.ts:26).  The reference walks the buffer serially; here a warp owns one
-// segment, every lane folds a contiguous slice (16-byte vector loads, slicing-by-16 tables in
-// shared memory for crc32, dp4a byte sums for adler32) and the 32 lane results are merged with the
-// combine algebra (crc: multiply by x^(8*bytes_after) mod P; adler: b += a * bytes_after).
+// segment and reads it in rows of 512 bytes, lane l taking the 16-byte unit l of every row, so that
+// each load instruction is one fully coalesced 512-byte access (lane-contiguous slices cost one
+// 128-byte line per lane and load, and the L1 wavefront rate -- which the crc tables in shared
+// memory share -- capped adler32 at 64 % and crc32 at 27 % of the HBM copy bandwidth).  Both
+// checksums are linear enough for that: adler32's b is a position-weighted sum, so a unit at
+// position p adds (len - p) * sum(d) - sum(i * d_i); for crc32 a lane's running remainder is
+// advanced over the 496 bytes it skips with four more table lookups (multiplication by
+// x^(8*496) mod P, byte-sliced) before the slicing-by-16 step of its next unit.  The 32 lane
+// results are merged with the combine algebra (crc: multiply by x^(8*bytes_after) mod P).
 // HBM-bound by design: algorithmic traffic = 1 read of every input byte.
 #include <cstdio>
 
@@ -17,8 +23,10 @@ constexpr uint32_t kAdlerBase = 65521u;
 
 // x^(8 * 2^k) mod P for k = 0..47 (reflected representation), filled by the host at start-up.
 __constant__ uint32_t c_xpow[48];
-// slicing-by-16 tables, built on the host once and kept in global memory.
-__device__ uint32_t g_crc_tab[16][256];
+// slicing-by-16 tables [0..15] and the byte-sliced multiplication by x^(8*496) mod P [16..19], built
+// on the host once and kept in global memory; [20..22]: x^(8*k), x^(8*256*k), x^(8*65536*k) mod P
+// for k = 0..255, which make x^(8*n) two multiplications for n < 2^24.
+__device__ uint32_t g_crc_tab[23][256];
 
 // ---- GF(2)[x] mod P helpers (host + device) -----------------------------------------------------
 __host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
@@ -60,63 +68,30 @@ __host__ __device__ inline uint32_t adler_combine(uint32_t a1v, uint32_t a2v, ui
     return (b << 16) | a;
 }
 
-// ---- per-lane slice folds -------------------------------------------------------------------------
-// raw crc remainder (state starts at `c`, no final xor) over [p, p+n); T = smem tables [16][256]
-__device__ inline uint32_t crc_slice(const uint8_t* __restrict__ p, uint64_t n, uint32_t c,
-                                     const uint32_t (*T)[256]) {
-    // head: reach 16-byte alignment
-    while (n && (reinterpret_cast<uintptr_t>(p) & 15u)) {
-        c = T[0][(c ^ *p) & 0xffu] ^ (c >> 8);
-        ++p; --n;
-    }
-    while (n >= 16) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-        uint32_t a = v.x ^ c;
-        c = T[15][a & 0xff] ^ T[14][(a >> 8) & 0xff] ^ T[13][(a >> 16) & 0xff] ^ T[12][a >> 24] ^
-            T[11][v.y & 0xff] ^ T[10][(v.y >> 8) & 0xff] ^ T[9][(v.y >> 16) & 0xff] ^ T[8][v.y >> 24] ^
-            T[7][v.z & 0xff] ^ T[6][(v.z >> 8) & 0xff] ^ T[5][(v.z >> 16) & 0xff] ^ T[4][v.z >> 24] ^
-            T[3][v.w & 0xff] ^ T[2][(v.w >> 8) & 0xff] ^ T[1][(v.w >> 16) & 0xff] ^ T[0][v.w >> 24];
-        p += 16; n -= 16;
-    }
-    while (n) {
-        c = T[0][(c ^ *p) & 0xffu] ^ (c >> 8);
-        ++p; --n;
-    }
-    return c;
+// ---- per-segment folds ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t crc_step16(uint32_t c, const uint4 v, const uint32_t (*T)[256]) {
+    const uint32_t a = v.x ^ c;
+    return T[15][a & 0xff] ^ T[14][(a >> 8) & 0xff] ^ T[13][(a >> 16) & 0xff] ^ T[12][a >> 24] ^
+           T[11][v.y & 0xff] ^ T[10][(v.y >> 8) & 0xff] ^ T[9][(v.y >> 16) & 0xff] ^ T[8][v.y >> 24] ^
+           T[7][v.z & 0xff] ^ T[6][(v.z >> 8) & 0xff] ^ T[5][(v.z >> 16) & 0xff] ^ T[4][v.z >> 24] ^
+           T[3][v.w & 0xff] ^ T[2][(v.w >> 8) & 0xff] ^ T[1][(v.w >> 16) & 0xff] ^ T[0][v.w >> 24];
 }
-
-// adler partial sums over [p, p+n): a = sum(bytes) mod BASE, b = sum((n - j) * byte_j) mod BASE
-__device__ inline void adler_slice(const uint8_t* __restrict__ p, uint64_t n, uint32_t& a_out, uint32_t& b_out) {
-    uint32_t a = 0, b = 0;
-    while (n && (reinterpret_cast<uintptr_t>(p) & 15u)) {
-        a += *p; b += a;
-        ++p; --n;
-    }
-    a %= kAdlerBase; b %= kAdlerBase;
-    while (n >= 16) {
-        uint64_t blk = n < 2048 ? (n & ~15ull) : 2048;  // bytes before the next reduction
-        for (uint64_t k = 0; k < blk; k += 16) {
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(p + k));
-            // b += 16*a + 16*b0 + 15*b1 + ... + 1*b15 ; a += sum
-            b += a << 4;
-            b = __dp4a(v.x, 0x0d0e0f10u, b);
-            b = __dp4a(v.y, 0x090a0b0cu, b);
-            b = __dp4a(v.z, 0x05060708u, b);
-            b = __dp4a(v.w, 0x01020304u, b);
-            a = __dp4a(v.x, 0x01010101u, a);
-            a = __dp4a(v.y, 0x01010101u, a);
-            a = __dp4a(v.z, 0x01010101u, a);
-            a = __dp4a(v.w, 0x01010101u, a);
-        }
-        a %= kAdlerBase; b %= kAdlerBase;
-        p += blk; n -= blk;
-    }
-    while (n) {
-        a += *p; b += a;
-        ++p; --n;
-    }
-    a_out = a % kAdlerBase;
-    b_out = b % kAdlerBase;
+// remainder * x^(8*496) mod P
+__device__ __forceinline__ uint32_t crc_skip496(uint32_t c, const uint32_t (*T)[256]) {
+    return T[16][c & 0xff] ^ T[17][(c >> 8) & 0xff] ^ T[18][(c >> 16) & 0xff] ^ T[19][c >> 24];
+}
+// x^(8*n) mod P
+__device__ __forceinline__ uint32_t crc_xpow(uint64_t n, const uint32_t (*T)[256]) {
+    if (n >> 24) return dev_xpow8n(n);
+    uint32_t r = T[20][n & 0xff];
+    if (n >> 8) r = gf2_mulmod(r, T[21][(n >> 8) & 0xff]);
+    if (n >> 16) r = gf2_mulmod(r, T[22][n >> 16]);
+    return r;
+}
+__device__ inline uint32_t crc_bytes(const uint8_t* __restrict__ p, unsigned n, const uint32_t (*T)[256]) {
+    uint32_t c = 0;
+    for (unsigned i = 0; i < n; i++) c = T[0][(c ^ __ldg(p + i)) & 0xffu] ^ (c >> 8);
+    return c;
 }
 
 // One warp per segment, grid-stride.  KIND 0 adler32, 1 crc32.
@@ -125,9 +100,9 @@ __global__ void __launch_bounds__(256) checksum_segments_kernel(const uint8_t* _
                                                                 const uint64_t* __restrict__ off,
                                                                 const uint64_t* __restrict__ seg_len, uint32_t n,
                                                                 uint32_t* __restrict__ out) {
-    __shared__ uint32_t T[KIND ? 16 : 1][256];
+    __shared__ uint32_t T[KIND ? 23 : 1][256];
     if (KIND) {
-        for (unsigned i = threadIdx.x; i < 16 * 256; i += blockDim.x) T[i >> 8][i & 255] = g_crc_tab[i >> 8][i & 255];
+        for (unsigned i = threadIdx.x; i < 23 * 256; i += blockDim.x) T[i >> 8][i & 255] = g_crc_tab[i >> 8][i & 255];
         __syncthreads();
     }
     const unsigned lane = zs_lane();
@@ -137,33 +112,74 @@ __global__ void __launch_bounds__(256) checksum_segments_kernel(const uint8_t* _
         // segment = [off[seg], off[seg+1]) or, when seg_len is given, seg_len[seg] bytes at off[seg]
         const uint64_t beg = off[seg];
         const uint64_t len = seg_len ? seg_len[seg] : off[seg + 1] - beg;
-        // slice length: multiple of 16 so that interior slices stay vector aligned
-        uint64_t S = ((len + 31) / 32 + 15) & ~15ull;
-        if (S == 0) S = 16;
-        uint64_t sb = (uint64_t)lane * S, se = sb + S;
-        if (sb > len) sb = len;
-        if (se > len) se = len;
-        const uint64_t after = len - se;
+        const uint8_t* p = buf + beg;
+        // head: bytes before the first 16-byte boundary; body: whole 16-byte units; tail: the rest
+        uint64_t head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+        if (head > len) head = len;
+        const uint64_t units = (len - head) >> 4;
+        const unsigned tail = (unsigned)(len - head - (units << 4));
+        const uint4* q = reinterpret_cast<const uint4*>(p + head);
+        // units of this lane: lane, lane + 32, ...; `mine` of them
+        const uint64_t mine = units > lane ? (units - lane + 31) >> 5 : 0;
         if (KIND) {
-            uint32_t r = crc_slice(buf + beg + sb, se - sb, 0u, T);
-            // the 0xffffffff preset behaves like a prefix term shifted over the whole segment
-            if (lane == 0) r ^= gf2_mulmod(dev_xpow8n(se - sb), 0xffffffffu);
-            if (after) r = gf2_mulmod(dev_xpow8n(after), r);
+            uint32_t c = 0;
+            uint64_t k = 0;
+            // two rows in flight per lane
+            for (; k + 2 <= mine; k += 2) {
+                const uint4 v0 = __ldg(q + lane + 32 * k), v1 = __ldg(q + lane + 32 * (k + 1));
+                c = crc_step16(crc_skip496(c, T), v0, T);
+                c = crc_step16(crc_skip496(c, T), v1, T);
+            }
+            if (k < mine) c = crc_step16(crc_skip496(c, T), __ldg(q + lane + 32 * k), T);
+            uint32_t r = 0;
+            if (mine) {
+                const uint64_t end = head + ((lane + 32 * (mine - 1) + 1) << 4);   // end of this lane's last unit
+                r = len - end ? gf2_mulmod(crc_xpow(len - end, T), c) : c;
+            }
+            if (lane == 0 && head) r ^= gf2_mulmod(crc_xpow(len - head, T), crc_bytes(p, (unsigned)head, T));
+            if (lane == 1 && tail) r ^= crc_bytes(p + len - tail, tail, T);
+            // the 0xffffffff preset behaves like a term in front of the whole segment
+            if (lane == 2) r ^= gf2_mulmod(crc_xpow(len, T), 0xffffffffu);
             for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(ZS_FULL_MASK, r, o);
             if (lane == 0) out[seg] = ~r;
         } else {
-            uint32_t a, b;
-            adler_slice(buf + beg + sb, se - sb, a, b);
-            uint64_t bb = (uint64_t)b + (uint64_t)a * (after % kAdlerBase);
-            uint32_t b2 = (uint32_t)(bb % kAdlerBase);
+            // A = 1 + sum d_j, B = len + sum (len - j) d_j   (mod 65521)
+            uint64_t A = 0, Bq = 0;
+            uint32_t w = (uint32_t)((len - head - 16ull * lane) % kAdlerBase);   // (len - position of the unit) mod BASE
+            if (units <= lane) w = 0;
+            auto unit = [&](const uint4 v) {
+                uint32_t s = __dp4a(v.x, 0x01010101u, 0u);
+                s = __dp4a(v.y, 0x01010101u, s);
+                s = __dp4a(v.z, 0x01010101u, s);
+                s = __dp4a(v.w, 0x01010101u, s);
+                uint32_t t = __dp4a(v.x, 0x03020100u, 0u);
+                t = __dp4a(v.y, 0x07060504u, t);
+                t = __dp4a(v.z, 0x0b0a0908u, t);
+                t = __dp4a(v.w, 0x0f0e0d0cu, t);
+                A += s;
+                Bq += (uint64_t)w * s + (kAdlerBase - t);   // t <= 30600 < BASE
+                w = w >= 512u ? w - 512u : w + kAdlerBase - 512u;
+            };
+            uint64_t k = 0;
+            for (; k + 4 <= mine; k += 4) {
+                const uint4 v0 = __ldg(q + lane + 32 * k), v1 = __ldg(q + lane + 32 * (k + 1));
+                const uint4 v2 = __ldg(q + lane + 32 * (k + 2)), v3 = __ldg(q + lane + 32 * (k + 3));
+                unit(v0); unit(v1); unit(v2); unit(v3);
+            }
+            for (; k < mine; k++) unit(__ldg(q + lane + 32 * k));
+            if (lane == 0)
+                for (uint64_t j = 0; j < head; j++) { const uint32_t d = __ldg(p + j); A += d; Bq += ((len - j) % kAdlerBase) * d; }
+            if (lane == 1)
+                for (unsigned j = 0; j < tail; j++) { const uint32_t d = __ldg(p + len - tail + j); A += d; Bq += (uint64_t)(tail - j) * d; }
+            uint32_t a = (uint32_t)(A % kAdlerBase), b2 = (uint32_t)(Bq % kAdlerBase);
             for (int o = 16; o; o >>= 1) {
                 a += __shfl_xor_sync(ZS_FULL_MASK, a, o);
                 b2 += __shfl_xor_sync(ZS_FULL_MASK, b2, o);
             }
             if (lane == 0) {
-                uint32_t A = (1u + a) % kAdlerBase;
-                uint32_t B = (uint32_t)(((uint64_t)b2 + len % kAdlerBase) % kAdlerBase);
-                out[seg] = (B << 16) | A;
+                const uint32_t Av = (1u + a) % kAdlerBase;
+                const uint32_t Bv = (uint32_t)(((uint64_t)b2 + len % kAdlerBase) % kAdlerBase);
+                out[seg] = (Bv << 16) | Av;
             }
         }
     }
@@ -220,7 +236,7 @@ bool g_tables_ready[64] = {false};
 
 int ensure_tables(zs_ctx* ctx) {
     if (ctx->device < 64 && g_tables_ready[ctx->device]) return ZS_OK;
-    static uint32_t tab[16][256];
+    static uint32_t tab[23][256];
     for (unsigned n = 0; n < 256; n++) {
         uint32_t c = n;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? (kPoly ^ (c >> 1)) : (c >> 1);
@@ -231,6 +247,15 @@ int ensure_tables(zs_ctx* ctx) {
             uint32_t p = tab[k - 1][n];
             tab[k][n] = (p >> 8) ^ tab[0][p & 0xffu];
         }
+    // multiplication by x^(8*496) mod P, one table per byte of the remainder
+    const uint32_t x496 = host_xpow8n(496);
+    for (int j = 0; j < 4; j++)
+        for (unsigned n = 0; n < 256; n++) tab[16 + j][n] = gf2_mulmod((uint32_t)n << (8 * j), x496);
+    for (unsigned n = 0; n < 256; n++) {
+        tab[20][n] = host_xpow8n(n);
+        tab[21][n] = host_xpow8n((uint64_t)n << 8);
+        tab[22][n] = host_xpow8n((uint64_t)n << 16);
+    }
     uint32_t xp[48];
     uint32_t sq = 0x00800000u;
     for (int k = 0; k < 48; k++) {
