@@ -118,6 +118,32 @@ def test_ragged_chunks(gpu_ctx, oracle):
 
 
 @pytest.mark.parametrize("level", [1, 6])
+@pytest.mark.parametrize("prime", [False, True])
+def test_many_tiny_ragged_chunks(gpu_ctx, oracle, level, prime):
+    """Thousands of chunks of 0..300 bytes: one LZ77 segment holds > 100 of them, so chunk boundaries
+    fall several to a 64-position parse hop (empty chunks, 1-byte chunks, boundaries at every offset)."""
+    B = pkg("batch")
+    rng = np.random.default_rng(12 + level)
+    lens = rng.integers(0, 300, size=20000)
+    lens[rng.integers(0, lens.size, 800)] = 0
+    lens[rng.integers(0, lens.size, 50)] = rng.integers(300, 40000, 50)     # a few multi-block chunks in between
+    off = np.zeros(lens.size + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    data = make_mixed(int(off[-1]), 10)
+    r = B.deflate_batch(data, 0, level, 0, B.MODE_INDEPENDENT, flags=B.FLAG_PRIME if prime else 0, in_off=off)
+    assert int(r.out_off[-1]) == len(r.data)
+    for i in range(lens.size):
+        lo, hi = int(off[i]), int(off[i + 1])
+        d = zlib.decompressobj(-15, zdict=data[max(0, lo - 32768): lo]) if (prime and lo) else zlib.decompressobj(-15)
+        assert d.decompress(r.stream(i)) + d.flush() == data[lo:hi] and d.eof, (i, lens[i])
+    # the oracle on a sample (same verdicts as C zlib, slower)
+    for i in range(0, lens.size, 997):
+        lo, hi = int(off[i]), int(off[i + 1])
+        ret, out, used, _ = oracle.inflate(r.stream(i), -15, hi - lo + 64, data[max(0, lo - 32768): lo] if (prime and lo) else None)
+        assert ret == oracle.Z_STREAM_END and out == data[lo:hi]
+
+
+@pytest.mark.parametrize("level", [1, 6])
 def test_compressed_size_within_tolerance(gpu_ctx, oracle, level):
     B = pkg("batch")
     report = {}

@@ -317,6 +317,19 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     }
     int rc = zs_launch_lz77(ctx, p);
     if (rc != ZS_OK) return rc;
+#ifdef ZS_DEBUG_HOOKS   // the match finder's raw output (block counts, descriptors, symbols), for diffing two runs: tools/dbg_ragged2.py
+    if (const char* dump = getenv("ZS_DUMP_LZ")) {
+        std::vector<uint32_t> sym(in_len), desc(slots * 4), nblk(n_chunks);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(sym.data(), p.d_sym, in_len * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(desc.data(), p.d_blk_desc, slots * 16, cudaMemcpyDeviceToHost);
+        cudaMemcpy(nblk.data(), p.d_chunk_nblk, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(dump, "wb")) {
+            fwrite(nblk.data(), 4, nblk.size(), f); fwrite(desc.data(), 4, desc.size(), f); fwrite(sym.data(), 4, sym.size(), f);
+            fclose(f);
+        }
+    }
+#endif
     return zs_launch_huffman(ctx, p);
 }
 

@@ -518,12 +518,16 @@ __device__ __forceinline__ void parse_group(Smem& S, const LzArgs& a, const Rang
                     // sub-hop [s, b): the symbols of the visited positions before the boundary
                     const unsigned b = ps.nb - q0;
                     unsigned c;
-                    if (s < 32u) {
+                    if (b <= s) {
+                        c = 0;   // an empty chunk; position q0 + s may be the end of the range, whose mj[] slot is stale
+                    } else if (s < 32u) {
                         const uint2 m = S.mj[mj_slot(q0 + s)];
                         c = __popc(m.x & below(b));
                         if (b > 32u) {
-                            const unsigned xa = mj_exit(m.y) - 32u;   // < 32: the chain lands on b
-                            c += __popc(S.mj[mj_slot(q0 + 32u + xa)].x & below(b - 32u));
+                            // the chain enters the second batch at xa <= b - 32; at xa == b - 32 it stands on the
+                            // boundary already (and that slot of mj[] is stale when b is the end of the range)
+                            const unsigned xa = mj_exit(m.y) - 32u;
+                            if (xa < b - 32u) c += __popc(S.mj[mj_slot(q0 + 32u + xa)].x & below(b - 32u));
                         }
                     } else {
                         c = __popc(S.mj[mj_slot(q0 + s)].x & below(b - 32u));
@@ -886,6 +890,9 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     ZS_CUDA_TRY(ctx, cudaMemsetAsync(p.d_seg_counter, 0, sizeof(uint32_t), ctx->stream));
     unsigned grid = a.n_seg < (unsigned)ctx->sm_count ? a.n_seg : (unsigned)ctx->sm_count;
     if (grid == 0) return ZS_OK;
+#ifdef ZS_DEBUG_HOOKS   // fewer CTAs: segments then run (nearly) in order, which separates scheduling effects from data effects
+    if (getenv("ZS_LZ_GRID")) { unsigned g = (unsigned)atoi(getenv("ZS_LZ_GRID")); if (g && g < grid) grid = g; }
+#endif
 #ifdef ZS_LZ_PROF
     unsigned long long zero[16] = {0};
     cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
