@@ -143,6 +143,26 @@ def test_many_tiny_ragged_chunks(gpu_ctx, oracle, level, prime):
         assert ret == oracle.Z_STREAM_END and out == data[lo:hi]
 
 
+@pytest.mark.parametrize("level", [1, 5, 9])
+def test_stitched_ragged_chunks_and_determinism(gpu_ctx, oracle, level):
+    """One stream stitched from thousands of ragged chunks (with and without sync markers), twice: the
+    bytes must not depend on how segments were scheduled."""
+    B = pkg("batch")
+    rng = np.random.default_rng(40 + level)
+    lens = np.concatenate([rng.integers(0, 200, size=6000), rng.integers(900, 1100, size=300), [0, 0, 1, 959, 960, 961, 1919, 1920, 1921, 0]])
+    rng.shuffle(lens)
+    off = np.zeros(lens.size + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    data = make_mixed(int(off[-1]), 11)
+    for flags in (0, B.FLAG_SYNC):
+        r1 = B.deflate_batch(data, 0, level, 1, B.MODE_STITCHED, flags=flags, in_off=off)
+        r2 = B.deflate_batch(data, 0, level, 1, B.MODE_STITCHED, flags=flags, in_off=off)
+        assert r1.data == r2.data
+        assert zlib.decompress(r1.data) == data
+        ret, out, used, check = oracle.inflate(r1.data, 15, len(data) + 64)
+        assert ret == oracle.Z_STREAM_END and out == data and used == len(r1.data) and check == zlib.adler32(data)
+
+
 @pytest.mark.parametrize("level", [1, 6])
 def test_compressed_size_within_tolerance(gpu_ctx, oracle, level):
     B = pkg("batch")
