@@ -357,6 +357,18 @@ def main():
         ok = bool((inf.status == 1).all().item()) and bool(torch.equal(inf.out[:n], data))
         extra["inflate_output_GBps"] = n / (e0.elapsed_time(e1) / reps / 1e3) / 1e9
         extra["inflate_roundtrip_bit_exact"] = ok
+        # the HBM-bound kernels of the path: per-chunk adler32 / crc32 of the same 1 GiB (64 KiB segments)
+        for kind, name in ((0, "adler32"), (1, "crc32")):
+            B.checksum_batch_dev(data, off, kind, ctx=ctx)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                B.checksum_batch_dev(data, off, kind, ctx=ctx)
+            e1.record()
+            torch.cuda.synchronize()
+            gbps = n / (e0.elapsed_time(e1) / 3 / 1e3) / 1e9
+            extra[f"{name}_GBps"] = gbps
+            extra[f"{name}_frac_of_hbm_peak"] = gbps / hbm_peak()[0]
         line["extra"] = extra
 
     if rank == 0:
