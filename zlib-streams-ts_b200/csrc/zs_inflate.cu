@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             // LEN..MATCH / LIT (inflate.ts:840-1005, inffast.ts:31-214), one symbol per trip
             const unsigned lmask = (1u << lenbits) - 1u, dmask = (1u << distbits) - 1u;
             for (;;) {
-                // ---- fast path: the role of inflate_fast (inffast.ts:5-228).  While at least 12 input bytes and
+                // ---- fast path: the role of inflate_fast (inffast.ts:5-228).  While at least 8 input bytes and
                 // room for the longest match remain, symbols are decoded without the per-symbol end-of-buffer
                 // tests; anything unusual -- end of block, an invalid code, a distance beyond the dictionary --
                 // is left, unconsumed, to the careful loop below, which reproduces the
@@ -462,30 +462,29 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                     uint32_t out_rem = out_left > 0xffffffffull ? 0xffffffffu : (uint32_t)out_left;
                     uint8_t* wp = out + op;
                     uint32_t made = 0;     // bytes written by the fast path since `op` was last updated
-                    // input window: the next 128 bytes, one aligned word per lane (a coalesced load); a refill is
-                    // a register shuffle.  woff = offset of the next unread byte inside the window.
-                    uint64_t win_base = br.pos & ~3ull;
-                    uint32_t woff = (uint32_t)(br.pos & 3u);
-                    uint32_t inw = 0;
-                    bool have_win = false;
-                    // one refill: up to 32 bits; the first one after an unaligned position only completes the word
+                    // input window: the 128 bytes from the current position, one word per lane (two coalesced
+                    // loads and a funnel shift per lane when the position is not word aligned); a refill is a
+                    // register shuffle.  woff = offset of the next unread byte inside the window, a multiple of 4.
+                    uint64_t win_base = br.pos;
+                    uint32_t woff = 0;
+                    uint32_t inw;
+#define ZS_LOAD_WINDOW()                                                                                   \
+    do {                                                                                                   \
+        const uint64_t wa_ = (win_base & ~3ull) + 4ull * lane;                                             \
+        const uint32_t lo_ = wa_ < br.safe_end ? __ldg(reinterpret_cast<const unsigned*>(br.base + wa_)) : 0u;          \
+        const uint32_t hi_ = wa_ + 4 < br.safe_end ? __ldg(reinterpret_cast<const unsigned*>(br.base + wa_ + 4)) : 0u;  \
+        inw = __funnelshift_r(lo_, hi_, 8u * (unsigned)(win_base & 3u));                                   \
+    } while (0)
 #define ZS_FAST_REFILL()                                                                                   \
     do {                                                                                                   \
-        if (!have_win || woff >= 128u) {                                                                   \
-            if (have_win) { win_base += 128; woff -= 128u; }                                               \
-            const uint64_t wa = win_base + 4ull * lane;                                                    \
-            inw = wa < br.safe_end ? __ldg(reinterpret_cast<const unsigned*>(br.base + wa)) : 0u;          \
-            have_win = true;                                                                               \
-        }                                                                                                  \
-        const uint32_t w_ = __shfl_sync(ZS_FULL_MASK, inw, woff >> 2);                                     \
-        const unsigned mis_ = woff & 3u, take_ = 4u - mis_;                                                \
-        br.hold |= (uint64_t)(w_ >> (8u * mis_)) << br.bits;                                               \
-        br.bits += 8u * take_; woff += take_; in_rem -= take_;                                             \
+        if (woff >= 128u) { win_base += 128; woff = 0; ZS_LOAD_WINDOW(); }                                 \
+        br.hold |= (uint64_t)__shfl_sync(ZS_FULL_MASK, inw, woff >> 2) << br.bits;                         \
+        br.bits += 32; woff += 4; in_rem -= 4;                                                             \
     } while (0)
-                    // a symbol pulls at most 11 bytes: two refills of 32 bits plus one that completes a word
-                    while (in_rem >= 12u && out_rem >= 258u) {
+                    ZS_LOAD_WINDOW();
+                    // a symbol pulls at most 8 bytes: two refills of 32 bits
+                    while (in_rem >= 8u && out_rem >= 258u) {
                         if (br.bits <= 32) ZS_FAST_REFILL();
-                        if (br.bits <= 32) ZS_FAST_REFILL();   // after an alignment refill of < 4 bytes
                         uint32_t here = lcode[(unsigned)br.hold & lmask];
                         unsigned used = E_BITS(here);
                         if (E_OP(here) && (E_OP(here) & 0xf0u) == 0) {  // second-level table
@@ -510,7 +509,6 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         const unsigned len = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
                         br.drop(used + xb);
                         if (br.bits <= 32) ZS_FAST_REFILL();
-                        if (br.bits <= 32) ZS_FAST_REFILL();   // after an alignment refill of < 4 bytes
                         here = dcode[(unsigned)br.hold & dmask];
                         used = E_BITS(here);
                         if ((E_OP(here) & 0xf0u) == 0) {
@@ -547,6 +545,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         made += len; out_rem -= len;
                     }
 #undef ZS_FAST_REFILL
+#undef ZS_LOAD_WINDOW
                     br.pos = win_base + woff;
                     op += made;
                 }
