@@ -138,6 +138,20 @@ def inflate(data, window_bits: int = 15, out_cap: int | None = None, dictionary=
     return ret, bytes(out[: ol.value]) if ol.value else b"", used.value, ck.value
 
 
+def deflate64_encode(data, max_len: int = 65538) -> bytes:
+    """Raw deflate64 stream of `data` (test-side encoder, oracle/deflate64_enc.c)."""
+    p, n, k = _buf(data)
+    cap = n + n // 2 + 64
+    out = (C.c_ubyte * cap)()
+    L = lib()
+    L.zo_deflate64_encode.restype = C.c_long
+    L.zo_deflate64_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_int, C.c_void_p, C.c_size_t]
+    r = L.zo_deflate64_encode(p, n, max_len, 1, C.addressof(out), cap)
+    if r < 0:
+        raise RuntimeError(f"deflate64 encoder failed: {r}")
+    return bytes(out[:r])
+
+
 def block_types(data, window_bits: int = -15):
     """Set of block types (0 stored, 1 fixed, 2 dynamic) of a complete stream."""
     ret, out, used, _ = inflate(data, window_bits)

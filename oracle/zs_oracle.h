@@ -86,6 +86,11 @@ int zo_inflate_oneshot(const uint8_t* in, size_t in_len, int window_bits, const 
  * (counts[3]); not thread safe. */
 void zo_inflate_last_blocks(uint32_t* counts);
 
+/* Test aid: raw deflate64 encoder (one fixed-Huffman block, greedy matching in a 64 KiB window); the
+ * reference has none.  max_len 258 stays within length codes <= 284, 65538 allows code 285.  Returns
+ * the bytes written, -1 out of memory, -2 output too small.  See deflate64_enc.c. */
+long zo_deflate64_encode(const uint8_t* in, size_t n, unsigned max_len, int final, uint8_t* out, size_t cap);
+
 /* ---- deflate: deflate/deflate.ts, trees.ts, deflate/utils.ts ---------------------------- */
 
 /* Upper bound of deflateBound for windowBits 15 / memLevel 8, deflate.ts:615-674.

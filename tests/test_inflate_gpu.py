@@ -198,3 +198,36 @@ def test_thread_per_stream_kernel_matches_oracle(gpu_ctx, oracle, fixtures64, mo
     kats = [bytes.fromhex("4b1cfdff07a3e5030000")] * 1024
     r = _run(kats, -16, [70000] * 1024)
     assert all(r.output(i) == b"a" * 66539 for i in (0, 511, 1023))
+
+
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_generated_deflate64_streams(gpu_ctx, oracle, monkeypatch, kernel):
+    """Config 5 of the scope table beyond the ten fixtures: raw deflate64 streams from the test-side
+    encoder -- distances up to 65536 (codes 30/31), lengths up to 65538 (code 285 with 16 extra bits) --
+    decoded with windowBits -16 by both kernels, bit-exact with the oracle; the same streams are a
+    data error under windowBits -15."""
+    monkeypatch.setenv("ZS_INFLATE_TPS" if kernel == "thread" else "ZS_INFLATE_WARP", "1")
+    B = pkg("batch")
+    rnd = np.random.default_rng(65)
+    blk = rnd.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    cases = []
+    for i in range(48):
+        gap = int(rnd.integers(33000, 62000))
+        far = blk + rnd.integers(0, 256, gap, dtype=np.uint8).tobytes() + blk + bytes(int(rnd.integers(0, 50))) + blk
+        runs = bytes(int(rnd.integers(300, 90000))) + b"xyz" * int(rnd.integers(100, 30000)) + bytes([i]) * int(rnd.integers(259, 70000))
+        cases += [far, runs, make_text(int(rnd.integers(1, 200000)), 70 + i), b""]
+    streams, raws = [], []
+    for j, c in enumerate(cases):
+        streams.append(oracle.deflate64_encode(c, 65538 if j % 3 else 258))
+        raws.append(c)
+    caps = [len(c) + 16 for c in raws]
+    res = B.inflate_batch(streams, -16, caps, ctx=gpu_ctx)
+    for j, c in enumerate(raws):
+        assert res.status[j] == oracle.Z_STREAM_END, (j, res.status[j])
+        assert res.output(j) == c, j
+        assert int(res.in_used[j]) == len(streams[j])
+    # plain deflate must reject what only deflate64 allows
+    bad = B.inflate_batch(streams[:8], -15, caps[:8], ctx=gpu_ctx)
+    for j in range(8):
+        ret, _, _, _ = oracle.inflate(streams[j], -15, caps[j])
+        assert bad.status[j] == ret, (j, bad.status[j], ret)

@@ -213,3 +213,30 @@ def test_build_tree_matches_stream(oracle):
     mc = oracle.lib().zo_build_tree(0, f.ctypes.data, lens.ctypes.data, codes.ctypes.data, C.byref(ol), C.byref(sl))
     assert mc >= 256 and lens.max() <= 15
     assert sum(2.0 ** -int(l) for l in lens if l) == 1.0      # complete prefix code
+
+
+def _d64_cases():
+    import numpy as np
+    rnd = np.random.default_rng(64)
+    blk = rnd.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    far = blk + rnd.integers(0, 256, 50000, dtype=np.uint8).tobytes() + blk + bytes(10) + blk   # repeats 53000 back: distance codes 30/31
+    runs = bytes(70000) + b"xyz" * 30000 + bytes([7]) * 66000                                       # matches far longer than 258: code 285
+    text = (b"the quick brown fox jumps over the lazy dog. " * 3000)[:120001]
+    return {"far": far, "runs": runs, "text": text, "empty": b"", "one": b"a"}
+
+
+def test_deflate64_test_encoder_roundtrip(oracle):
+    """The test-side deflate64 encoder (oracle/deflate64_enc.c) against the restated reference decoder:
+    distances above 32768 and lengths above 258 must decode under windowBits -16 and must NOT decode
+    as plain deflate."""
+    for name, data in _d64_cases().items():
+        for max_len in (258, 65538):
+            z = oracle.deflate64_encode(data, max_len)
+            ret, out, used, _ = oracle.inflate(z, -16, len(data) + 64)
+            assert ret == oracle.Z_STREAM_END and out == data and used == len(z), (name, max_len)
+    z = oracle.deflate64_encode(_d64_cases()["far"], 258)
+    assert len(z) < 57500                        # 53000 random bytes at ~8.4 bits each; the two far repeats (distance 53000) cost nothing
+    ret, out, _, _ = oracle.inflate(z, -15, 200000)
+    assert ret == oracle.Z_DATA_ERROR            # distance codes 30/31 are invalid in plain deflate
+    z = oracle.deflate64_encode(_d64_cases()["runs"], 65538)
+    assert len(z) < 400                          # 70000 zeros in two symbols

@@ -13,7 +13,7 @@
 //    own Z_SYNC_FLUSH marker (empty stored block) and is byte aligned; the wrapper trailer of a
 //    multi-part stream is assembled from the per-part checksums with *_combine.
 //  * inflate: input is buffered and the stream is decoded from its start whenever enough new input
-//    has arrived (every call below 4 MiB, then geometrically); bytes decoded so far are final and
+//    has arrived (every call below 256 KiB or on a flush request, then whenever it has grown by half); bytes decoded so far are final and
 //    are handed out immediately, Z_STREAM_END gives back the unused input.
 #include <cstdio>
 #include <cstring>
@@ -574,11 +574,13 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         }
         if (st->need_dict) return ZS_NEED_DICT;
         fill_gz_header(st);
-        const bool due = flush == ZS_FINISH || st->in.size() >= st->next_attempt;
+        // every call while the stream is short, then whenever it has grown by half (the decode restarts from
+        // the beginning, so this keeps the total work linear); any flush request decodes now
+        const bool due = flush != ZS_NO_FLUSH || st->in.size() >= st->next_attempt;
         if (due && !st->in.empty()) {
             int rc = inflate_attempt(strm, st);
             if (rc != ZS_OK) return rc;
-            st->next_attempt = st->in.size() < (4u << 20) ? st->in.size() + 1 : st->in.size() + st->in.size() / 4;
+            st->next_attempt = st->in.size() < (256u << 10) ? st->in.size() + 1 : st->in.size() + st->in.size() / 2;
             if (st->need_dict) {
                 strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
                 return ZS_NEED_DICT;
