@@ -882,6 +882,8 @@ __global__ void zero_output_kernel(uint8_t* out, const zs_deflate_result* result
 }
 
 constexpr int kEncThreads = 256;
+constexpr int kSymPerThread = 4;
+constexpr unsigned kStageWords = kEncThreads * kSymPerThread * 2 + 4;   // up to 48+ bits per symbol, plus a lead-in word
 
 // compress_block (trees.ts:476-520) for one block per CTA
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
@@ -890,7 +892,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
     const uint32_t chunk = (uint32_t)(gid / a.max_bpc), j = (uint32_t)(gid % a.max_bpc);
     if (j >= a.chunk_nblk[chunk]) return;
     __shared__ uint32_t s_code[320];
-    __shared__ uint32_t s_stage[kEncThreads * 2 + 4];  // up to 48+ bits per symbol, plus a lead-in word
+    __shared__ uint32_t s_stage[kStageWords];
     __shared__ uint32_t s_warp[kEncThreads / 32];
     const unsigned t = threadIdx.x, lane = t & 31u, wid = t >> 5;
     uint32_t* out32 = reinterpret_cast<uint32_t*>(a.out);
@@ -932,39 +934,49 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
     __syncthreads();
 
     const uint32_t* sym = a.sym + (int64_t)cbase + (int32_t)sym0;   // sym0 may be negative (zs_lz77.cu, close_block)
-    for (uint32_t tile = 0; tile < nsym; tile += kEncThreads) {
-        const uint32_t i = tile + t;
-        uint64_t v = 0;
-        unsigned nb = 0;
-        if (i < nsym) {
-            const uint32_t s = sym[i];
-            const unsigned dist = s >> 16, lc = s & 0xffffu;
-            if (dist == 0) {
-                const uint32_t e = s_code[lc];
-                v = e & 0xffffu; nb = e >> 16;
-            } else {
-                const unsigned l3 = lc - 3u;
-                const unsigned lcode = zs_len_code(l3);
-                uint32_t e = s_code[257u + lcode];
-                v = e & 0xffffu; nb = e >> 16;
-                unsigned xb = zs_len_xbits(lcode);
-                v |= (uint64_t)(l3 - zs_len_base(lcode)) << nb; nb += xb;
-                const unsigned d1 = dist - 1u;
-                const unsigned dcode = zs_dist_code(d1);
-                e = s_code[288u + dcode];
-                v |= (uint64_t)(e & 0xffffu) << nb; nb += e >> 16;
-                xb = zs_dist_xbits(dcode);
-                v |= (uint64_t)(d1 - zs_dist_base(dcode)) << nb; nb += xb;
+    // Tiles of kEncThreads * kSymPerThread symbols; a thread owns kSymPerThread consecutive symbols, so one
+    // CTA-wide scan (and three barriers) serves 1024 symbols.
+    constexpr uint32_t kTile = kEncThreads * kSymPerThread;
+    for (uint32_t tile = 0; tile < nsym; tile += kTile) {
+        uint64_t v[kSymPerThread];
+        unsigned nb[kSymPerThread];
+        unsigned mine = 0;
+#pragma unroll
+        for (int u = 0; u < kSymPerThread; u++) {
+            const uint32_t i = tile + t * kSymPerThread + u;
+            v[u] = 0; nb[u] = 0;
+            if (i < nsym) {
+                const uint32_t s = sym[i];
+                const unsigned dist = s >> 16, lc = s & 0xffffu;
+                if (dist == 0) {
+                    const uint32_t e = s_code[lc];
+                    v[u] = e & 0xffffu; nb[u] = e >> 16;
+                } else {
+                    const unsigned l3 = lc - 3u;
+                    const unsigned lcode = zs_len_code(l3);
+                    uint32_t e = s_code[257u + lcode];
+                    uint64_t vv = e & 0xffffu; unsigned n = e >> 16;
+                    unsigned xb = zs_len_xbits(lcode);
+                    vv |= (uint64_t)(l3 - zs_len_base(lcode)) << n; n += xb;
+                    const unsigned d1 = dist - 1u;
+                    const unsigned dcode = zs_dist_code(d1);
+                    e = s_code[288u + dcode];
+                    vv |= (uint64_t)(e & 0xffffu) << n; n += e >> 16;
+                    xb = zs_dist_xbits(dcode);
+                    vv |= (uint64_t)(d1 - zs_dist_base(dcode)) << n; n += xb;
+                    v[u] = vv; nb[u] = n;
+                }
             }
+            mine += nb[u];
         }
-        // CTA-wide exclusive scan of nb
-        unsigned incl = nb;
+        // CTA-wide exclusive scan of the per-thread bit counts
+        unsigned incl = mine;
         for (int o = 1; o < 32; o <<= 1) {
             unsigned x = __shfl_up_sync(ZS_FULL_MASK, incl, o);
             if ((int)lane >= o) incl += x;
         }
         if (lane == 31) s_warp[wid] = incl;
-        for (unsigned k = t; k < kEncThreads * 2 + 4; k += kEncThreads) s_stage[k] = 0;
+        for (unsigned k = t; k < kStageWords; k += kEncThreads) s_stage[k] = 0;
         __syncthreads();
         unsigned wbase = 0, tile_bits = 0;
         for (unsigned k = 0; k < kEncThreads / 32; k++) {
@@ -973,14 +985,18 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(EncodeArgs a) {
             tile_bits += x;
         }
         const unsigned lead = (unsigned)(pos & 31u);
-        const unsigned off = lead + wbase + incl - nb;
-        if (nb) {
-            const unsigned w = off >> 5, sh = off & 31u;
-            atomicOr(&s_stage[w], (uint32_t)(v << sh));
-            if (sh + nb > 32) {
-                const uint64_t rest = v >> (32 - sh);
-                atomicOr(&s_stage[w + 1], (uint32_t)rest);
-                if (sh + nb > 64) atomicOr(&s_stage[w + 2], (uint32_t)(rest >> 32));
+        unsigned off = lead + wbase + incl - mine;
+#pragma unroll
+        for (int u = 0; u < kSymPerThread; u++) {
+            if (nb[u]) {
+                const unsigned w = off >> 5, sh = off & 31u;
+                atomicOr(&s_stage[w], (uint32_t)(v[u] << sh));
+                if (sh + nb[u] > 32) {
+                    const uint64_t rest = v[u] >> (32 - sh);
+                    atomicOr(&s_stage[w + 1], (uint32_t)rest);
+                    if (sh + nb[u] > 64) atomicOr(&s_stage[w + 2], (uint32_t)(rest >> 32));
+                }
+                off += nb[u];
             }
         }
         __syncthreads();
