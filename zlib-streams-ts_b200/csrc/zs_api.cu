@@ -89,6 +89,9 @@ __global__ void make_chunk_offsets_kernel(uint64_t* off, uint64_t len, uint64_t 
     }
 }
 
+// Every entry point works on the context's device, whatever the caller's current device is.
+inline void bind_device(zs_ctx* ctx) { cudaSetDevice(ctx->device); }
+
 int bad_arg(zs_ctx* ctx, const char* msg) {
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
     return ZS_STREAM_ERROR;
@@ -188,6 +191,7 @@ const char* zs_last_error(const zs_ctx* ctx) { return ctx ? ctx->err : "no conte
 uint64_t zs_ctx_launch_count(const zs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int zs_ctx_synchronize(zs_ctx* ctx) {
+    if (ctx) bind_device(ctx);
     if (!ctx) return ZS_STREAM_ERROR;
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ZS_OK;
@@ -212,11 +216,13 @@ uint32_t zs_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2) { return zs
 // ---- checksums ---------------------------------------------------------------------------------------
 int zs_checksum_batch_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, const uint64_t* d_off, uint32_t n,
                           uint32_t* d_out) {
+    if (ctx) bind_device(ctx);
     if (!ctx || (kind != 0 && kind != 1) || (n && (!d_buf || !d_off || !d_out))) return bad_arg(ctx, "checksum: bad arguments");
     return zs_launch_checksum_segments(ctx, kind, d_buf, d_off, nullptr, n, d_out);
 }
 
 int zs_checksum_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, uint32_t init, uint32_t* result) {
+    if (ctx) bind_device(ctx);
     if (!ctx || (kind != 0 && kind != 1) || !result || (len && !d_buf)) return bad_arg(ctx, "checksum: bad arguments");
     uint32_t* d_res = (uint32_t*)zs_scratch_get(ctx, SCR_SMALL, 256);
     if (!d_res) return ZS_MEM_ERROR;
@@ -228,6 +234,7 @@ int zs_checksum_dev(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, u
 }
 
 int zs_checksum(zs_ctx* ctx, int kind, const uint8_t* buf, uint64_t len, uint32_t init, uint32_t* result) {
+    if (ctx) bind_device(ctx);
     if (!ctx || !result || (len && !buf)) return bad_arg(ctx, "checksum: bad arguments");
     uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, len + 64);
     if (!d_in) return ZS_MEM_ERROR;
@@ -240,6 +247,7 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
                          uint32_t n_chunks, uint32_t chunk_size, uint32_t max_chunk, uint32_t history, int level,
                          int wrap, int mode, uint32_t flags, uint8_t* d_out, uint64_t out_cap, uint64_t* d_out_off,
                          uint64_t* d_out_bits, uint32_t* d_checks, zs_deflate_result* d_result) {
+    if (ctx) bind_device(ctx);
     if (!ctx) return ZS_STREAM_ERROR;
     if (level == -1) level = 6;
     // argument rules of deflateInit2_ (deflate.ts:263-297) that apply to the batch form
@@ -452,6 +460,7 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
 int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
                      uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out, uint64_t out_cap,
                      uint64_t* out_off, uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
+    if (ctx) bind_device(ctx);
     if (!ctx) return ZS_STREAM_ERROR;
     if (!out || !result || (in_len && !in) || n_chunks == 0) return bad_arg(ctx, "deflate: null buffer or zero chunks");
     uint32_t max_chunk = chunk_size;
@@ -505,6 +514,7 @@ int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint
 }
 
 int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits) {
+    if (ctx) bind_device(ctx);
     if (!ctx || !d_dst || (n_bits && !d_src)) return bad_arg(ctx, "bit_concat: bad arguments");
     return zs_launch_bit_concat(ctx, d_dst, dst_bit_off, d_src, n_bits);
 }
@@ -513,6 +523,7 @@ int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const u
 int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint32_t n, int window_bits,
                          uint8_t* d_out, const uint64_t* d_out_off, uint64_t* d_out_len, uint64_t* d_in_used,
                          uint32_t* d_checks, int32_t* d_status, const uint8_t* d_dict, const uint64_t* d_dict_rng) {
+    if (ctx) bind_device(ctx);
     if (!ctx) return ZS_STREAM_ERROR;
     if (n == 0) return ZS_OK;
     if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return bad_arg(ctx, "inflate: null buffer");
@@ -567,6 +578,7 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
 int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits, uint8_t* out,
                      const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks, int32_t* status,
                      const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total) {
+    if (ctx) bind_device(ctx);
     if (!ctx) return ZS_STREAM_ERROR;
     if (n == 0) return ZS_OK;
     if (!in_off || !out_off || !out_len || !status) return bad_arg(ctx, "inflate: null buffer");
@@ -608,6 +620,7 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
 }
 
 int zs_inflate_last_details(zs_ctx* ctx, int32_t* detail, uint32_t n) {
+    if (ctx) bind_device(ctx);
     if (!ctx || !detail) return ZS_STREAM_ERROR;
     if (!ctx->d_last_detail || n > ctx->last_detail_n) return bad_arg(ctx, "inflate: no details available");
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(detail, ctx->d_last_detail, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1186,6 +1186,7 @@ int zs_launch_bit_concat(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, cons
 extern "C" int zs_huffman_blocks(zs_ctx* ctx, const uint32_t* freq, const uint32_t* in_len, uint32_t n, uint32_t* code,
                                  uint32_t* type, uint64_t* bits) {
     if (!ctx) return ZS_STREAM_ERROR;
+    cudaSetDevice(ctx->device);
     if (n == 0) return ZS_OK;
     if (!freq || !in_len) return ZS_STREAM_ERROR;
     uint32_t *d_freq = nullptr, *d_nblk = nullptr, *d_desc = nullptr, *d_code = nullptr, *d_hdr = nullptr;

@@ -826,12 +826,14 @@ __global__ void literal_symbols_kernel(const uint8_t* in, uint32_t* sym, uint64_
 }  // namespace
 
 int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static bool attr_set[64] = {false};
+    const int dev_slot = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    if (!attr_set[dev_slot] || ctx->device >= 64) {
         ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(lz77_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        attr_set = true;
+        attr_set[dev_slot] = true;
     }
     LzArgs a;
     const uintptr_t first = reinterpret_cast<uintptr_t>(p.d_in) - p.history;

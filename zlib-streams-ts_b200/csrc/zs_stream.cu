@@ -134,6 +134,7 @@ void put_gzip_header(DeflateState* st) {
 // Compress everything buffered as one part.  `finish` makes it the last part of the stream.
 int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     zs_ctx* ctx = st->ctx;
+    cudaSetDevice(ctx->device);
     const size_t hist_len = st->hist.size(), n = st->in.size();
     // zlib header with a preset dictionary carries FDICT + DICTID: host framing (deflate.ts:754-777)
     if (!st->header_done && st->wrap == ZS_WRAP_ZLIB && st->have_dict) {
