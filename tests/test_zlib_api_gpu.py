@@ -237,3 +237,77 @@ def test_decompression_stream_deflate64(gpu_ctx, fixtures64):
     f = next(x for x in fixtures64 if x["name"] == "10k_lines.deflate64")
     out = S.DecompressionStream("deflate64-raw").transform(f["data"])
     assert len(out) == f["out_len"] and zlib.crc32(out) == f["crc32"]
+
+
+@pytest.mark.parametrize("wbits", [15, 31, -15])
+def test_incremental_inflate_of_a_long_stream(gpu_ctx, wbits):
+    """A multi-megabyte stream fed in 32 KiB pieces (the slicing of src/mod/streams.ts:7): decoding resumes
+    at block boundaries, the trailer is checked after the last attempt, input behind the end is handed back."""
+    import time
+    from conftest import make_mixed
+    Z = _Z()
+    data = make_mixed(6 << 20, 77) + make_text(1 << 20, 78)
+    co = zlib.compressobj(6, zlib.DEFLATED, wbits)
+    stream = co.compress(data) + co.flush()
+    tail = b"TRAILING-GARBAGE"
+    t0 = time.time()
+    for corrupt in (False, True):
+        src = bytearray(stream)
+        if corrupt and wbits > 0:
+            src[-1] ^= 0x55                      # last trailer byte: ISIZE (gzip) / adler32 (zlib)
+        src += tail
+        s = Z.createInflateStream()
+        assert Z.inflateInit2_(s, wbits) == Z.Z_OK
+        out = bytearray()
+        pos, r = 0, Z.Z_OK
+        while r == Z.Z_OK:
+            piece = bytes(src[pos: pos + 32768])
+            s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+            while True:
+                buf = bytearray(65536)
+                s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+                r = Z.inflate(s, Z.Z_NO_FLUSH)
+                out += buf[: s.next_out_index]
+                if r != Z.Z_OK or (s.avail_in == 0 and s.avail_out != 0):
+                    break
+            pos += len(piece) - s.avail_in
+            if pos >= len(src) and r == Z.Z_OK:
+                r = Z.inflate(s, Z.Z_FINISH)
+                break
+        if corrupt and wbits > 0:
+            assert r == Z.Z_DATA_ERROR and s.msg in ("incorrect data check", "incorrect length check"), (r, s.msg)
+            assert bytes(out) == data            # everything decoded before the check is still delivered
+        else:
+            assert r == Z.Z_STREAM_END, (r, s.msg)
+            assert bytes(out) == data
+            assert s.total_in == len(stream) and pos == len(stream), (s.total_in, pos, len(stream))
+            if wbits == 15:
+                assert s._adler == zlib.adler32(data)
+            if wbits == 31:
+                assert s._adler == zlib.crc32(data)
+        assert Z.inflateEnd(s) == Z.Z_OK
+    assert time.time() - t0 < 60                 # linear: a restart-from-scratch decoder needs minutes here
+
+
+def test_incremental_inflate_truncated(gpu_ctx):
+    Z = _Z()
+    data = make_text(900000, 79)
+    stream = zlib.compress(data, 6)[:-300000 // 100]     # cut inside the last blocks
+    s = Z.createInflateStream()
+    assert Z.inflateInit(s) == Z.Z_OK
+    out = bytearray()
+    for pos in range(0, len(stream), 10000):
+        piece = stream[pos: pos + 10000]
+        s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+        buf = bytearray(1 << 20)
+        s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+        assert Z.inflate(s, Z.Z_NO_FLUSH) == Z.Z_OK
+        out += buf[: s.next_out_index]
+    buf = bytearray(1 << 20)
+    s.next_in, s.next_in_index, s.avail_in = b"", 0, 0
+    s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+    assert Z.inflate(s, Z.Z_FINISH) == Z.Z_BUF_ERROR     # inflate.ts:1092-1098
+    out += buf[: s.next_out_index]
+    d = zlib.decompressobj()
+    assert bytes(out) == d.decompress(stream)            # exactly what C zlib can decode from the same bytes
+    assert Z.inflateEnd(s) == Z.Z_OK

@@ -14,7 +14,7 @@ enum {
     SCR_D_PR = 10, SCR_D_OFF = 11, SCR_D_CHECKS = 12,
     SCR_I_MISC = 13,
     SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
-    SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23,
+    SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23, SCR_I_RESUME = 24,
 };
 
 void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
@@ -552,6 +552,15 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
     a.d_trailer = misc + n;
     a.d_flags = misc + 3 * (size_t)n;
     a.d_dict = d_dict; a.d_dict_rng = d_dict_rng;
+    a.d_start_bit = nullptr; a.d_block_mark = nullptr;
+    if (ctx->inflate_resume && n == 1) {
+        // one stream of the streaming shim: [0] start bit (in), [1..2] block mark (out)
+        uint64_t* d_rs = (uint64_t*)zs_scratch_get(ctx, SCR_I_RESUME, 64);
+        if (!d_rs) return ZS_MEM_ERROR;
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_rs, &ctx->inflate_start_bit, 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->inflate_start_bit != ~0ull) a.d_start_bit = d_rs;
+        a.d_block_mark = d_rs + 1;
+    }
     // test hooks: force the thread-per-stream (1) or the warp-per-stream (-1) kernel
     a.force_tps = getenv("ZS_INFLATE_TPS") ? 1 : getenv("ZS_INFLATE_WARP") ? -1 : 0;
     uint32_t* d_adler = misc + 4 * (size_t)n;
@@ -615,6 +624,10 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
     if (in_used) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(in_used, d_used, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (checks) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->inflate_resume && n == 1) {
+        const uint64_t* d_rs = (const uint64_t*)zs_scratch_get(ctx, SCR_I_RESUME, 64);
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->inflate_mark, d_rs + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ZS_OK;
 }

@@ -21,7 +21,7 @@ struct zs_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     // grow-only device scratch, one slot per purpose (see zs_api.cu)
-    zs_scratch scr[24];
+    zs_scratch scr[32];
     // pinned host staging for small results
     void* h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -30,6 +30,10 @@ struct zs_ctx {
     uint32_t last_detail_n = 0;
     // copy streams + events of the pipelined host-buffer path (zs_deflate_batch)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_res = nullptr;   // host-buffer path: H2D, bulk D2H, small result readbacks
+    // streaming shim -> zs_inflate_batch (one stream): resume request and the block mark that comes back
+    bool inflate_resume = false;
+    uint64_t inflate_start_bit = 0;
+    uint64_t inflate_mark[2] = {0, 0};
     uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
     cudaEvent_t ev[64] = {nullptr};
     // profiling (zs_ctx_profile)
@@ -153,6 +157,11 @@ struct zs_inflate_args {
     const uint8_t* d_dict;
     const uint64_t* d_dict_rng;
     int force_tps;        // tests: 1 = thread-per-stream kernel for any batch of >= 32 streams, -1 = never
+    // streaming shim (warp kernel only): decode raw blocks from this bit of each stream instead of
+    // from its start, and report where the last block that was begun starts: [2n] = (bit offset in the
+    // stream, bytes produced before it) -- the point a later call can resume from
+    const uint64_t* d_start_bit;
+    uint64_t* d_block_mark;
 };
 int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a);
 int zs_launch_inflate_verify(zs_ctx* ctx, uint32_t n, const uint32_t* d_adler, const uint32_t* d_crc,

@@ -334,8 +334,19 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
         unsigned tflags = 0;  // 1 zlib trailer, 2 gzip trailer
         uint32_t t_check = 0, t_isize = 0;
 
+        uint64_t mark_bit = 0, mark_out = 0;   // where the last block that was begun starts
+        if (a.d_start_bit) {
+            // continuation of a stream whose wrapper and earlier blocks a previous call consumed
+            const uint64_t sb = a.d_start_bit[sidx];
+            br.pos = in_start + (sb >> 3);
+            if (br.pos > br.end) br.pos = br.end;
+            if (sb & 7u) {
+                if (!br.need(8)) status = ZS_BUF_ERROR;
+                else br.drop((unsigned)(sb & 7u));
+            }
+        }
         // ---- wrapper header: HEAD..HCRC / DICTID of inflate() (inflate.ts:377-593) ----
-        if (a.wrap) {
+        if (a.wrap && !a.d_start_bit) {
             if (!br.need(16)) {
                 status = ZS_BUF_ERROR;
             } else {
@@ -404,6 +415,8 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
         // ---- blocks ----
         bool last = false;
         while (status == ZS_OK && !last) {
+            mark_bit = (br.pos - in_start) * 8 - br.bits;
+            mark_out = op;
             if (!br.need(3)) { status = ZS_BUF_ERROR; break; }
             last = br.take(1) != 0;
             unsigned type = br.take(2);
@@ -635,6 +648,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             a.d_trailer[2 * sidx] = t_check;
             a.d_trailer[2 * sidx + 1] = t_isize;
             a.d_flags[sidx] = (status == ZS_STREAM_END) ? tflags : 0u;
+            if (a.d_block_mark) { a.d_block_mark[2 * sidx] = mark_bit; a.d_block_mark[2 * sidx + 1] = mark_out; }
         }
         __syncwarp();
     }
@@ -673,7 +687,8 @@ int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a) {
     // thread per stream needs >= 32 k streams to fill the GPU (1024 warps); measured (tools/infmatrix.py):
     // 28-29 GB/s from 32768 streams up whatever the record size, 16-18 GB/s at 16384, where a warp per
     // stream gives 14 (4 KiB records) to 21 GB/s (64 KiB)
-    if (a.force_tps >= 0 && (a.n >= 32768 || (a.force_tps > 0 && a.n >= 32))) return zs_launch_inflate_tps(ctx, a);
+    if (!a.d_start_bit && !a.d_block_mark && a.force_tps >= 0 && (a.n >= 32768 || (a.force_tps > 0 && a.n >= 32)))
+        return zs_launch_inflate_tps(ctx, a);
     unsigned ctas = (a.n + kWarps - 1) / kWarps;
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;

@@ -12,9 +12,11 @@
 //    last 32 KiB of the previous part.  Every non-final part therefore ends with the reference's
 //    own Z_SYNC_FLUSH marker (empty stored block) and is byte aligned; the wrapper trailer of a
 //    multi-part stream is assembled from the per-part checksums with *_combine.
-//  * inflate: input is buffered and the stream is decoded from its start whenever enough new input
-//    has arrived (every call below 256 KiB or on a flush request, then whenever it has grown by half); bytes decoded so far are final and
-//    are handed out immediately, Z_STREAM_END gives back the unused input.
+//  * inflate: input is buffered and decoded incrementally at block granularity: every attempt reports
+//    where the last block it began starts; the blocks before that point are final (their input is
+//    dropped, their output joins the running checksum and the 64 KiB window) and the next attempt
+//    resumes there in raw mode.  Bytes decoded so far are handed out immediately, Z_STREAM_END gives
+//    back the unused input; the wrapper trailer of a stream decoded in several attempts is checked here.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -65,12 +67,25 @@ struct InflateState {
     uint32_t magic = 0x494e464c;  // 'INFL'
     zs_ctx* ctx = nullptr;
     int window_bits = 15;
-    std::vector<uint8_t> in;        // the whole stream so far
-    std::vector<uint8_t> out;       // decoded so far
-    std::vector<uint8_t> dict;
+    // Decoding is incremental at block granularity: every attempt reports where the last block it began
+    // starts; the blocks before that point are final, their input is dropped and the next attempt
+    // resumes there in raw mode with the last 64 KiB of output as its window.
+    std::vector<uint8_t> in;        // input not yet consumed: from the byte that holds the next block header on
+    std::vector<uint8_t> out;       // output of the latest attempt (from the resume point)
+    std::vector<uint8_t> ready;     // decoded, not yet delivered
+    std::vector<uint8_t> hist;      // window: the last <= 64 KiB of final output, or the preset dictionary
     std::vector<uint8_t> leftover;  // input after the end of the stream that could not be handed back
-    size_t delivered = 0, next_attempt = 0;
+    size_t ready_pos = 0;           // delivered part of `ready`
+    size_t out_pushed = 0;          // bytes of `out` already copied to `ready`
+    size_t next_attempt = 0;
     size_t out_cap_hint = 1 << 20;
+    bool body = false;              // the wrapper header is behind us: raw blocks from start_bit
+    uint64_t start_bit = 0;         // of the next block header inside `in`
+    int trailer = 0;                // 0 none (raw), 1 zlib (adler32), 2 gzip (crc32 + isize)
+    uint32_t run_check = 0;         // checksum of the final output so far (adler32 for zlib, crc32 otherwise)
+    uint64_t run_len = 0;           // its length
+    bool await_trailer = false;     // the last block is decoded, the trailer bytes are not all here yet
+    size_t trailer_pos = 0;         // where they start inside `in`
     bool done = false, failed = false, need_dict = false, have_dict = false;
     int fail_code = 0;
     const char* fail_msg = "";
@@ -442,9 +457,15 @@ int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint3
         uint32_t want = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
         if (id != want) return ZS_DATA_ERROR;
         st->need_dict = false;
+        // the 2-byte header and the DICTID are behind us: raw blocks from byte 6, adler32 trailer
+        st->body = true;
+        st->start_bit = 48;
+        st->trailer = 1;
+        st->run_check = 1u;
+        st->run_len = 0;
     }
     const uint32_t keep = dict_len < 65536 ? dict_len : 65536;
-    st->dict.assign(dict + (dict_len - keep), dict + dict_len);
+    st->hist.assign(dict + (dict_len - keep), dict + dict_len);
     st->have_dict = true;
     st->next_attempt = 0;
     return ZS_OK;
@@ -454,7 +475,7 @@ int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint3
 // kernel parses and checks the header on its own, inflate.ts:423-580).
 static void fill_gz_header(InflateState* st) {
     zs_gz_header* g = st->gzhead;
-    if (!g || g->done != 0) return;
+    if (!g || g->done != 0 || st->body) return;   // `in` starts at the stream start only until the first resume
     const std::vector<uint8_t>& b = st->in;
     if (b.size() < 2) return;
     if (!(b[0] == 0x1f && b[1] == 0x8b)) { g->done = -1; return; }   // a zlib stream (windowBits 32+), inflate.ts:404
@@ -494,64 +515,120 @@ static void fill_gz_header(InflateState* st) {
     g->done = 1;
 }
 
+// Everything of `out` below `upto` that has not been queued for delivery yet goes to `ready`.
+static void push_ready(InflateState* st, size_t upto) {
+    if (upto > st->out_pushed) {
+        st->ready.insert(st->ready.end(), st->out.begin() + st->out_pushed, st->out.begin() + upto);
+        st->out_pushed = upto;
+    }
+}
+
+// The blocks before (mark_bit, mark_out) are final: fold their output into the running checksum and
+// the window, drop their input, and make the mark the next resume point.
+static int advance_to_mark(InflateState* st, uint64_t mark_bit, uint64_t mark_out) {
+    if (mark_out) {
+        push_ready(st, (size_t)mark_out);
+        int rc = zs_checksum(st->ctx, st->trailer == 1 ? 0 : 1, st->out.data(), mark_out, st->run_check, &st->run_check);
+        if (rc != ZS_OK) return rc;
+        st->run_len += mark_out;
+        st->hist.insert(st->hist.end(), st->out.begin(), st->out.begin() + (size_t)mark_out);
+        if (st->hist.size() > 65536) st->hist.erase(st->hist.begin(), st->hist.end() - 65536);
+        st->out.erase(st->out.begin(), st->out.begin() + (size_t)mark_out);
+        st->out_pushed -= (size_t)mark_out;
+    }
+    const size_t bytes = (size_t)(mark_bit >> 3);
+    st->in.erase(st->in.begin(), st->in.begin() + bytes);
+    st->start_bit = mark_bit & 7u;
+    st->body = true;
+    return ZS_OK;
+}
+
+// The last block is decoded and `out` holds its output: check the trailer (CHECK / LENGTH,
+// inflate.ts:1006-1037) if its bytes are here.
+static int finish_stream(InflateState* st) {
+    const size_t T = st->trailer == 1 ? 4 : st->trailer == 2 ? 8 : 0;
+    if (st->in.size() < st->trailer_pos + T) { st->await_trailer = true; return ZS_OK; }
+    st->await_trailer = false;
+    uint32_t total = st->run_check;
+    int rc = zs_checksum(st->ctx, st->trailer == 1 ? 0 : 1, st->out.data(), st->out.size(), st->run_check, &total);
+    if (rc != ZS_OK) return rc;
+    const uint64_t total_len = st->run_len + st->out.size();
+    const uint8_t* t = st->in.data() + st->trailer_pos;
+    if (st->trailer == 1) {
+        const uint32_t want = (uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3];
+        if (want != total) { st->failed = true; st->fail_code = ZS_DATA_ERROR; st->fail_msg = "incorrect data check"; return ZS_OK; }
+    } else if (st->trailer == 2) {
+        const uint32_t want = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+        const uint32_t isize = (uint32_t)t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+        if (want != total) { st->failed = true; st->fail_code = ZS_DATA_ERROR; st->fail_msg = "incorrect data check"; return ZS_OK; }
+        if (isize != (uint32_t)total_len) { st->failed = true; st->fail_code = ZS_DATA_ERROR; st->fail_msg = "incorrect length check"; return ZS_OK; }
+    }
+    st->check = total;
+    st->done = true;
+    const size_t used = st->trailer_pos + T;
+    if (st->in.size() > used) st->leftover.assign(st->in.begin() + used, st->in.end());
+    st->in.clear();
+    return ZS_OK;
+}
+
 static int inflate_attempt(zs_stream* strm, InflateState* st) {
     zs_ctx* ctx = st->ctx;
-    // a zlib stream with a preset dictionary: the 2-byte header and the DICTID are host framing, the
-    // body is decoded as a raw stream with the dictionary and the adler32 trailer is checked here
-    const bool zdict = st->have_dict && st->window_bits > 0;
-    const uint8_t* src = st->in.data();
-    size_t src_len = st->in.size();
-    int wb = st->window_bits;
-    if (zdict) {
-        if (src_len < 6) return ZS_OK;
-        src += 6;
-        src_len -= 6;
-        wb = -15;
-    }
+    if (st->await_trailer) return finish_stream(st);
+    const int raw_wb = st->window_bits == -16 ? -16 : -15;
     for (;;) {
-        const uint64_t in_off[2] = {0, src_len}, out_off[2] = {0, st->out_cap_hint};
+        const uint64_t in_off[2] = {0, st->in.size()}, out_off[2] = {0, st->out_cap_hint};
+        // `out` is rebuilt by every attempt; what was queued from it stays in `ready`
         st->out.resize(st->out_cap_hint);
-        uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->dict.size()};
+        uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->hist.size()};
         uint32_t check = 0;
         int32_t status = 0, detail = 0;
-        int rc = zs_inflate_batch(ctx, src, in_off, 1, wb, st->out.data(), out_off, &out_len, &in_used, &check, &status,
-                                  st->dict.empty() ? nullptr : st->dict.data(), st->dict.empty() ? nullptr : rng,
-                                  st->dict.size());
+        ctx->inflate_resume = true;
+        ctx->inflate_start_bit = st->body ? st->start_bit : ~0ull;
+        int rc = zs_inflate_batch(ctx, st->in.data(), in_off, 1, st->body ? raw_wb : st->window_bits, st->out.data(), out_off,
+                                  &out_len, &in_used, &check, &status, st->hist.empty() ? nullptr : st->hist.data(),
+                                  st->hist.empty() ? nullptr : rng, st->hist.size());
+        ctx->inflate_resume = false;
         if (rc != ZS_OK) { strm->msg = zs_last_error(ctx); return rc; }
         if (status == ZS_BUF_ERROR && out_len == st->out_cap_hint) {  // output full: grow and decode again
             st->out_cap_hint *= 4;
             continue;
         }
+        const uint64_t mark_bit = ctx->inflate_mark[0], mark_out = ctx->inflate_mark[1];
         st->out.resize(out_len);
-        st->check = check;
         if (status == ZS_STREAM_END) {
-            if (zdict) {
-                // adler32 trailer of the wrapped stream follows the raw body
-                if (src_len - in_used < 4) { st->out.resize(out_len); return ZS_OK; }  // trailer not here yet
-                const uint8_t* t = src + in_used;
-                uint32_t want = (uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3];
-                uint32_t got = 1;
-                rc = zs_checksum(ctx, 0, st->out.data(), out_len, 1u, &got);
-                if (rc != ZS_OK) return rc;
-                st->check = got;
-                if (got != want) { st->failed = true; st->fail_code = ZS_DATA_ERROR; st->fail_msg = "incorrect data check"; return ZS_OK; }
-                in_used += 4 + 6;
+            if (!st->body) {
+                // the whole stream in one attempt: wrapper and trailer were checked on the device
+                push_ready(st, out_len);
+                st->check = check;
+                st->done = true;
+                if (st->in.size() > (size_t)in_used) st->leftover.assign(st->in.begin() + (size_t)in_used, st->in.end());
+                st->in.clear();
+                return ZS_OK;
             }
-            st->done = true;
-            // unused input goes back to the caller (or is kept for the next member)
-            const size_t extra = st->in.size() - (size_t)in_used;
-            if (extra) {
-                st->leftover.assign(st->in.end() - extra, st->in.end());
-                st->in.resize((size_t)in_used);
-            }
-        } else if (status == ZS_NEED_DICT) {
-            st->need_dict = true;
-        } else if (status == ZS_DATA_ERROR) {
+            push_ready(st, out_len);
+            st->trailer_pos = (size_t)in_used;
+            return finish_stream(st);
+        }
+        if (status == ZS_NEED_DICT) { st->need_dict = true; return ZS_OK; }
+        if (status == ZS_DATA_ERROR) {
             zs_inflate_last_details(ctx, &detail, 1);
+            push_ready(st, out_len);   // what was decoded before the error is delivered first, like the reference
             st->failed = true;
             st->fail_code = ZS_DATA_ERROR;
             st->fail_msg = zs_inflate_message(detail);
+            return ZS_OK;
         }
+        // the input ran dry (Z_BUF_ERROR / Z_OK): everything decoded so far is final output
+        push_ready(st, out_len);
+        if (!st->body) {
+            // mark_bit > 0 means the wrapper header is complete and the block loop was entered
+            if (mark_bit == 0 && st->window_bits > 0) return ZS_OK;
+            const bool gz = st->window_bits > 15 && st->in.size() >= 2 && st->in[0] == 0x1f && st->in[1] == 0x8b;
+            st->trailer = st->window_bits < 0 ? 0 : gz ? 2 : 1;
+            st->run_check = st->trailer == 1 ? 1u : 0u;
+            st->run_len = 0;
+        }
+        if (mark_bit > st->start_bit || !st->body) return advance_to_mark(st, mark_bit, mark_out);
         return ZS_OK;
     }
 }
@@ -575,8 +652,9 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         }
         if (st->need_dict) return ZS_NEED_DICT;
         fill_gz_header(st);
-        // every call while the stream is short, then whenever it has grown by half (the decode restarts from
-        // the beginning, so this keeps the total work linear); any flush request decodes now
+        // `in` holds only what follows the last resume point, so an attempt costs the current block plus
+        // the new input: every call while that is short, then whenever it has grown by half (a single
+        // huge block is decoded from its start each time); any flush request decodes now
         const bool due = flush != ZS_NO_FLUSH || st->in.size() >= st->next_attempt;
         if (due && !st->in.empty()) {
             int rc = inflate_attempt(strm, st);
@@ -597,16 +675,18 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         }
     }
     // deliver what has been decoded
-    if (st->delivered < st->out.size()) {
-        size_t c = st->out.size() - st->delivered;
+    if (st->ready_pos < st->ready.size()) {
+        size_t c = st->ready.size() - st->ready_pos;
         if (c > strm->avail_out) c = (size_t)strm->avail_out;
-        memcpy(strm->next_out, st->out.data() + st->delivered, c);
+        memcpy(strm->next_out, st->ready.data() + st->ready_pos, c);
         strm->next_out += c;
         strm->avail_out -= c;
         strm->total_out += c;
-        st->delivered += c;
+        st->ready_pos += c;
+        if (st->ready_pos == st->ready.size()) { st->ready.clear(); st->ready_pos = 0; }
+        else if (st->ready_pos > (8u << 20)) { st->ready.erase(st->ready.begin(), st->ready.begin() + st->ready_pos); st->ready_pos = 0; }
     }
-    const bool all_out = st->delivered >= st->out.size();
+    const bool all_out = st->ready_pos >= st->ready.size();
     if (st->failed && all_out) {
         strm->msg = st->fail_msg;
         return st->fail_code;
@@ -637,9 +717,16 @@ int zs_stream_inflate_reset(zs_stream* strm) {
     if (!st) return ZS_STREAM_ERROR;
     st->in.clear();
     st->out.clear();
-    st->dict.clear();
-    st->delivered = 0;
+    st->ready.clear();
+    st->hist.clear();
+    st->ready_pos = st->out_pushed = 0;
     st->next_attempt = 0;
+    st->body = st->await_trailer = false;
+    st->start_bit = 0;
+    st->trailer = 0;
+    st->run_check = 0;
+    st->run_len = 0;
+    st->trailer_pos = 0;
     st->done = st->failed = st->need_dict = st->have_dict = false;
     st->gzhead = nullptr;   // inflateResetKeep drops the header request
     strm->total_in = strm->total_out = 0;
