@@ -143,6 +143,45 @@ def test_many_tiny_ragged_chunks(gpu_ctx, oracle, level, prime):
         assert ret == oracle.Z_STREAM_END and out == data[lo:hi]
 
 
+def _kinds(n):
+    rng = np.random.default_rng(5)
+    pool = rng.integers(0, 256, (64, 3), dtype=np.uint8)
+    sr = rng.integers(0, 256, n, dtype=np.uint8)
+    for i in range(0, n - 9, 9):
+        sr[i:i + 3] = pool[rng.integers(0, 64)]
+    rows = b"".join(b'{"id":%d,"name":"user%d","score":%d,"tags":["a","b%d"]},' % (i, i * 7 % 1000, i * 13 % 97, i % 5) for i in range(n // 50))
+    return {
+        "text": make_text(n, 1), "mixed": make_mixed(n, 2),
+        "dna": bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), n)),        # 4-letter alphabet: very long hash chains
+        "short_repeats": sr.tobytes(),                                          # 3-byte matches only
+        "counters": np.arange(n // 4, dtype=np.uint32).tobytes(),               # 3 of every 4 bytes repeat
+        "floats": np.cumsum(rng.normal(0, 1, n // 8)).astype(np.float64).tobytes(),
+        "json": rows[:n],
+    }
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 9])
+def test_size_across_data_kinds(gpu_ctx, level):
+    """Size against C zlib at the same level and with the same block plan (one stream, a block boundary
+    after every 64 KiB chunk) on data the bench corpora do not cover.  Gate 3 %.  Known deviation: the
+    engine inserts every position into the hash chains, the reference's deflate_fast (levels 1-3) skips the
+    positions inside matches longer than max_insert (deflate.ts:1310-1322); on JSON-like rows that costs
+    4.5 % at level 1 and 3.1 % at level 2 (and gains 4.4 % at level 3) -- the same numbers C zlib itself
+    produces when it is made to insert every position."""
+    B = pkg("batch")
+    n = 1 << 20
+    for name, data in _kinds(n).items():
+        r = B.deflate_batch(data, 65536, level, 1, B.MODE_STITCHED)
+        assert zlib.decompress(r.data) == data
+        co = zlib.compressobj(level)
+        ref = 0
+        for i in range(0, len(data), 65536):
+            ref += len(co.compress(data[i:i + 65536])) + len(co.flush(zlib.Z_BLOCK))
+        ref += len(co.flush())
+        tol = 1.055 if (name == "json" and level <= 2) else RATIO_TOL
+        assert len(r.data) <= ref * tol + 64, (name, level, len(r.data), ref, len(r.data) / ref)
+
+
 @pytest.mark.parametrize("level", [1, 5, 9])
 def test_stitched_ragged_chunks_and_determinism(gpu_ctx, oracle, level):
     """One stream stitched from thousands of ragged chunks (with and without sync markers), twice: the

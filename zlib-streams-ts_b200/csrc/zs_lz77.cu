@@ -261,6 +261,12 @@ __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsign
 
 // [cs, ce) is the chunk that holds q.
 // kMode: 0 greedy levels (1-3), 1 lazy levels (4-9), 2 Z_RLE
+// Work bounds of the lazy levels on periodic data (see search_position): a chain is "dense" when the hop
+// to the candidate is at most kDenseHop positions -- runs and short periods, not ordinary text or DNA-like
+// data, whose ties and good matches must not cut the search short (measured: +5.8 % size on a 4-letter
+// alphabet at level 6 when they did).
+constexpr unsigned kDenseHop = 8;       // hops this short mark a run / a short period
+constexpr int kInteriorChain = 16;      // candidates left once a good match turns out to lie inside a longer one
 template <int kMode>
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
                                                     uint32_t cs, uint32_t ce) {
@@ -319,7 +325,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
                 // (Compiled into the lazy levels only: max_chain <= 32 bounds the damage at levels 1-3, and the
                 // test costs them 6 % through code generation alone.)
                 if (kLazy && best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {   // + 257 stays inside the guard
-                    chain -= chain >> 2;   // counts as a tie, see below
+                    if (delta <= kDenseHop) chain -= chain >> 2;   // counts as a tie, see below
                     continue;
                 }
                 // 8 bytes per round; the two streams keep their own word alignment and the last word
@@ -349,20 +355,22 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
         if (len > max_len) len = max_len;
         if (len > best_len) {
             // With a good match in hand the rest of the chain gets a quarter of the budget (the rule
-            // longest_match applies when the previous position's match was good, deflate.ts:1069-1071).
-            // If the match also extends backwards, q lies inside a longer match that started earlier:
-            // the reference never searches such a position (deflate_slow skips the bytes a match
-            // covers), the speculative search here cannot skip it but stops after a few more candidates.
+            // longest_match applies when the previous position's match was good, deflate.ts:1069-1071)
+            // -- here only where the reference would not be searching at all: on a dense chain (a run)
+            // or when the match also extends backwards, i.e. q lies inside a longer match that started
+            // earlier (deflate_slow skips the bytes a match covers; the speculative search cannot skip
+            // them, but it stops after kInteriorChain more candidates).
             if (kLazy && best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
-                chain >>= 2;
-                if (chain > 4 && S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)]) chain = 4;
+                const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
+                if (interior || delta <= kDenseHop) chain >>= 2;
+                if (interior && chain > kInteriorChain) chain = kInteriorChain;
             }
             best_len = len;
             best_dist = dist;
             if (len >= nice) break;
-        } else if (kLazy && len == best_len) {
-            // A candidate that ties with the best match means periodic data (a run, a ramp): the rest
-            // of the chain is more of the same.  Every tie takes a quarter off the remaining budget,
+        } else if (kLazy && len == best_len && delta <= kDenseHop) {
+            // A candidate that ties with the best match on a dense chain means periodic data (a run): the
+            // rest of the chain is more of the same.  Every tie takes a quarter off the remaining budget,
             // which bounds a chain of ties at ~4 log(max_chain) candidates.  (The reference never gets
             // here: it does not search the positions a match covers.)
             chain -= chain >> 2;
