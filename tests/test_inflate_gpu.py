@@ -231,3 +231,49 @@ def test_generated_deflate64_streams(gpu_ctx, oracle, monkeypatch, kernel):
     for j in range(8):
         ret, _, _, _ = oracle.inflate(streams[j], -15, caps[j])
         assert bad.status[j] == ret, (j, bad.status[j], ret)
+
+
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_fuzzed_streams_same_verdict_and_message(gpu_ctx, oracle, monkeypatch, kernel):
+    """The reference's fuzz strategy (test/inflate/test-fuzz.ts) against the restated reference: bit flips,
+    byte stomps and truncations of zlib / gzip / raw / deflate64 streams (stored, fixed and dynamic
+    blocks).  Status, strm.msg and the bytes produced before the error must all be the reference's."""
+    monkeypatch.setenv("ZS_INFLATE_TPS" if kernel == "thread" else "ZS_INFLATE_WARP", "1")
+    rnd = random.Random(1234)
+    text = make_text(6000, 81)
+    bases = []
+    for wb, zwb in ((15, 15), (31, 31), (-15, -15)):
+        for level, strategy in ((0, 0), (1, 0), (6, 0), (6, zlib.Z_FIXED), (9, zlib.Z_HUFFMAN_ONLY)):
+            co = zlib.compressobj(level, zlib.DEFLATED, zwb, 8, strategy)
+            bases.append((wb, co.compress(text) + co.flush()))
+    bases.append((-16, oracle.deflate64_encode(text + bytes(70000) + text, 65538)))
+    per_wb = {}
+    for wb, z in bases:
+        lst = per_wb.setdefault(wb, [])
+        for _ in range(60):
+            s = bytearray(z)
+            kind = rnd.randrange(4)
+            if kind == 0:
+                s[rnd.randrange(len(s))] ^= 1 << rnd.randrange(8)
+            elif kind == 1:
+                s[rnd.randrange(len(s))] = rnd.randrange(256)
+            elif kind == 2:
+                s = s[: rnd.randrange(1, len(s))]
+            else:
+                p = rnd.randrange(len(s))
+                s[p: p + 3] = bytes(rnd.randrange(256) for _ in range(3))
+            lst.append(bytes(s))
+    n_err = 0
+    for wb, streams in per_wb.items():
+        cap = 100000 if wb == -16 else 8000
+        r = _run(streams, wb, [cap] * len(streams))
+        for i, s in enumerate(streams):
+            st = oracle.InflateStream(wb)
+            ret, out, used = st.step(s, cap, oracle.Z_FINISH)
+            assert int(r.status[i]) == ret, (kernel, wb, i, int(r.status[i]), ret, r.message(i), st.msg)
+            assert r.output(i) == out, (kernel, wb, i, len(r.output(i)), len(out))
+            if ret == oracle.Z_DATA_ERROR:
+                assert r.message(i) == st.msg, (kernel, wb, i, r.message(i), st.msg)
+                n_err += 1
+            st.close()
+    assert n_err > 100
