@@ -495,6 +495,11 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
         br.bits += 32; woff += 4; in_rem -= 4;                                                             \
     } while (0)
                     ZS_LOAD_WINDOW();
+                    // A match of <= 32 bytes is one load and one store per lane; the store is deferred to the next
+                    // match (or the end of the fast path), so the load's latency overlaps the symbols in between.
+                    unsigned pend_n = 0;
+                    uint8_t pend_v = 0;
+                    uint8_t* pend_dp = nullptr;
                     // a symbol pulls at most 8 bytes: two refills of 32 bits
                     while (in_rem >= 8u && out_rem >= 258u) {
                         if (br.bits <= 32) ZS_FAST_REFILL();
@@ -539,6 +544,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         }
                         br.drop(used + xb);
                         // copy: the source is periodic with period dist, so every byte comes from before wp + made
+                        if (pend_n) { if (lane < pend_n) pend_dp[lane] = pend_v; pend_n = 0; }
                         __syncwarp();
                         const uint8_t* sp = wp + made - dist;
                         uint8_t* dp = wp + made;
@@ -549,14 +555,22 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                                 const int64_t si = s0 + (int64_t)(dist >= len ? j : j % dist);
                                 dp[j] = si >= 0 ? out[si] : __ldg(dict + dict_len + si);
                             }
+                            __syncwarp();
+                        } else if (len <= 32u) {
+                            if (lane < len) pend_v = sp[dist >= len ? lane : lane % dist];
+                            pend_dp = dp;
+                            pend_n = len;
                         } else if (dist >= len) {
                             for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j];
+                            __syncwarp();
                         } else {
                             for (unsigned j = lane; j < len; j += 32) dp[j] = sp[j % dist];
+                            __syncwarp();
                         }
-                        __syncwarp();
                         made += len; out_rem -= len;
                     }
+                    if (pend_n) { if (lane < pend_n) pend_dp[lane] = pend_v; }
+                    __syncwarp();
 #undef ZS_FAST_REFILL
 #undef ZS_LOAD_WINDOW
                     br.pos = win_base + woff;
