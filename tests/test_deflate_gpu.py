@@ -271,3 +271,13 @@ def test_bit_concat(gpu_ctx, oracle):
     torch.cuda.synchronize()
     stream = dst[: (total_bits + 7) // 8].cpu().numpy().tobytes()
     assert _decode_both(oracle, stream, 0, len(data)) == data
+
+
+def test_randomised_soak(gpu_ctx):
+    """tools/soak.py for a few seconds: random data kind / size / chunking (down to 1-byte chunks) / level /
+    strategy / wrapper / mode; every result decoded by C zlib, every call run twice (determinism).  This is
+    the test that found the stale reads at the end of a range when segments are a few bytes long."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "12", "7"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "soak ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

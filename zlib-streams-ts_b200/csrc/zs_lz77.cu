@@ -580,8 +580,12 @@ __device__ __forceinline__ void emit_batch(const Smem& S, const LzArgs& a, uint6
         entry = xa;
         first += mj_count(ya);
     }
+    // The chain may have reached the end of the range inside this pair: the mj[] slots from position n on
+    // are stale (resolve never writes them), and symbols written from them would land in the slots of
+    // the segments that follow.
+    if (q0 + entry >= n) return;
     const unsigned visited = S.mj[mj_slot(q0 + entry)].x;  // same address in all lanes: a broadcast
-    if ((visited >> lane) & 1u) {
+    if (((visited >> lane) & 1u) && q0 + lane < n) {
         const uint32_t q = q0 + lane;
         const uint32_t r = S.res[res_slot(q)];
         const bool is_match = (S.mj[mj_slot(q)].y & MJ_MATCH) != 0;
