@@ -277,3 +277,13 @@ def test_fuzzed_streams_same_verdict_and_message(gpu_ctx, oracle, monkeypatch, k
                 n_err += 1
             st.close()
     assert n_err > 100
+
+
+def test_randomised_soak_inflate_and_api(gpu_ctx):
+    """tools/soak_inflate.py for a few seconds: random batches (valid, truncated, corrupted, too-small
+    outputs; zlib / gzip / raw / auto / deflate64) on both kernels against the oracle, and random piece /
+    flush patterns through the z_stream API against C zlib."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "soak_inflate.py"), "24", "3"], capture_output=True, text=True, timeout=400)
+    assert p.returncode == 0 and p.stdout.count("soak ok") == 3, p.stdout[-2000:] + p.stderr[-2000:]
