@@ -57,3 +57,32 @@ def test_segments_ragged(gpu_ctx, oracle):
         acc_a = B.adler32_combine(acc_a, int(adl[i]), int(lens[i]))
     assert acc_c == zlib.crc32(data.tobytes()) and acc_a == zlib.adler32(data.tobytes())
     assert B.checksum_dev(t, 1) == acc_c and B.checksum_dev(t, 0) == acc_a
+
+
+def test_long_segments_and_row_boundaries(gpu_ctx):
+    """One warp per segment reads rows of 512 bytes: lengths around multiples of 16 and 512 at every start
+    alignment, and single segments of tens of MiB (worst-case bytes for the adler32 accumulators)."""
+    import torch
+    B = pkg("batch")
+    rng = np.random.default_rng(6)
+    lens = []
+    for base in (0, 16, 496, 512, 528, 1024, 5 * 512, 65536):
+        for d in (-17, -16, -15, -1, 0, 1, 15, 16, 17):
+            if base + d >= 0:
+                lens.append(base + d)
+    lens += [int(x) for x in rng.integers(0, 40, 40)]        # shifts the alignment of what follows
+    lens += [20 << 20, (24 << 20) + 13]
+    lens = np.array(lens, dtype=np.int64)
+    rng.shuffle(lens[:-2])
+    off = np.zeros(lens.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    data = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    data[off[-3]: off[-2]] = 0xff                               # the 20 MiB segment: all 0xff
+    t = torch.from_numpy(data).cuda()
+    o = torch.from_numpy(off).cuda()
+    crc = B.checksum_batch_dev(t, o, 1).cpu().numpy().view(np.uint32)
+    adl = B.checksum_batch_dev(t, o, 0).cpu().numpy().view(np.uint32)
+    for i in range(lens.size):
+        seg = data[off[i]: off[i + 1]].tobytes()
+        assert crc[i] == zlib.crc32(seg), (i, lens[i], off[i] % 16)
+        assert adl[i] == zlib.adler32(seg), (i, lens[i], off[i] % 16)
