@@ -26,6 +26,33 @@ for wrap, level, chunk, n in ((1, 6, 262144, 24 << 20), (2, 1, 65536, 10 << 20),
         print(f"wrap {wrap} level {level} world {world}: ok={good} size {len(stream)} vs zlib {ref} ({len(stream)/ref:.4f}) bit offsets {plan.bit_offset}")
         ok &= good
     dist.barrier()
+# randomised part (argument: seconds): sizes down to fewer chunks than ranks, every level, both chunk sizes
+import numpy as np, time
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
+rng = np.random.default_rng(11)     # same sequence on every rank
+t0 = time.time(); it = 0
+while True:
+    go = torch.tensor([1 if time.time() - t0 < budget else 0], device="cuda")
+    dist.broadcast(go, 0)
+    if not int(go.item()):
+        break
+    it += 1
+    n = int(rng.choice([1, 100, 70000, 300000, 2 << 20, (9 << 20) + 77]))
+    wrap, level = int(rng.integers(0, 3)), int(rng.integers(0, 10))
+    chunk = int(rng.choice([4096, 65536, 262144]))
+    seed = int(rng.integers(1 << 30))
+    data = torch.from_numpy(corpus.mixed_numpy(n, seed)).cuda()
+    res, rr, plan = S.deflate_sharded(data, chunk, level, wrap)
+    stream = S.gather_stream(res, rr, plan, wrap, dst=0)
+    if rank == 0:
+        host = data.cpu().numpy().tobytes()
+        d = zlib.decompressobj({0: -15, 1: 15, 2: 31}[wrap])
+        good = d.decompress(stream) + d.flush() == host and d.eof
+        if not good:
+            print("random case FAILED", it, n, wrap, level, chunk, seed)
+        ok &= good
+    dist.barrier()
 if rank == 0:
+    print("random cases:", it)
     print("SHARDED_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
