@@ -465,11 +465,12 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             const unsigned lmask = (1u << lenbits) - 1u, dmask = (1u << distbits) - 1u;
             for (;;) {
                 // ---- fast path: the role of inflate_fast (inffast.ts:5-228).  While at least 8 input bytes and
-                // room for the longest match remain, symbols are decoded without the per-symbol end-of-buffer
-                // tests; anything unusual -- end of block, an invalid code, a distance beyond the dictionary --
+                // some output room remain, symbols are decoded without the per-symbol end-of-buffer tests;
+                // anything unusual -- end of block, an invalid code, a distance beyond the dictionary, a match
+                // longer than the room left --
                 // is left, unconsumed, to the careful loop below, which reproduces the
-                // reference's verdicts.  (deflate64 keeps to the careful loop: its matches can be 64 KiB long.)
-                if (!d64) {
+                // reference's verdicts.  (deflate64: matches of up to 65538 bytes, 16 length extra bits.)
+                {
                     uint64_t in_left = br.end - br.pos, out_left = cap - op;
                     uint32_t in_rem = in_left > 0xffffffffull ? 0xffffffffu : (uint32_t)in_left;
                     uint32_t out_rem = out_left > 0xffffffffull ? 0xffffffffu : (uint32_t)out_left;
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                     // register shuffle.  woff = offset of the next unread byte inside the window, a multiple of 4.
                     uint64_t win_base = br.pos;
                     uint32_t woff = 0;
-                    uint32_t inw;
+                    uint32_t inw = 0;
 #define ZS_LOAD_WINDOW()                                                                                   \
     do {                                                                                                   \
         const uint64_t wa_ = (win_base & ~3ull) + 4ull * lane;                                             \
@@ -494,14 +495,14 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
         br.hold |= (uint64_t)__shfl_sync(ZS_FULL_MASK, inw, woff >> 2) << br.bits;                         \
         br.bits += 32; woff += 4; in_rem -= 4;                                                             \
     } while (0)
-                    ZS_LOAD_WINDOW();
+                    if (in_rem >= 8u && out_rem) ZS_LOAD_WINDOW();
                     // A match of <= 32 bytes is one load and one store per lane; the store is deferred to the next
                     // match (or the end of the fast path), so the load's latency overlaps the symbols in between.
                     unsigned pend_n = 0;
                     uint8_t pend_v = 0;
                     uint8_t* pend_dp = nullptr;
                     // a symbol pulls at most 8 bytes: two refills of 32 bits
-                    while (in_rem >= 8u && out_rem >= 258u) {
+                    while (in_rem >= 8u && out_rem) {
                         if (br.bits <= 32) ZS_FAST_REFILL();
                         uint32_t here = lcode[(unsigned)br.hold & lmask];
                         unsigned used = E_BITS(here);
@@ -518,12 +519,12 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                             continue;
                         }
                         if (lop & 0x60u) break;   // end of block / invalid code
-                        // length + distance: <= 15 + 5 + 15 + 13 bits; the state is restored if the pair is unusual
+                        // length + distance: <= 15 + 16 + 15 + 14 bits; the state is restored if the pair is unusual
                         const uint64_t hold0 = br.hold;
                         const unsigned bits0 = br.bits;
                         const uint64_t wb0 = win_base;
                         const uint32_t woff0 = woff;
-                        unsigned xb = lop & 15u;
+                        unsigned xb = lop & (d64 ? 31u : 15u);
                         const unsigned len = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
                         br.drop(used + xb);
                         if (br.bits <= 32) ZS_FAST_REFILL();
@@ -536,8 +537,8 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         }
                         xb = E_OP(here) & 15u;
                         const unsigned dist = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
-                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made + dict_len) {
-                            // invalid distance code or a distance too far back: undo the pair
+                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made + dict_len || len > out_rem) {
+                            // invalid distance code, a distance too far back, or a match that does not fit: undo the pair
                             br.hold = hold0; br.bits = bits0;
                             win_base = wb0; woff = woff0;
                             break;
