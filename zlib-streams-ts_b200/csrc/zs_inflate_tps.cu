@@ -11,11 +11,11 @@
 // streams (minus divergence), which is what a batch of 1 M x 4 KiB gzip records wants
 // (BASELINE.json configs[3]).  The price is table memory: 32 streams per warp cannot each hold the
 // reference's 852+594-entry lookup tables, so the tables here are canonical-code tables
-// (per code length: left-justified limit and symbol base; symbols sorted by code) -- 930 bytes per
+// (per code length: left-justified limit and symbol base; symbols sorted by code) -- 640 bytes per
 // stream, interleaved by lane in shared memory so that equal indices of different lanes never
 // conflict.  The verdicts of inflate_table (over-subscribed / incomplete sets) are reproduced from
 // the same length counts; decode results are identical because both describe the same canonical
-// code.  The dispatcher (zs_launch_inflate) picks this kernel for >= 1024 streams.
+// code.  The dispatcher (zs_launch_inflate) picks this kernel for >= 32768 streams.
 #include <cstdio>
 
 #include "zs_common.cuh"
@@ -28,20 +28,30 @@ enum {
     D_DIST_CODE, D_TOO_FAR, D_DATA_CHECK, D_LENGTH_CHECK
 };
 
-// per-thread table layout, in 16-bit units (index i of lane l lives at [i * 32 + l])
-constexpr int T_LSYM = 0;        // 288 literal/length symbols sorted by code
+// Per-thread table layout.  Shared memory per stream decides how many warps an SM holds (the kernel is
+// latency-bound: 7 warps per SM with 928 bytes per stream, 11 with 640), so the sorted symbols are
+// bytes: a literal/length symbol is its low byte plus "index >= thr[length]" as bit 8 -- inside one code
+// length the symbols are sorted, so those >= 256 sit at the end of the group.
+// 16-bit units (index i of lane l lives at w[i * 32 + l]):
+constexpr int T_LLIM = 0;        // [16] left-justified exclusive code limit per length (literal/length)
+constexpr int T_LBASE = 16;      // [16] symbol index base per length
+constexpr int T_DLIM = 32;
+constexpr int T_DBASE = 48;
+constexpr int T_LTHR = 64;       // [16] first index of each length group whose symbol is >= 256
+constexpr int T_LENS = 80;       // 320 code lengths, 4 bits each -> 80 units
+constexpr int T_UNITS = 160;
+// bytes (index i of lane l lives at b[i * 32 + l]):
+constexpr int T_LSYM = 0;        // 288 literal/length symbols sorted by code (low byte)
 constexpr int T_DSYM = 288;      // 32 distance symbols sorted by code
-constexpr int T_LLIM = 320;      // [16] left-justified exclusive code limit per length (literal/length)
-constexpr int T_LBASE = 336;     // [16] symbol index base per length
-constexpr int T_DLIM = 352;
-constexpr int T_DBASE = 368;
-constexpr int T_LENS = 384;      // 320 code lengths, 4 bits each -> 80 units
-constexpr int T_UNITS = 464;
+constexpr int T_BYTES = 320;
+constexpr int kArenaBytes = T_UNITS * 64 + T_BYTES * 32;   // per warp
 constexpr int kWarpsPerCta = 1;
 
 struct Tab {
     uint16_t* w;  // warp arena + lane
+    uint8_t* b;   // byte region of the warp arena + lane
     __device__ __forceinline__ uint16_t& at(int i) const { return w[i * 32]; }
+    __device__ __forceinline__ uint8_t& sym(int i) const { return b[i * 32]; }
     __device__ __forceinline__ unsigned len_get(unsigned i) const { return (w[(T_LENS + (i >> 2)) * 32] >> ((i & 3u) * 4u)) & 15u; }
     __device__ __forceinline__ void len_set(unsigned i, unsigned v) const {
         uint16_t& x = w[(T_LENS + (i >> 2)) * 32];
@@ -104,10 +114,13 @@ __device__ int build_canon(const Tab& T, unsigned first, unsigned n, int type, b
     }
     if (left > 0 && (type == 0 || mx != 1)) return -1;   // incomplete set
     unsigned off = 0;
-    for (int l = 1; l <= 15; l++) { T.at(t_base + l) = (uint16_t)off; off += T.at(t_lim + l); }
+    for (int l = 1; l <= 15; l++) { T.at(t_base + l) = (uint16_t)off; off += T.at(t_lim + l); if (type == 1) T.at(T_LTHR + l) = 0; }
     for (unsigned i = 0; i < n; i++) {
         const unsigned l = T.len_get(first + i);
-        if (l) T.at(t_sym + T.at(t_base + l)++) = (uint16_t)i;
+        if (l) {
+            T.sym(t_sym + T.at(t_base + l)++) = (uint8_t)i;
+            if (type == 1 && i < 256) T.at(T_LTHR + l)++;   // literals of this length, for now
+        }
     }
     unsigned code = 0;
     off = 0;
@@ -117,6 +130,7 @@ __device__ int build_canon(const Tab& T, unsigned first, unsigned n, int type, b
         if (cnt && !mn) mn = (unsigned)l;
         T.at(t_lim + l) = (uint16_t)((code + cnt) << (15 - l));   // 0x8000 at most
         T.at(t_base + l) = (uint16_t)(off - code);                 // modulo 2^16, used modulo 2^16
+        if (type == 1) T.at(T_LTHR + l) = (uint16_t)(off + T.at(T_LTHR + l));
         off += cnt;
         code = (code + cnt) << 1;
     }
@@ -155,9 +169,10 @@ __device__ __forceinline__ int decode_sym(const Tab& T, uint64_t hold, int t_sym
     *nbits = l;
     if (l > 15) return -1;
     const unsigned idx = (unsigned)(uint16_t)(T.at(t_base + (int)l) + (v >> (15 - l)));
-    return (int)T.at(t_sym + (int)idx);
+    return (int)T.sym(t_sym + (int)idx);   // code-length code: symbols 0..18
 }
-// the same with the limits held in registers
+// the same with the limits held in registers; kLitLen adds bit 8 of a literal/length symbol
+template <bool kLitLen>
 __device__ __forceinline__ int decode_sym_fast(const Tab& T, const LimSet& L, uint64_t hold, int t_sym, int t_base,
                                                unsigned* nbits) {
     const unsigned v = __brev((unsigned)hold) >> 17;
@@ -165,7 +180,9 @@ __device__ __forceinline__ int decode_sym_fast(const Tab& T, const LimSet& L, ui
     *nbits = l;
     if (l > 15) return -1;
     const unsigned idx = (unsigned)(uint16_t)(T.at(t_base + (int)l) + (v >> (15 - l)));
-    return (int)T.at(t_sym + (int)idx);
+    unsigned sym = T.sym(t_sym + (int)idx);
+    if (kLitLen && idx >= T.at(T_LTHR + (int)l)) sym |= 256u;
+    return (int)sym;
 }
 
 __device__ __forceinline__ void len_base(unsigned idx, bool d64, unsigned& base, unsigned& xb, bool& invalid) {
@@ -200,10 +217,11 @@ __device__ __forceinline__ uint32_t crc_bitwise(uint32_t crc, unsigned byte) {
 }
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta) inflate_tps_kernel(zs_inflate_args a) {
-    __shared__ uint16_t s_tab[kWarpsPerCta][T_UNITS * 32];
+    __shared__ __align__(16) uint8_t s_tab[kWarpsPerCta][kArenaBytes];
     const unsigned lane = zs_lane();
     Tab T;
-    T.w = s_tab[threadIdx.x >> 5] + lane;
+    T.w = reinterpret_cast<uint16_t*>(s_tab[threadIdx.x >> 5]) + lane;
+    T.b = s_tab[threadIdx.x >> 5] + T_UNITS * 64 + lane;
     const bool d64 = a.deflate64 != 0;
     const uint64_t in_total = a.d_in_off[a.n];
     const uint64_t safe_end = (in_total + 7) & ~7ull;
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) inflate_tps_kernel(zs_infla
             for (;;) {
                 br.refill();
                 unsigned nb;
-                const int sym = decode_sym_fast(T, LL, br.hold, T_LSYM, T_LBASE, &nb);
+                const int sym = decode_sym_fast<true>(T, LL, br.hold, T_LSYM, T_LBASE, &nb);
                 if (sym < 0) {
                     if (nb > br.bits && br.bits < 15) status = ZS_BUF_ERROR;
                     else { status = ZS_DATA_ERROR; detail = D_LITLEN_CODE; }
@@ -406,7 +424,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) inflate_tps_kernel(zs_infla
                 br.drop(nb);
                 const unsigned len = base + br.take(xb);
                 br.refill();
-                const int ds = decode_sym_fast(T, DL, br.hold, T_DSYM, T_DBASE, &nb);
+                const int ds = decode_sym_fast<false>(T, DL, br.hold, T_DSYM, T_DBASE, &nb);
                 if (ds < 0) {
                     if (nb > br.bits && br.bits < 15) status = ZS_BUF_ERROR;
                     else { status = ZS_DATA_ERROR; detail = D_DIST_CODE; }
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) inflate_tps_kernel(zs_infla
 int zs_launch_inflate_tps(zs_ctx* ctx, const zs_inflate_args& a) {
     if (a.n == 0) return ZS_OK;
     unsigned ctas = (a.n + 31) / 32;
-    const unsigned cap = (unsigned)ctx->sm_count * 7u * 4u;
+    const unsigned cap = (unsigned)ctx->sm_count * (227u * 1024u / (unsigned)(kArenaBytes * kWarpsPerCta)) * 4u;
     if (ctas > cap) ctas = cap;
     ZS_KERNEL(ctx, "inflate_tps_kernel", inflate_tps_kernel<<<ctas, 32 * kWarpsPerCta, 0, ctx->stream>>>(a));
     return ZS_OK;
