@@ -1,6 +1,7 @@
 """GPU: the sharded entry point on one rank (world size 1) -- part flags, exchange plan, gather."""
 import zlib
 
+import numpy as np
 import pytest
 
 from conftest import make_mixed, pkg
@@ -48,3 +49,33 @@ def test_two_parts_in_one_process(gpu_ctx, oracle):
     stream = body + S.wrapper_trailer(1, check, len(data))
     assert zlib.decompress(stream) == data
     assert stream[:2] == S.wrapper_header(1, 6)
+
+
+def test_empty_middle_part(gpu_ctx, oracle):
+    """A rank whose chunk range is empty but lies in the middle of the stream (fewer chunks than ranks):
+    no input bytes, 32 KiB of history before them, neither first nor last -- found by the 8-rank run of
+    tools/sharded_check.py (torch hands out a null data_ptr() for an empty view)."""
+    import zlib, torch
+    B = pkg("batch")
+    S = pkg("sharded")
+    data = torch.from_numpy(np.frombuffer(make_mixed(70000, 3), dtype=np.uint8).copy()).cuda()
+    for wrap in (0, 1, 2):
+        for level in (0, 1, 6):
+            parts = []
+            for r, (b0, b1) in enumerate(((0, 0), (0, 65536), (65536, 65536), (65536, 65536), (65536, 70000))):
+                flags = (0 if r == 0 else B.FLAG_NOT_FIRST) | (0 if r == 4 else B.FLAG_NOT_LAST)
+                res = B.deflate_batch_dev(data[b0:b1], 65536, level, wrap, B.MODE_STITCHED, flags, history=min(b0, 32768), want_checks=True)
+                rr = res.read_result()
+                parts.append((bytes(res.out[: (rr.total_out_bits + 7) // 8].cpu().numpy()), int(rr.total_out_bits), int(rr.check), b1 - b0))
+            body, nbits = S.bit_concat_host([(p[0], p[1]) for p in parts])
+            check, total = None, 0
+            for _, _, c, ln in parts:
+                if wrap == 1:
+                    check = c if check is None else B.adler32_combine(check, c, ln)
+                elif wrap == 2:
+                    check = c if check is None else B.crc32_combine(check, c, ln)
+                total += ln
+            stream = body + S.wrapper_trailer(wrap, check or 0, total)
+            d = zlib.decompressobj({0: -15, 1: 15, 2: 31}[wrap])
+            host = bytes(data.cpu().numpy())
+            assert d.decompress(stream) + d.flush() == host and d.eof, (wrap, level)

@@ -39,6 +39,11 @@ def default_context(device: int | None = None) -> Context:
 def _ptr(t) -> C.c_void_p:
     if t is None:
         return None
+    if t.numel() == 0:
+        # torch reports a null data_ptr() for an empty view; the engine still needs the position of the
+        # view inside its storage (the history of an empty part of a sharded stream lies before it)
+        base = t.untyped_storage().data_ptr()
+        return C.c_void_p(base + t.storage_offset() * t.element_size() if base else 0)
     return C.c_void_p(t.data_ptr())
 
 

@@ -261,6 +261,7 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     if ((flags & ZS_FLAG_PRIME) && (mode != ZS_MODE_INDEPENDENT || wrap != ZS_WRAP_RAW))
         return bad_arg(ctx, "deflate: ZS_FLAG_PRIME needs INDEPENDENT mode and the raw wrapper (deflate.ts:373)");
     if (history > 32768) history = 32768;
+    if (!d_in) history = 0;   // no input pointer, nothing before it either
     if (mode == ZS_MODE_INDEPENDENT && !(flags & ZS_FLAG_PRIME)) history = 0;
     if (!d_in_off) {
         if (chunk_size == 0) return bad_arg(ctx, "deflate: chunk_size is zero");

@@ -48,10 +48,16 @@ int zs_set_cuda_error(zs_ctx* ctx, cudaError_t e, const char* where);
         cudaError_t _e = (expr);                                                 \
         if (_e != cudaSuccess) return zs_set_cuda_error((ctx), _e, #expr);       \
     } while (0)
+#ifdef ZS_DEBUG_HOOKS   // wait for every kernel so that a fault names the kernel that caused it
+#define ZS_DEBUG_SYNC(ctx, e) do { if ((e) == cudaSuccess) (e) = cudaStreamSynchronize((ctx)->stream); } while (0)
+#else
+#define ZS_DEBUG_SYNC(ctx, e) do { } while (0)
+#endif
 #define ZS_LAUNCH_CHECK(ctx, name)                                               \
     do {                                                                         \
         (ctx)->launches++;                                                       \
         cudaError_t _e = cudaGetLastError();                                     \
+        ZS_DEBUG_SYNC(ctx, _e);                                                  \
         if (_e != cudaSuccess) return zs_set_cuda_error((ctx), _e, name);        \
     } while (0)
 
