@@ -42,3 +42,16 @@ def test_host_side_combine_and_bounds():
         assert lib.zs_deflate_bound(n, 1) == lib.zs_deflate_bound(n, 0) + 6
         assert lib.zs_deflate_bound(n, 2) == lib.zs_deflate_bound(n, 0) + 18
     assert lib.zs_inflate_message(17) == b"invalid distance too far back"
+
+
+def test_pointer_of_an_empty_view_keeps_its_position():
+    """torch reports data_ptr() == 0 for an empty view; the engine needs where the view sits (the history
+    of an empty part of a sharded stream lies before it)."""
+    import torch
+    B = pkg("batch")
+    t = torch.arange(100, dtype=torch.uint8)
+    v = t[60:60]
+    assert v.data_ptr() == 0
+    assert B._ptr(v).value == t.data_ptr() + 60
+    assert B._ptr(t[10:20]).value == t.data_ptr() + 10
+    assert B._ptr(None) is None
