@@ -1,12 +1,14 @@
 // zsgpu_addon.cc -- Node-API addon: pure marshalling between JavaScript typed arrays and the C ABI of
 // include/zsgpu.h.  NOT compiled in this repository's image (no node, no node_api.h); it is the
 // binding a zlib-streams-ts maintainer adds.  Build:
-//   g++ -shared -fPIC -I$(node -p "require('node-addon-api').include_dir") -I<node headers> \
-//       -I../../include zsgpu_addon.cc -L../../zlib-streams-ts_b200 -lzsgpu -o zsgpu.node
+//   g++ -O2 -shared -fPIC -I<node headers> -I../../include zsgpu_addon.cc
+//       -L../../zlib-streams-ts_b200 -lzsgpu -Wl,-rpath,'$ORIGIN' -o zsgpu.node
 #include <node_api.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "zsgpu.h"
 
@@ -92,13 +94,21 @@ napi_value Checksum(napi_env env, napi_callback_info info) {
 }
 
 // ---- streaming shim: one external zs_stream per JS Stream object -------------------------------------
-void FreeStream(napi_env, void* data, void*) { delete (zs_stream*)data; }
-zs_stream* strm_of(napi_env env, napi_value v) { void* p = nullptr; napi_get_value_external(env, v, &p); return (zs_stream*)p; }
+// The holder owns what the C ABI only borrows: the gzip header record inflateGetHeader registers and
+// the buffers its extra / name / comment fields point at.
+struct Holder {
+    zs_stream s;
+    zs_gz_header gz;
+    std::vector<uint8_t> extra, name, comment;
+};
+void FreeStream(napi_env, void* data, void*) { delete (Holder*)data; }
+Holder* holder_of(napi_env env, napi_value v) { void* p = nullptr; napi_get_value_external(env, v, &p); return (Holder*)p; }
+zs_stream* strm_of(napi_env env, napi_value v) { Holder* h = holder_of(env, v); return h ? &h->s : nullptr; }
 
 // streamNew() -> external
 napi_value StreamNew(napi_env env, napi_callback_info) {
-    zs_stream* s = new zs_stream(); memset(s, 0, sizeof *s);
-    napi_value v; napi_create_external(env, s, FreeStream, nullptr, &v); return v;
+    Holder* h = new Holder(); memset(&h->s, 0, sizeof h->s); memset(&h->gz, 0, sizeof h->gz);
+    napi_value v; napi_create_external(env, h, FreeStream, nullptr, &v); return v;
 }
 // deflateInit2(h, level, method, windowBits, memLevel, strategy) -> rc  zs_stream_deflate_init
 napi_value DeflateInit2(napi_env env, napi_callback_info info) {
@@ -185,12 +195,44 @@ napi_value DeflateSetHeader(napi_env env, napi_callback_info info) {
     return num(env, zs_stream_deflate_set_header(strm_of(env, a[0]), &g));
 }
 
+// inflateGetHeader(h, extraMax, nameMax, commMax) -> rc                   zs_stream_inflate_get_header
+napi_value InflateGetHeader(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value a[4]; napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+    Holder* h = holder_of(env, a[0]);
+    if (!h) return num(env, -2);
+    memset(&h->gz, 0, sizeof h->gz);
+    h->extra.assign((size_t)i32(env, a[1]), 0); h->name.assign((size_t)i32(env, a[2]), 0); h->comment.assign((size_t)i32(env, a[3]), 0);
+    if (!h->extra.empty()) { h->gz.extra = h->extra.data(); h->gz.extra_max = (uint32_t)h->extra.size(); }
+    if (!h->name.empty()) { h->gz.name = h->name.data(); h->gz.name_max = (uint32_t)h->name.size(); }
+    if (!h->comment.empty()) { h->gz.comment = h->comment.data(); h->gz.comm_max = (uint32_t)h->comment.size(); }
+    return num(env, zs_stream_inflate_get_header(&h->s, &h->gz));
+}
+// inflateHeaderState(h) -> [done, text, time, xflags, os, hcrc, extraLen, extra, name, comment]
+// (read by the facade after inflate() while head._done is still 0)
+napi_value InflateHeaderState(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; napi_get_cb_info(env, info, &argc, a, nullptr, nullptr);
+    Holder* h = holder_of(env, a[0]);
+    napi_value arr; napi_create_array_with_length(env, 10, &arr);
+    if (!h) return arr;
+    const zs_gz_header& g = h->gz;
+    const double f[7] = {(double)g.done, (double)g.text, (double)g.time, (double)g.xflags, (double)g.os, (double)g.hcrc, (double)g.extra_len};
+    for (uint32_t i = 0; i < 7; ++i) napi_set_element(env, arr, i, num(env, f[i]));
+    const std::vector<uint8_t>* b[3] = {&h->extra, &h->name, &h->comment};
+    for (uint32_t i = 0; i < 3; ++i) {
+        void* dst = nullptr; napi_value buf;
+        napi_create_buffer_copy(env, b[i]->size(), b[i]->data(), &dst, &buf);
+        napi_set_element(env, arr, 7 + i, buf);
+    }
+    return arr;
+}
+
 napi_value Register(napi_env env, napi_value exports) {
     const struct { const char* name; napi_callback fn; } fns[] = {
         {"init", Init}, {"deflateBatch", DeflateBatch}, {"inflateBatch", InflateBatch}, {"checksum", Checksum},
         {"streamNew", StreamNew}, {"deflateInit2", DeflateInit2}, {"inflateInit2", InflateInit2}, {"process", Process},
         {"end", End}, {"setDictionary", SetDictionary}, {"inflateReset", InflateReset}, {"control", Control},
-        {"deflatePending", DeflatePending}, {"deflateSetHeader", DeflateSetHeader}};
+        {"deflatePending", DeflatePending}, {"deflateSetHeader", DeflateSetHeader},
+        {"inflateGetHeader", InflateGetHeader}, {"inflateHeaderState", InflateHeaderState}};
     for (auto& f : fns) {
         napi_value v; napi_create_function(env, f.name, NAPI_AUTO_LENGTH, f.fn, nullptr, &v);
         napi_set_named_property(env, exports, f.name, v);

@@ -21,7 +21,13 @@ function createStream(): Stream {
   return { next_in: EMPTY, next_in_index: 0, avail_in: 0, total_in: 0, next_out: EMPTY, next_out_index: 0,
            avail_out: 0, total_out: 0, msg: "", _data_type: 0, _adler: 0, _state: undefined };
 }
-type Handle = { h: unknown; which: 0 | 1 };
+// the reference's GzipHeader record, src/mod/common/types.ts
+export interface GzipHeader {
+  _text: number; _time: number; _xflags: number; _os: number; _hcrc: number; _done: number;
+  _extra: Uint8Array | null; _extra_max: number; _extra_len: number;
+  _name: Uint8Array | null; _name_max: number; _comment: Uint8Array | null; _comm_max: number;
+}
+type Handle = { h: unknown; which: 0 | 1; gzhead?: GzipHeader };
 
 export const createDeflateStream = createStream;   // deflate.ts:80
 export const createInflateStream = createStream;   // inflate.ts:68
@@ -49,7 +55,20 @@ function process(strm: Stream, flush: number, which: 0 | 1 | 2): number {
     strm.avail_in, strm.next_out, strm.next_out_index, strm.avail_out);
   strm.next_in_index += used; strm.avail_in -= used; strm.next_out_index += made; strm.avail_out -= made;
   strm.total_in = tin; strm.total_out = tout; strm._adler = adler;
+  if (st.gzhead && st.gzhead._done === 0) syncGzipHeader(st);
   return rc;
+}
+function syncGzipHeader(st: Handle): void {
+  const head = st.gzhead as GzipHeader;
+  const [done, text, time, xflags, os, hcrc, extraLen, extra, name, comment] = addon.inflateHeaderState(st.h);
+  if (!done) return;
+  head._done = done;              // 1 = header read, -1 = the stream is not gzip
+  if (done !== 1) return;
+  head._text = text; head._time = time; head._xflags = xflags; head._os = os; head._hcrc = hcrc; head._extra_len = extraLen;
+  if (head._extra_max) head._extra = (extra as Uint8Array).subarray(0, Math.min(extraLen, head._extra_max));
+  const cstr = (b: Uint8Array) => { const i = b.indexOf(0); return i < 0 ? b : b.subarray(0, i + 1); };
+  if (head._name_max) head._name = cstr(name as Uint8Array);
+  if (head._comm_max) head._comment = cstr(comment as Uint8Array);
 }
 export function deflate(strm: Stream, flush: number): number { return process(strm, flush, 0); }         // deflate.ts:716
 export function inflate(strm: Stream, flush: number): number { return process(strm, flush, 1); }         // inflate.ts:332
@@ -105,6 +124,13 @@ export function deflateSetHeader(strm: Stream, head: { _text: number; _time: num
   const z = (b?: Uint8Array | null) => { if (!b) return null; const i = b.indexOf(0); const r = new Uint8Array((i < 0 ? b.length : i) + 1); r.set(b.subarray(0, r.length - 1)); return r; };
   return addon.deflateSetHeader(st.h, head._text ? 1 : 0, head._time >>> 0, head._os & 0xff, head._hcrc ? 1 : 0,
     head._extra ? head._extra.subarray(0, head._extra_len ?? head._extra.length) : null, z(head._name), z(head._comment));
+}
+export function inflateGetHeader(strm: Stream, head: GzipHeader): number {                               // inflate.ts:1251
+  const st = strm && (strm._state as Handle);
+  if (!st || st.which !== 1 || !head) return Z_STREAM_ERROR;
+  const rc = addon.inflateGetHeader(st.h, head._extra_max | 0, head._name_max | 0, head._comm_max | 0);
+  if (rc === Z_OK) { head._done = 0; st.gzhead = head; }
+  return rc;
 }
 export function inflateReset2(strm: Stream, windowBits: number): number {                                // inflate.ts:138
   const st = strm && (strm._state as Handle);
