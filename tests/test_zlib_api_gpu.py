@@ -311,3 +311,20 @@ def test_incremental_inflate_truncated(gpu_ctx):
     d = zlib.decompressobj()
     assert bytes(out) == d.decompress(stream)            # exactly what C zlib can decode from the same bytes
     assert Z.inflateEnd(s) == Z.Z_OK
+
+
+def test_window_bits_zero_is_a_zlib_stream(gpu_ctx):
+    """inflateInit2_(strm, 0): zlib wrapper with the window size taken from the header
+    (inflateReset2, inflate.ts:138-172; CINFO check :396-415).  Fed in 7-byte pieces so that the first
+    call sees less than the 2-byte header + first block."""
+    Z = _Z()
+    s = Z.createInflateStream()
+    assert Z.inflateInit2_(s, 0) == Z.Z_OK
+    assert s._adler == 1
+    assert Z.inflateEnd(s) == Z.Z_OK
+    data = make_text(30000, 83)
+    stream = zlib.compress(data, 6)
+    out, r, total_in = chunked_inflate(stream[:1] , 0, 1, 4096)      # one byte only: no progress beyond buffering
+    assert out == b"" and r != Z.Z_STREAM_END
+    out, r, total_in = chunked_inflate(stream, 0, 7, 4096)
+    assert r == Z.Z_STREAM_END and out == data and total_in == len(stream)

@@ -439,7 +439,7 @@ int zs_stream_inflate_init(zs_ctx* ctx, zs_stream* strm, int window_bits) {
     st->window_bits = window_bits;
     strm->state = st;
     strm->total_in = strm->total_out = 0;
-    strm->adler = (window_bits > 0 && ((window_bits >> 4) + 5) & 1) ? 1u : 0u;
+    strm->adler = (window_bits >= 0 && (((window_bits >> 4) + 5) & 1)) ? 1u : 0u;   // 0 = window size from the zlib header
     strm->data_type = 0;
     return ZS_OK;
 }
@@ -448,7 +448,7 @@ int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint3
     InflateState* st = istate(strm);
     if (!st || !dict) return ZS_STREAM_ERROR;
     // inflate.ts:1229: raw streams any time before data, wrapped streams only when Z_NEED_DICT was returned
-    if (st->window_bits > 0 && !st->need_dict) return ZS_STREAM_ERROR;
+    if (st->window_bits >= 0 && !st->need_dict) return ZS_STREAM_ERROR;
     if (st->need_dict) {
         // DICTID check (inflate.ts:1233-1238): bytes 2..5 of the zlib stream
         uint32_t id = 0;
@@ -622,7 +622,7 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
         push_ready(st, out_len);
         if (!st->body) {
             // mark_bit > 0 means the wrapper header is complete and the block loop was entered
-            if (mark_bit == 0 && st->window_bits > 0) return ZS_OK;
+            if (mark_bit == 0 && st->window_bits >= 0) return ZS_OK;
             const bool gz = st->window_bits > 15 && st->in.size() >= 2 && st->in[0] == 0x1f && st->in[1] == 0x8b;
             st->trailer = st->window_bits < 0 ? 0 : gz ? 2 : 1;
             st->run_check = st->trailer == 1 ? 1u : 0u;
@@ -750,7 +750,7 @@ int zs_stream_inflate_reset2(zs_stream* strm, int window_bits) {
     st->window_bits = window_bits;
     st->leftover.clear();
     const int rc = zs_stream_inflate_reset(strm);
-    strm->adler = (window_bits > 0 && ((window_bits >> 4) + 5) & 1) ? 1u : 0u;
+    strm->adler = (window_bits >= 0 && (((window_bits >> 4) + 5) & 1)) ? 1u : 0u;   // 0 = window size from the zlib header
     return rc;
 }
 
