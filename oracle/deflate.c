@@ -253,7 +253,7 @@ typedef struct {
     size_t strstart, fill, wbase, block_start;
     size_t insert;
     uint32_t head[W_SIZE], prev[W_SIZE];
-    int level;
+    int level, strategy;
     size_t match_start;
     unsigned match_length, prev_length;
     size_t prev_match;
@@ -408,7 +408,7 @@ static void flush_block(enc_t* e, int last) {
     e->bc.opt_len += 3u * ((unsigned)max_blindex + 1) + 5 + 5 + 4;
     size_t opt_lenb = (e->bc.opt_len + 3 + 7) >> 3;
     size_t static_lenb = (e->bc.static_len + 3 + 7) >> 3;
-    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (static_lenb <= opt_lenb || e->strategy == ZO_FIXED) opt_lenb = static_lenb; /* trees.ts:567 */
 
     if (stored_len + 4 <= opt_lenb && can_store) {
         stored_block(e, e->win + e->block_start, stored_len, last);
@@ -557,7 +557,8 @@ static void run_slow(enc_t* e) {
         if (hash_head > e->wbase && e->prev_length < (unsigned)cfg->lazy &&
             e->strstart - hash_head <= MAX_DIST) {
             e->match_length = longest_match(e, hash_head);
-            if (e->match_length <= 5 && e->match_length == MIN_MATCH && e->strstart - e->match_start > TOO_FAR)
+            if (e->match_length <= 5 && (e->strategy == ZO_FILTERED || /* deflate.ts:1386-1392 */
+                                         (e->match_length == MIN_MATCH && e->strstart - e->match_start > TOO_FAR)))
                 e->match_length = MIN_MATCH - 1;
         }
         if (e->prev_length >= MIN_MATCH && e->match_length <= e->prev_length) {
@@ -585,6 +586,72 @@ static void run_slow(enc_t* e) {
     }
 }
 
+/* deflate_huff, deflate.ts:1525-1560, driven to the end of the input: literals only */
+static void run_huff(enc_t* e) {
+    for (;;) {
+        if (e->fill == e->strstart) {
+            fill_window(e);
+            if (e->fill == e->strstart) break;
+        }
+        e->match_length = 0;
+        int bflush = tally_lit(e, e->win[e->strstart]);
+        e->strstart++;
+        if (bflush) flush_block(e, 0);
+    }
+}
+
+/* deflate_rle as C zlib 1.3 defines it (deflate.c deflate_rle): matches at distance 1 only.  The
+ * reference's port compares the previous byte with the scan INDEX instead of the byte at that
+ * index (deflate.ts:1467-1469, `prev == ++scan`), which can never hold three times in a row, so
+ * the reference itself emits literals only for Z_RLE -- byte for byte what run_huff produces
+ * (zo_deflate_oneshot2's `rle_like_reference`).  The engine implements the intended algorithm,
+ * so this is the one it is compared with. */
+static void run_rle(enc_t* e) {
+    for (;;) {
+        if (e->fill - e->strstart <= MAX_MATCH) {
+            fill_window(e);
+            if (e->fill == e->strstart) break;
+        }
+        size_t lookahead = e->fill - e->strstart;
+        unsigned ml = 0;
+        if (lookahead >= MIN_MATCH && e->strstart > 0) {
+            const uint8_t* w = e->win;
+            const uint8_t prev = w[e->strstart - 1];
+            while (ml < MAX_MATCH && w[e->strstart + ml] == prev) ml++;   /* the 8-way unrolled scan */
+            if (ml < MIN_MATCH) ml = 0;
+            if (ml > lookahead) ml = (unsigned)lookahead;
+        }
+        int bflush;
+        if (ml >= MIN_MATCH) {
+            bflush = tally_dist(e, 1, ml - MIN_MATCH);
+            e->strstart += ml;
+        } else {
+            bflush = tally_lit(e, e->win[e->strstart]);
+            e->strstart++;
+        }
+        if (bflush) flush_block(e, 0);
+    }
+}
+
+/* deflate_stored, deflate.ts:1140-1279, for one call that holds the whole input and an output
+ * buffer of at least deflateBound bytes: the first loop (:1146-1197) then copies straight from the
+ * input in blocks of MAX_STORED = 65535 bytes -- `have` never limits a block, and a shorter block is
+ * only ever the last piece (`len == left + avail_in`) -- and marks the block that takes the last
+ * byte as final under Z_FINISH; an empty input still gets its empty final block (:1160-1163). */
+static void run_stored(enc_t* e, int finish) {
+    size_t pos = e->strstart;
+    for (;;) {
+        size_t rest = e->total - pos;
+        size_t len = rest > 65535 ? 65535 : rest;
+        if (len == 0 && !finish) break;
+        int last = finish && len == rest;
+        stored_block(e, e->win + pos, len, last);
+        pos += len;
+        if (last || pos == e->total) break;
+    }
+    e->strstart = e->block_start = pos;
+}
+
 /* deflateBound, deflate.ts:615-674 for the default windowBits 15 / memLevel 8 state */
 size_t zo_deflate_bound(size_t n, int wrap) {
     size_t wraplen = wrap == 0 ? 0 : wrap == 1 ? 6 : 18;
@@ -593,8 +660,15 @@ size_t zo_deflate_bound(size_t n, int wrap) {
 
 int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap, const uint8_t* dict,
                            size_t dict_len, int flush, uint8_t* out, size_t out_cap) {
+    if (level == 0) return ZO_STREAM_ERROR; /* the historical entry point: levels 1..9 */
+    return zo_deflate_oneshot2(in, in_len, level, ZO_DEFAULT_STRATEGY, 0, wrap, dict, dict_len, flush, out, out_cap);
+}
+
+int64_t zo_deflate_oneshot2(const uint8_t* in, size_t in_len, int level, int strategy, int rle_like_reference,
+                            int wrap, const uint8_t* dict, size_t dict_len, int flush, uint8_t* out,
+                            size_t out_cap) {
     if (level == -1) level = 6;
-    if (level < 1 || level > 9 || wrap < 0 || wrap > 2) return ZO_STREAM_ERROR;
+    if (level < 0 || level > 9 || wrap < 0 || wrap > 2 || strategy < 0 || strategy > ZO_FIXED) return ZO_STREAM_ERROR;
     if (flush != ZO_FINISH && flush != ZO_SYNC_FLUSH) return ZO_STREAM_ERROR;
     if (dict_len && wrap == 2) return ZO_STREAM_ERROR; /* deflateSetDictionary, deflate.ts:373 */
     if (!tables_ready) tables_build();
@@ -604,13 +678,14 @@ int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap
      * bytes are loaded (deflate.ts:383-392) */
     uint32_t dict_id = dict_len ? zo_adler32(1u, dict, dict_len) : 0;
     if (dict_len > W_SIZE) { dict += dict_len - W_SIZE; dict_len = W_SIZE; }
-    uint8_t* vbuf = (uint8_t*)malloc(dict_len + in_len + 8);
+    uint8_t* vbuf = (uint8_t*)malloc(dict_len + in_len + MAX_MATCH + 8);
     if (!vbuf) { free(e); return ZO_MEM_ERROR; }
     if (dict_len) memcpy(vbuf, dict, dict_len);
     if (in_len) memcpy(vbuf + dict_len, in, in_len);
-    memset(vbuf + dict_len + in_len, 0, 8);
+    memset(vbuf + dict_len + in_len, 0, MAX_MATCH + 8);
     e->win = vbuf;
     e->level = level;
+    e->strategy = strategy;
     e->out = out;
     e->out_cap = out_cap;
     e->match_length = e->prev_length = MIN_MATCH - 1;
@@ -619,7 +694,7 @@ int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap
     /* headers, deflate.ts:750-832 */
     if (wrap == 1) {
         unsigned header = (8u + (7u << 4)) << 8;
-        unsigned lf = level < 2 ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+        unsigned lf = (strategy >= ZO_HUFFMAN_ONLY || level < 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3; /* deflate.ts:757-766 */
         header |= lf << 6;
         if (dict_len) header |= 0x20;
         header += 31 - header % 31;
@@ -631,7 +706,7 @@ int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap
     } else if (wrap == 2) {
         put_byte(e, 0x1f); put_byte(e, 0x8b); put_byte(e, 8);
         for (int i = 0; i < 5; i++) put_byte(e, 0);
-        put_byte(e, level == 9 ? 2 : level < 2 ? 4 : 0);
+        put_byte(e, level == 9 ? 2 : (strategy >= ZO_HUFFMAN_ONLY || level < 2) ? 4 : 0); /* deflate.ts:797 */
         put_byte(e, 255); /* OS_CODE, deflate/constants.ts:30 */
     }
 
@@ -653,9 +728,17 @@ int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap
     }
     e->total = dict_len + in_len;
 
-    if (LEVELS[level].lazy_fn) run_slow(e); else run_fast(e);
+    /* deflate(), deflate.ts:917-926: which block function runs */
+    const int stored = level == 0;
+    if (stored) run_stored(e, flush == ZO_FINISH);
+    else if (strategy == ZO_HUFFMAN_ONLY || (strategy == ZO_RLE && rle_like_reference)) run_huff(e);
+    else if (strategy == ZO_RLE) run_rle(e);
+    else if (LEVELS[level].lazy_fn) run_slow(e);
+    else run_fast(e);
 
-    if (flush == ZO_FINISH) {
+    if (stored) {
+        if (flush != ZO_FINISH) stored_block(e, NULL, 0, 0);
+    } else if (flush == ZO_FINISH) {
         flush_block(e, 1);
     } else {
         if (e->sym_next) flush_block(e, 0);

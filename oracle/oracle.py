@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
         L.zo_deflate_oneshot.restype = C.c_int64
         L.zo_deflate_oneshot.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.c_size_t, C.c_int, u8p,
                                          C.c_size_t]
+        L.zo_deflate_oneshot2.restype = C.c_int64
+        L.zo_deflate_oneshot2.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_size_t,
+                                          C.c_int, u8p, C.c_size_t]
         L.zo_build_tree.restype = C.c_int
         L.zo_build_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32)]
@@ -161,13 +164,16 @@ def block_types(data, window_bits: int = -15):
     return {t for t in range(3) if counts[t]}
 
 
-def deflate(data, level: int = 6, wrap: int = 1, dictionary=None, flush: int = Z_FINISH) -> bytes:
-    """One-shot deflateInit2_(level, 8, wbits(wrap), 8, 0) [+ dictionary] + deflate(flush)."""
+def deflate(data, level: int = 6, wrap: int = 1, dictionary=None, flush: int = Z_FINISH, strategy: int = 0,
+            rle_like_reference: bool = False) -> bytes:
+    """One-shot deflateInit2_(level, 8, wbits(wrap), 8, strategy) [+ dictionary] + deflate(flush).
+    Z_RLE is C zlib's algorithm unless rle_like_reference (the reference's scan never finds a run)."""
     p, n, k = _buf(data)
     dp, dn, dk = _buf(dictionary)
     cap = lib().zo_deflate_bound(n, wrap) + 64
     out = (C.c_ubyte * cap)()
-    r = lib().zo_deflate_oneshot(p, n, level, wrap, dp, dn, flush, C.addressof(out), cap)
+    r = lib().zo_deflate_oneshot2(p, n, level, strategy, int(rle_like_reference), wrap, dp, dn, flush,
+                                  C.addressof(out), cap)
     if r < 0:
         raise RuntimeError(f"oracle deflate failed: {r}")
     return bytes(out[:r])

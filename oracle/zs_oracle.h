@@ -105,6 +105,22 @@ int64_t zo_deflate_oneshot(const uint8_t* in, size_t in_len, int level, int wrap
                            const uint8_t* dict, size_t dict_len, int flush, uint8_t* out,
                            size_t out_cap);
 
+/* The same with every level and strategy of deflateInit2_ (deflate.ts:253-297): level 0 is
+ * deflate_stored (deflate.ts:1140-1279), ZO_FILTERED changes deflate_slow's short-match rule
+ * (:1386-1392), ZO_HUFFMAN_ONLY is deflate_huff (:1525-1560), ZO_FIXED forces static trees
+ * (trees.ts:567).  ZO_RLE is C zlib's deflate_rle -- the algorithm the port intends and the engine
+ * implements; with rle_like_reference != 0 it is what the reference really emits for Z_RLE: its
+ * scan compares a byte with an index (deflate.ts:1467-1469), never finds a run, and degenerates to
+ * deflate_huff's output. */
+#define ZO_DEFAULT_STRATEGY 0
+#define ZO_FILTERED 1
+#define ZO_HUFFMAN_ONLY 2
+#define ZO_RLE 3
+#define ZO_FIXED 4
+int64_t zo_deflate_oneshot2(const uint8_t* in, size_t in_len, int level, int strategy,
+                            int rle_like_reference, int wrap, const uint8_t* dict, size_t dict_len,
+                            int flush, uint8_t* out, size_t out_cap);
+
 /* build_tree + gen_bitlen + gen_codes (trees.ts:54-76,187-316) for one tree, exposed so the GPU
  * code-length construction can be compared entry by entry.  kind: 0 literal/length (286 symbols,
  * limit 15), 1 distance (30, limit 15), 2 bit-length (19, limit 7).  freq is modified like the

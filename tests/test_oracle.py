@@ -240,3 +240,65 @@ def test_deflate64_test_encoder_roundtrip(oracle):
     assert ret == oracle.Z_DATA_ERROR            # distance codes 30/31 are invalid in plain deflate
     z = oracle.deflate64_encode(_d64_cases()["runs"], 65538)
     assert len(z) < 400                          # 70000 zeros in two symbols
+
+
+def _run_heavy(seed):
+    rnd = random.Random(seed)
+    return b"".join(bytes([rnd.randrange(256)]) * rnd.randrange(1, 700) for _ in range(600))
+
+
+@pytest.mark.parametrize("strategy", [1, 2, 3, 4])   # Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED
+def test_deflate_strategies_byte_exact_with_zlib(oracle, strategy):
+    """deflateInit2_'s strategies (deflate.ts:253-297, :1386-1392, :1450-1560, trees.ts:567) against C zlib
+    1.3, the stand-in the reference's own tests use.  Z_RLE is C zlib's algorithm here."""
+    cases = [b"", b"a", b"abc", b"aaaa", bytes(200000), bytes(j % 251 for j in range(1 << 17)), rand_bytes(100000, 7),
+             make_text(300000, strategy), make_mixed(300000, strategy), _run_heavy(strategy)]
+    for level in (1, 3, 4, 6, 9):
+        for d in cases:
+            for wrap, wb in ((0, -15), (1, 15), (2, 31)):
+                co = zlib.compressobj(level, 8, wb, 8, strategy)
+                z = co.compress(d) + co.flush()
+                if wrap == 2:
+                    z = z[:9] + b"\xff" + z[10:]
+                assert oracle.deflate(d, level, wrap, strategy=strategy) == z, (level, len(d), wrap)
+
+
+def test_deflate_rle_as_the_reference_runs_it(oracle):
+    """The reference's deflate_rle compares the previous byte with the scan index (deflate.ts:1467-1469), so it
+    never finds a run: its Z_RLE output is deflate_huff's, literal for literal."""
+    for d in (b"", bytes(5000), _run_heavy(1), make_text(100000, 2)):
+        ref = oracle.deflate(d, 6, 1, strategy=3, rle_like_reference=True)
+        assert ref == oracle.deflate(d, 6, 1, strategy=2)
+        assert len(oracle.deflate(d, 6, 1, strategy=3)) <= len(ref)
+        ret, out, _, _ = oracle.inflate(ref, 15, len(d) + 64)
+        assert ret == oracle.Z_STREAM_END and out == d
+
+
+def test_deflate_level0_byte_exact_with_zlib(oracle):
+    """deflate_stored (deflate.ts:1140-1279) in one call with a deflateBound-sized buffer, against libz's
+    compress2 (Python's zlib.compress hands deflate a growing 16 KiB buffer, which changes where stored
+    blocks are cut, so libz is called directly)."""
+    import ctypes as C
+    import ctypes.util
+    name = ctypes.util.find_library("z") or "libz.so.1"
+    try:
+        libz = C.CDLL(name)
+    except OSError:
+        pytest.skip("no libz")
+    libz.compressBound.restype = C.c_ulong
+    libz.compressBound.argtypes = [C.c_ulong]
+    libz.compress2.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_char_p, C.c_ulong, C.c_int]
+    for d in (b"", b"a", bytes(65535), bytes(65536), bytes(131070), rand_bytes(65535 * 3 + 1, 9), make_text(200000, 1)):
+        cap = libz.compressBound(len(d)) + 64
+        out = C.create_string_buffer(cap)
+        n = C.c_ulong(cap)
+        assert libz.compress2(out, C.byref(n), d, len(d), 0) == 0
+        o = oracle.deflate(d, 0, 1)
+        assert o == out.raw[: n.value]
+        assert oracle.block_types(o, 15) == {0}
+        # every strategy runs deflate_stored at level 0 (deflate.ts:917-926); only the header's FLEVEL is shared
+        assert oracle.deflate(d, 0, 1, strategy=2) == o
+    # a sync-flushed part: the blocks, then the empty stored block of Z_SYNC_FLUSH
+    part = oracle.deflate(b"xyz" * 30000, 0, 0, flush=oracle.Z_SYNC_FLUSH)
+    assert part.endswith(b"\x00\x00\x00\xff\xff")
+    assert zlib.decompressobj(-15).decompress(part) == b"xyz" * 30000

@@ -69,6 +69,7 @@ def test_strategy_roundtrip_and_size(gpu_ctx, oracle, name, level, strategy):
     assert ret == oracle.Z_STREAM_END and out == data and used == len(s)
     assert zlib.decompress(s) == data
     ref = _zlib_size(data, level, st, 15)
+    assert len(oracle.deflate(data, level, 1, strategy=st)) == ref   # the oracle's restatement is C zlib's, byte for byte
     # every 64 KiB chunk starts its own block: allow one dynamic header per chunk on top of the 3 %
     n_chunks = max(1, -(-len(data) // 65536))
     assert len(s) <= ref * 1.03 + 64 + 80 * n_chunks, (name, level, strategy, len(s), ref)
