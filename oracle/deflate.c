@@ -1,8 +1,8 @@
 /*
  * deflate.c -- oracle (test infrastructure): CPU restatement of the reference encoder for levels
- * 1..9, default strategy, windowBits 15, memLevel 8 -- deflate/deflate.ts (CONFIGURATION_TABLE,
- * INSERT_STRING, fill_window/slide_hash, longest_match, deflate_fast, deflate_slow,
- * deflateSetDictionary, header/trailer emission), deflate/trees.ts (build_tree, gen_bitlen,
+ * 0..9 and every strategy, windowBits 15, memLevel 8 -- deflate/deflate.ts (CONFIGURATION_TABLE,
+ * INSERT_STRING, fill_window/slide_hash, longest_match, deflate_stored, deflate_fast, deflate_slow,
+ * deflate_huff, deflate_rle, deflateSetDictionary, header/trailer emission), deflate/trees.ts (build_tree, gen_bitlen,
  * gen_codes, scan_tree/send_tree, compress_block, _tr_flush_block, _tr_stored_block) and
  * deflate/utils.ts (_tr_tally_*, d_code).
  *
