@@ -386,6 +386,107 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     return lit | (best_len << 15) | best_dist;
 }
 
+#ifdef ZS_LZ_STRAGGLER
+// EXPERIMENT (off by default; build with ZS_NVCC_EXTRA=-DZS_LZ_STRAGGLER): the lazy levels' chain walk in
+// warp-synchronous form with a straggler stop.  All 32 lanes of the batch run the candidate loop in lock
+// step; once at least kStopAfter candidates have been visited and at most kStopActive lanes are still
+// walking, the batch stops and those lanes keep the best match they have.  A lone long chain otherwise
+// holds up its warp and, through the step barrier, the whole CTA: in the CPU model of this policy
+// (tools/lzmodel.c, `stop_active=4 stop_after=8`) the heaviest batch of a step shrinks from 26.7 to 15.5
+// (text, level 6), 166 to 28 (mixed corpus, level 9) and 86 to 33 (32-bit counters) at +0.2 % / +0.1 % /
+// +0.0 % size; the worst size found is +1.6 % (JSON rows at level 9).  The vote is taken on well defined
+// per-lane state, so the result does not depend on scheduling.
+// Same rules as search_position<1>, `live` = the lane holds a data position of the range.
+#ifndef ZS_STOP_AFTER
+#define ZS_STOP_AFTER 8
+#endif
+#ifndef ZS_STOP_ACTIVE
+#define ZS_STOP_ACTIVE 4
+#endif
+__device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
+                                                         uint32_t cs, uint32_t ce, bool live) {
+    const uint32_t room = live ? ce - q : 0u;
+    const unsigned max_len = room < 258u ? room : 258u;
+    const unsigned pi = (c.cb + q) & (kRing - 1u);
+    uint32_t pw0 = 0, pw1 = 0;
+    if (live) { pw0 = ring32(S, pi); pw1 = ring32(S, pi + 4); }
+    const uint32_t lit = (pw0 & 0xffu) << 24;
+    const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
+    const uint32_t back = c.cross ? q + c.pre : q - cs;
+    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
+    unsigned best_len = 2, best_dist = 0;
+    unsigned ci = pi, dist = 0;
+    int chain = (live && max_len >= 3) ? cfg.chain : 0;
+    for (unsigned it = 0;; ++it) {
+        const unsigned walking = __ballot_sync(ZS_FULL_MASK, chain > 0);
+        if (walking == 0) break;
+        if (it >= (unsigned)ZS_STOP_AFTER && (unsigned)__popc(walking) <= (unsigned)ZS_STOP_ACTIVE) break;
+        if (chain > 0) {
+            do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
+                const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
+                if (delta == 0) { chain = 0; break; }
+                dist += delta;
+                if (dist > max_back) { chain = 0; break; }
+                ci = (ci - delta) & (kRing - 1u);
+                uint32_t x = ring32(S, ci) ^ pw0;
+                if ((x & 0xffffffu) != 0) break;  // hash collision
+                unsigned len;
+                if (x) {
+                    len = 3;
+                } else {
+                    x = ring32(S, ci + 4) ^ pw1;
+                    if (x) {
+                        len = 4 + first_diff_byte(x);
+                    } else {
+                        if (best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {
+                            if (delta <= kDenseHop) chain -= chain >> 2;
+                            break;
+                        }
+                        len = 8;
+                        unsigned aa = (ci + 8u) & ~3u, ab = (pi + 8u) & ~3u;
+                        const unsigned sa = ((ci + 8u) & 3u) * 8u, sb = ((pi + 8u) & 3u) * 8u;
+                        uint32_t a0 = *reinterpret_cast<const uint32_t*>(S.ring + aa);
+                        uint32_t b0 = *reinterpret_cast<const uint32_t*>(S.ring + ab);
+                        while (len < max_len) {
+                            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 4);
+                            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 8);
+                            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 4);
+                            const uint32_t b2 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 8);
+                            const uint32_t yl = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+                            const uint32_t yh = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+                            if (yl | yh) {
+                                len += yl ? first_diff_byte(yl) : 4 + first_diff_byte(yh);
+                                break;
+                            }
+                            a0 = a2; b0 = b2;
+                            aa += 8; ab += 8;
+                            len += 8;
+                        }
+                    }
+                }
+                if (len > max_len) len = max_len;
+                if (len > best_len) {
+                    if (best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
+                        const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
+                        if (interior || delta <= kDenseHop) chain >>= 2;
+                        if (interior && chain > kInteriorChain) chain = kInteriorChain;
+                    }
+                    best_len = len;
+                    best_dist = dist;
+                    if (len >= nice) chain = 0;
+                } else if (len == best_len && delta <= kDenseHop) {
+                    chain -= chain >> 2;
+                }
+            } while (0);
+            --chain;
+        }
+    }
+    if (best_len < c.min_len) return lit;
+    if (best_len == 3 && best_dist > kTooFar) return lit;
+    return lit | (best_len << 15) | best_dist;
+}
+#endif  // ZS_LZ_STRAGGLER
+
 // ---- stage 4: resolve (wide) -----------------------------------------------------------------------
 // mj[].y layout: exit (9 bits) | is_match << 9 | popc(visited) << 10 (6 bits) | pair exit - 32 << 16
 // (9 bits) | pair symbol count << 25 (7 bits).  The pair fields are valid for the first batch of an
@@ -755,6 +856,18 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                     if (qw + 32u > qd64 && qw < n) {
                         while (qw >= ce_w) { ++js; cs_w = ce_w; ce_w = S.bnd[js + 1]; }   // qw < n: terminates
                         uint32_t r = 0;
+#ifdef ZS_LZ_STRAGGLER
+                        if constexpr (kMode == 1) {   // every lane of the batch takes part in the votes
+                            const bool live = q >= rc.q_data && q < n;
+                            uint32_t cs = cs_w, ce = ce_w;
+                            if (live && q >= ce) {
+                                unsigned jl = js;
+                                do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
+                            }
+                            const uint32_t rr = search_position_sync(S, cfg, rc, q, cs, ce, live);
+                            r = live ? rr : 0u;
+                        } else
+#endif
                         if (q >= rc.q_data && q < n) {
                             uint32_t cs = cs_w, ce = ce_w;
                             if (q >= ce) {   // a boundary inside the batch
