@@ -15,6 +15,9 @@
  *                                at least M candidates have been visited (0 = off)
  *   dense_hop=H interior=C       the two constants of the lazy levels' work bounds (8, 16)
  *   work_shift=S                 lazy levels: every 8-byte compare round also takes 1/2^S off the chain budget (-1 = off)
+ *   skip_lag=D skip_cap=N        greedy levels: a candidate at distance >= D that the parse did not visit and that lies
+ *                                inside a match longer than max_insert (deflate_fast would not have inserted it,
+ *                                deflate.ts:1310-1322) is passed over without using up the chain budget; at most N per position
  *   dump=path                    write the symbols (lit<<24 | len<<15 | dist) as little-endian u32
  */
 #include <stdint.h>
@@ -32,6 +35,8 @@ static const uint8_t* buf;      /* the whole input, absolute positions; 300 read
 static size_t total;
 static uint16_t head[1 << kHashBits], prev16[32768];
 static int dense_hop = 8, interior_chain = 16, stop_active = 0, stop_after = 0, work_shift = -1;
+static int skip_lag = 0, skip_cap = 16;   /* greedy levels: candidates the reference would not have inserted are passed over */
+static uint8_t* mark;                     /* 1 = deflate_fast would have put this position into its hash chains */
 
 static inline uint32_t ld32(size_t p) { uint32_t v; memcpy(&v, buf + p, 4); return v; }
 static inline unsigned hash3(uint32_t w) { return ((w & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
@@ -61,7 +66,7 @@ static uint32_t search_pos(const level_cfg* cfg, int lazy, size_t abs, size_t ra
     const unsigned nice = (unsigned)cfg->nice < max_len ? (unsigned)cfg->nice : max_len;
     const uint32_t back = cross ? (uint32_t)(abs - range0) + pre : (uint32_t)(abs - cs);
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
-    unsigned best_len = 2, best_dist = 0, dist = 0;
+    unsigned best_len = 2, best_dist = 0, dist = 0, skipped = 0;
     unsigned ci = (unsigned)abs & 0xffffu;
     const uint32_t pw0 = ld32(abs), pw1 = ld32(abs + 4);
     for (int chain = cfg->chain; chain > 0; --chain) {
@@ -73,6 +78,11 @@ static uint32_t search_pos(const level_cfg* cfg, int lazy, size_t abs, size_t ra
         if (dist > max_back) break;
         ci = (ci - delta) & 0xffffu;
         const size_t cand = abs - dist;
+        if (skip_lag && dist >= (unsigned)skip_lag && !mark[cand] && skipped < (unsigned)skip_cap) {
+            ++skipped;
+            ++chain;   /* free: undoes the loop's decrement */
+            continue;
+        }
         uint32_t x = ld32(cand) ^ pw0;
         if ((x & 0xffffffu) != 0) continue;
         unsigned len;
@@ -247,6 +257,8 @@ int main(int argc, char** argv) {
         else if (!strncmp(argv[i], "interior=", 9)) interior_chain = atoi(argv[i] + 9);
         else if (!strncmp(argv[i], "cross=", 6)) cross = atoi(argv[i] + 6);
         else if (!strncmp(argv[i], "work_shift=", 11)) work_shift = atoi(argv[i] + 11);
+        else if (!strncmp(argv[i], "skip_lag=", 9)) skip_lag = atoi(argv[i] + 9);
+        else if (!strncmp(argv[i], "skip_cap=", 9)) skip_cap = atoi(argv[i] + 9);
         else if (!strncmp(argv[i], "dump=", 5)) dump = argv[i] + 5;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
@@ -256,6 +268,7 @@ int main(int argc, char** argv) {
 
     uint32_t* res = (uint32_t*)malloc(sizeof(uint32_t) * (seg_chunks * chunk + 64));
     uint32_t* sym = (uint32_t*)malloc(sizeof(uint32_t) * (chunk + 64));
+    if (skip_lag) mark = (uint8_t*)calloc(total + 300, 1);
     uint64_t bits = 0, nsym_total = 0, cand_total = 0, simt_total = 0, batches = 0, nblocks = 0, stopped = 0, rounds_total = 0, simt_heavy = 0, step_heavy_total = 0, steps = 0;
     uint64_t hist[16] = {0};   /* longest walk of a batch, log2 buckets */
 
@@ -274,7 +287,29 @@ int main(int argc, char** argv) {
         const size_t n = seg_end - prime0, q_data = seg_start - prime0;
         /* insert + search, batch by batch (aligned to the range start like the kernel's batches) */
         unsigned step_heavy = 0;
+        /* resolve + parse + blocks, incrementally: the parse trails the search like in the pipeline */
+        size_t pp = seg_start, pcs = seg_start, pce = seg_start + chunk < seg_end ? seg_start + chunk : seg_end, pns = 0, pblk0 = seg_start;
+        if (mark) memset(mark + prime0, 1, seg_start - prime0);   /* deflateSetDictionary inserts every position */
+#define PARSE_UNTIL(limit_)                                                                                              \
+        while (pp < (limit_)) {                                                                                          \
+            const uint32_t r = res[pp - seg_start];                                                                      \
+            const unsigned L = (r >> 15) & 0x1ffu;                                                                       \
+            const unsigned Ln = pp + 1 < pce ? (res[pp + 1 - seg_start] >> 15) & 0x1ffu : 0;                             \
+            const int deferred = lazy && L >= 3 && L < (unsigned)cfg->lazy && Ln > L;                                    \
+            if (pns == kSymLimit) { bits += block_bits(sym, pns, pp - pblk0); if (fd) fwrite(sym, 4, pns, fd); nblocks++; nsym_total += pns; pns = 0; pblk0 = pp; } \
+            if (L >= 3 && !deferred) {                                                                                   \
+                sym[pns++] = r;                                                                                          \
+                if (mark) { mark[pp] = 1; if (L <= (unsigned)cfg->lazy) memset(mark + pp, 1, L); }                       \
+                pp += L;                                                                                                 \
+            } else { sym[pns++] = r & 0xff000000u; if (mark) mark[pp] = 1; pp += 1; }                                    \
+            if (pp >= pce) {                                                                                             \
+                bits += block_bits(sym, pns, pce - pblk0); if (fd) fwrite(sym, 4, pns, fd); nblocks++; nsym_total += pns; \
+                pns = 0; pcs = pce; pce = pcs + chunk < seg_end ? pcs + chunk : seg_end; pblk0 = pcs; pp = pcs;          \
+                if (pcs >= seg_end) break;                                                                               \
+            }                                                                                                            \
+        }
         for (size_t q0 = 0; q0 < n; q0 += 32) {
+            if (skip_lag && prime0 + q0 > seg_start + (size_t)skip_lag) PARSE_UNTIL(prime0 + q0 - (size_t)skip_lag);
             unsigned walk[32], rnd[32];
             unsigned longest = 0;
             for (unsigned l = 0; l < 32 && q0 + l < n; l++) insert_pos(prime0 + q0 + l, prime0, pre);
@@ -319,23 +354,7 @@ int main(int argc, char** argv) {
             int b = 0; while ((1u << b) <= longest && b < 15) b++;
             hist[b]++;
         }
-        /* resolve + parse + blocks, chunk by chunk */
-        for (size_t cs = seg_start; cs < seg_end; cs += chunk) {
-            size_t ce = cs + chunk; if (ce > seg_end) ce = seg_end;
-            size_t ns = 0, blk_pos0 = cs, p = cs;
-            while (p < ce) {
-                const uint32_t r = res[p - seg_start];
-                const unsigned L = (r >> 15) & 0x1ffu;
-                const unsigned Ln = p + 1 < ce ? (res[p + 1 - seg_start] >> 15) & 0x1ffu : 0;
-                const int deferred = lazy && L >= 3 && L < (unsigned)cfg->lazy && Ln > L;
-                if (ns == kSymLimit) { bits += block_bits(sym, ns, p - blk_pos0); if (fd) fwrite(sym, 4, ns, fd); nblocks++; nsym_total += ns; ns = 0; blk_pos0 = p; }
-                if (L >= 3 && !deferred) { sym[ns++] = r; p += L; }
-                else { sym[ns++] = r & 0xff000000u; p += 1; }
-            }
-            bits += block_bits(sym, ns, ce - blk_pos0);
-            if (fd) fwrite(sym, 4, ns, fd);
-            nblocks++; nsym_total += ns;
-        }
+        PARSE_UNTIL(seg_end);
     }
     printf("bytes_in %zu  bytes_out %llu  ratio %.5f  blocks %llu  symbols %llu\n", total, (unsigned long long)((bits + 7) / 8),
            (double)((bits + 7) / 8) / (double)total, (unsigned long long)nblocks, (unsigned long long)nsym_total);
