@@ -282,6 +282,21 @@ def main():
             traffic = json.load(open(tpath))["lz77_kernel_dram_bytes_per_input_byte"] * n
         except Exception:
             traffic = None
+    # Second yardstick, because the kernel is issue bound and not DRAM bound: warp instructions per second
+    # against the SMs' issue rate (4 schedulers per SM, one warp instruction each per clock).  Instructions
+    # per input byte come from the committed ncu capture, time and clock are this run's.
+    issue = None
+    try:
+        ipb = json.load(open(tpath))["lz77_kernel_warp_inst_per_input_byte"]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+        if lz_avg_ms > 0 and mhz:
+            ach = ipb * n / (lz_avg_ms / 1e3) / 1e9
+            pk = sms * 4 * mhz * 1e6 / 1e9
+            issue = {"warp_inst_per_input_byte": ipb, "achieved_ginst_per_s": ach, "peak_ginst_per_s": pk,
+                     "frac": ach / pk, "sm_mhz": mhz, "source": "profiles/lz77_r1e_summary.md x this run's kernel time"}
+    except Exception:
+        issue = None
     roofline = {"bound": "hbm", "kernel": "lz77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms_per_launch": lz_avg_ms, "algorithmic_bytes_per_launch": algo_bytes,
@@ -289,7 +304,8 @@ def main():
                 "per_kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())},
                 # what actually limits the kernel (ncu --set full, profiles/lz77_r1e_summary.md): not DRAM
                 "limiter": "integer ALU pipe / instruction issue: SM throughput 72 %, IPC 2.86 of 4, "
-                           "28 warp-instructions per input byte, DRAM throughput 0.7 %"}
+                           "28 warp-instructions per input byte, DRAM throughput 0.7 %",
+                "issue": issue}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
