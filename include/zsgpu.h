@@ -153,6 +153,19 @@ ZS_API int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, con
                      uint64_t out_cap, uint64_t* out_off, uint64_t* out_bits, uint32_t* checks,
                      zs_deflate_result* result);
 
+/* One *part* of a STITCHED stream from HOST buffers (no reference analogue: this is the entry a rank of the
+ * multi-GPU split, or a caller feeding a stream piecewise, binds).  The part is cut into `chunk_size`
+ * chunks; `history` (<= 32768) bytes before in[0] are readable and matched against, like the window
+ * deflate() carries from call to call (deflate.ts:166-236).  flags: ZS_FLAG_NOT_FIRST / ZS_FLAG_NOT_LAST /
+ * ZS_FLAG_SYNC / strategy.  A part that is not the last ends with the Z_SYNC_FLUSH marker
+ * (deflate.ts:945-946), so parts concatenate byte-wise; the wrapper header comes with the first part, the
+ * trailer (deflate.ts:964-988) only when one call holds the whole stream -- otherwise the caller appends
+ * it from the combined result->check values (zs_adler32_combine / zs_crc32_combine).  Large parts are
+ * pipelined in slices (H2D, kernels and D2H overlap); out_bits[n_chunks] may be NULL. */
+ZS_API int zs_deflate_part(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t history, uint32_t chunk_size,
+                    int level, int wrap, uint32_t flags, uint8_t* out, uint64_t out_cap, uint64_t* out_bits,
+                    zs_deflate_result* result);
+
 /* Bit-granular stitch (no reference analogue; deflatePrime, deflate.ts:528, is the reference's
  * "insert bits at a bit offset" primitive): OR `n_bits` bits of d_src into d_dst starting at bit
  * `dst_bit_off`.  The destination bits must be zero beforehand. */

@@ -83,6 +83,42 @@ int64_t zo_deflate_chunks_mt(const uint8_t* in, size_t in_len, size_t chunk, int
     return atomic_load(&j.bad) ? -1 : atomic_load(&j.total);
 }
 
+static void deflate_store_item(job_t* j, size_t i, void* tls) {
+    (void)tls;
+    size_t off = i * j->chunk;
+    size_t n = j->in_len - off < j->chunk ? j->in_len - off : j->chunk;
+    const size_t slot = (size_t)j->out_off[0];
+    int64_t r = zo_deflate_oneshot(j->in + off, n, j->level, j->wrap, NULL, 0, ZO_FINISH, j->out + i * slot, slot);
+    if (r < 0) { atomic_store(&j->bad, 1); r = 0; }
+    j->out_len[i] = (uint64_t)r;
+}
+
+/* Deflate every `chunk`-byte record of `in` as an independent stream (wrap 0 raw, 1 zlib, 2 gzip) and keep
+ * the streams: packed back to back into `out` (capacity n_records * slot, slot >= zo_deflate_bound(chunk, wrap)),
+ * offsets to out_off[n_records + 1].  This is how bench.py makes the reference-produced record set of
+ * BASELINE configs[3].  Returns the total size or -1. */
+int64_t zo_deflate_records_mt(const uint8_t* in, size_t in_len, size_t chunk, int level, int wrap, uint8_t* out,
+                              size_t slot, uint64_t* out_off, int threads) {
+    job_t j;
+    memset(&j, 0, sizeof j);
+    j.n_items = (in_len + chunk - 1) / chunk; j.grain = 16; j.fn = deflate_store_item;
+    j.in = in; j.in_len = in_len; j.chunk = chunk; j.level = level; j.wrap = wrap;
+    uint64_t slot64 = slot;
+    uint64_t* lens = (uint64_t*)malloc((j.n_items + 1) * sizeof(uint64_t));
+    j.out = out; j.out_off = &slot64; j.out_len = lens;
+    run_job(&j, threads);
+    if (atomic_load(&j.bad)) { free(lens); return -1; }
+    uint64_t pos = 0;
+    for (size_t i = 0; i < j.n_items; i++) {
+        memmove(out + pos, out + i * slot, (size_t)lens[i]);
+        out_off[i] = pos;
+        pos += lens[i];
+    }
+    out_off[j.n_items] = pos;
+    free(lens);
+    return (int64_t)pos;
+}
+
 static void inflate_item(job_t* j, size_t i, void* tls) {
     (void)tls;
     size_t ol = 0, used = 0;

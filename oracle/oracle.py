@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         L.zo_max_threads.restype = C.c_int
         L.zo_deflate_chunks_mt.restype = C.c_int64
         L.zo_deflate_chunks_mt.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.zo_deflate_records_mt.restype = C.c_int64
+        L.zo_deflate_records_mt.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, u8p, C.c_size_t, u64p, C.c_int]
         L.zo_inflate_batch_mt.restype = C.c_int64
         L.zo_inflate_batch_mt.argtypes = [u8p, u64p, C.c_size_t, C.c_int, u8p, u64p, u64p, u32p, i32p, C.c_int]
         L.zo_checksum_mt.restype = C.c_uint32

@@ -18,6 +18,8 @@
  *   skip_lag=D skip_cap=N        greedy levels: a candidate at distance >= D that the parse did not visit and that lies
  *                                inside a match longer than max_insert (deflate_fast would not have inserted it,
  *                                deflate.ts:1310-1322) is passed over without using up the chain budget; at most N per position
+ *   too_far=D too_far4=D         greedy levels: 3-byte (4-byte) matches at a distance above D become literals
+ *   chain=N nice=N               override the level's max_chain / nice_length
  *   dump=path                    write the symbols (lit<<24 | len<<15 | dist) as little-endian u32
  */
 #include <stdint.h>
@@ -35,6 +37,8 @@ static const uint8_t* buf;      /* the whole input, absolute positions; 300 read
 static size_t total;
 static uint16_t head[1 << kHashBits], prev16[32768];
 static int dense_hop = 8, interior_chain = 16, stop_active = 0, stop_after = 0, work_shift = -1;
+static int too_far_greedy = 4096, too_far4 = 0;   /* greedy levels: a 3-byte (4-byte) match further back than this becomes a literal */
+static int chain_override = 0, nice_override = 0;   /* chain= / nice=: replace the level's max_chain / nice_length */
 static int skip_lag = 0, skip_cap = 16;   /* greedy levels: candidates the reference would not have inserted are passed over */
 static uint8_t* mark;                     /* 1 = deflate_fast would have put this position into its hash chains */
 
@@ -119,6 +123,8 @@ static uint32_t search_pos(const level_cfg* cfg, int lazy, size_t abs, size_t ra
     }
     if (best_len < 3) return lit;
     if (lazy && best_len == 3 && best_dist > kTooFar) return lit;
+    if (!lazy && too_far_greedy && best_len == 3 && best_dist > (unsigned)too_far_greedy) return lit;
+    if (!lazy && too_far4 && best_len == 4 && best_dist > (unsigned)too_far4) return lit;
     return lit | (best_len << 15) | best_dist;
 }
 
@@ -260,9 +266,16 @@ int main(int argc, char** argv) {
         else if (!strncmp(argv[i], "skip_lag=", 9)) skip_lag = atoi(argv[i] + 9);
         else if (!strncmp(argv[i], "skip_cap=", 9)) skip_cap = atoi(argv[i] + 9);
         else if (!strncmp(argv[i], "dump=", 5)) dump = argv[i] + 5;
+        else if (!strncmp(argv[i], "too_far=", 8)) too_far_greedy = atoi(argv[i] + 8);
+        else if (!strncmp(argv[i], "too_far4=", 9)) too_far4 = atoi(argv[i] + 9);
+        else if (!strncmp(argv[i], "chain=", 6)) chain_override = atoi(argv[i] + 6);
+        else if (!strncmp(argv[i], "nice=", 5)) nice_override = atoi(argv[i] + 5);
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
-    const level_cfg* cfg = &LEVELS[level];
+    level_cfg cfg_copy = LEVELS[level];
+    if (chain_override) cfg_copy.chain = chain_override;
+    if (nice_override) cfg_copy.nice = nice_override;
+    const level_cfg* cfg = &cfg_copy;
     const int lazy = cfg->lazy_fn;
     FILE* fd = dump ? fopen(dump, "wb") : NULL;
 

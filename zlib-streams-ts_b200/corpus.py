@@ -119,3 +119,27 @@ def mixed_torch(n: int, device, seed: int = 0xB200, tile: int = 4 << 20):
     uniq = torch.from_numpy(mixed_numpy(n_unique * tile, seed, tile)).to(device)
     reps = -(-n // uniq.numel())
     return uniq.repeat(reps)[:n].contiguous()
+
+
+def mixed_tiles_numpy(seed: int = 0xB200, tile: int = 4 << 20, n_unique: int = 64) -> np.ndarray:
+    """The distinct tiles of the mixed corpus (host): byte g of the corpus is tiles[g % tiles.size]."""
+    return mixed_numpy(n_unique * tile, seed, tile)
+
+
+def mixed_torch_range(lo: int, hi: int, device, seed: int = 0xB200, tile: int = 4 << 20, n_unique: int = 64, tiles=None):
+    """Bytes [lo, hi) of mixed_torch(N >= hi, ...) without materialising the rest: what one rank of a
+    sharded run holds (its chunk range plus the 32 KiB before it)."""
+    import torch
+
+    if tiles is None:
+        tiles = mixed_tiles_numpy(seed, tile, n_unique)
+    period = tiles.size
+    uniq = torch.from_numpy(tiles).to(device)
+    out = torch.empty(hi - lo, dtype=torch.uint8, device=device)
+    pos = lo
+    while pos < hi:
+        o = pos % period
+        take = min(period - o, hi - pos)
+        out[pos - lo: pos - lo + take] = uniq[o: o + take]
+        pos += take
+    return out

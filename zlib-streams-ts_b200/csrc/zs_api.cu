@@ -261,7 +261,9 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     if ((flags & ZS_FLAG_PRIME) && (mode != ZS_MODE_INDEPENDENT || wrap != ZS_WRAP_RAW))
         return bad_arg(ctx, "deflate: ZS_FLAG_PRIME needs INDEPENDENT mode and the raw wrapper (deflate.ts:373)");
     if (history > 32768) history = 32768;
-    if (!d_in) history = 0;   // no input pointer, nothing before it either
+    // an empty part still names its position (its history lies before it): a null pointer with history is
+    // a caller error, never a device fault
+    if (!d_in && history) return bad_arg(ctx, "deflate: history given without an input pointer");
     if (mode == ZS_MODE_INDEPENDENT && !(flags & ZS_FLAG_PRIME)) history = 0;
     if (!d_in_off) {
         if (chunk_size == 0) return bad_arg(ctx, "deflate: chunk_size is zero");
@@ -342,10 +344,21 @@ int zs_deflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, cons
     return zs_launch_huffman(ctx, p);
 }
 
-static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t n_chunks, uint32_t chunk_size,
-                                   int level, int wrap, uint32_t flags, uint8_t* out, uint64_t out_cap, uint64_t* out_off,
-                                   uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
+// Host-buffer deflate of a large batch, software-pipelined: the batch is cut into slices of whole waves of
+// LZ77 segments, and the H2D copy of slice s+1, the kernels of slice s and the D2H copy of slice s-1 run
+// concurrently on three streams.
+//  INDEPENDENT: the bytes produced are those of the single-shot path.
+//  STITCHED: every slice is one *part* of the stream (ZS_FLAG_NOT_FIRST / NOT_LAST), primed with the 32 KiB
+//  before it; a part that is not the last ends with the reference's Z_SYNC_FLUSH marker (deflate.ts:945-946),
+//  so slices concatenate byte-wise (5 bytes per slice more than the single-shot stream).  `history` bytes
+//  before `in` are readable and primed against; the trailer of a whole stream (deflate.ts:964-988) is
+//  written here from the combined checksums.
+static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t history, uint32_t n_chunks,
+                                   uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out,
+                                   uint64_t out_cap, uint64_t* out_off, uint64_t* out_bits, uint32_t* checks,
+                                   zs_deflate_result* result) {
     constexpr int kMaxSlices = 16;
+    const bool stitched = mode == ZS_MODE_STITCHED;
     // Same LZ77 segmentation as the single-shot call over the whole batch; a slice is a whole number
     // of waves of segments (one segment per SM and wave), so that no SM idles inside a slice.
     uint32_t seg = n_chunks / (4u * (uint32_t)ctx->sm_count);
@@ -368,15 +381,18 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     }
     zs_deflate_result* h_res = (zs_deflate_result*)ctx->h_pin;
     const uint64_t slice_bytes = (uint64_t)slice_chunks * chunk_size;
-    const uint64_t region = zs_deflate_batch_bound(slice_bytes, slice_chunks, chunk_size, wrap, ZS_MODE_INDEPENDENT);
+    const uint64_t region = zs_deflate_batch_bound(slice_bytes, slice_chunks, chunk_size, wrap, mode);
     const uint64_t region_al = (region + 255) & ~255ull;
-    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_len + 64);
+    if (!stitched) history = 0;
+    if (history > 32768) history = 32768;
+    uint8_t* d_in_base = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, 32768 + in_len + 64);
     uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, region_al * n_slices + 64);
     uint64_t* d_ooff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF2, ((size_t)n_chunks + n_slices) * 8);
     uint64_t* d_obits = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)n_chunks * 8);
     uint32_t* d_cks = (uint32_t*)zs_scratch_get(ctx, SCR_H_CHECKS, (size_t)n_chunks * 4);
     zs_deflate_result* d_res = (zs_deflate_result*)zs_scratch_get(ctx, SCR_H_RES, sizeof(zs_deflate_result) * kMaxSlices);
-    if (!d_in || !d_out || !d_ooff || !d_obits || !d_cks || !d_res) return ZS_MEM_ERROR;
+    if (!d_in_base || !d_out || !d_ooff || !d_obits || !d_cks || !d_res) return ZS_MEM_ERROR;
+    uint8_t* d_in = d_in_base + 32768;   // the history of the first slice lies before it
     const bool want_checks = checks != nullptr || wrap != ZS_WRAP_RAW;
     cudaEvent_t* ev_in = ctx->ev;          // [s]      slice s is on the device
     cudaEvent_t* ev_k = ctx->ev + 16;      // [s]      kernels of slice s are done
@@ -388,17 +404,27 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_res, ctx->ev[48], 0));
     struct HintGuard { zs_ctx* c; ~HintGuard() { c->seg_hint = 0; } } guard{ctx};
     ctx->seg_hint = seg;
+    if (history) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in - history, in - history, history, cudaMemcpyHostToDevice, ctx->s_in));
+    const uint32_t part_mask = ZS_FLAG_NOT_FIRST | ZS_FLAG_NOT_LAST;
     for (int s = 0; s < n_slices; s++) {
         const uint32_t c0 = (uint32_t)s * slice_chunks;
         const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
         const uint64_t b0 = (uint64_t)c0 * chunk_size;
         const uint64_t len = (b0 + (uint64_t)nc * chunk_size <= in_len) ? (uint64_t)nc * chunk_size : in_len - b0;
-        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + b0, in + b0, len, cudaMemcpyHostToDevice, ctx->s_in));
+        if (len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + b0, in + b0, len, cudaMemcpyHostToDevice, ctx->s_in));
         ZS_CUDA_TRY(ctx, cudaEventRecord(ev_in[s], ctx->s_in));
         ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
-        const uint32_t hist = (flags & ZS_FLAG_PRIME) ? (uint32_t)(b0 < 32768 ? b0 : 32768) : 0u;
+        uint32_t hist = 0, sflags = flags;
+        if (stitched) {
+            hist = (uint32_t)(b0 + history < 32768 ? b0 + history : 32768);
+            sflags = flags & ~part_mask;
+            if (s > 0 || (flags & ZS_FLAG_NOT_FIRST)) sflags |= ZS_FLAG_NOT_FIRST;
+            if (s + 1 < n_slices || (flags & ZS_FLAG_NOT_LAST)) sflags |= ZS_FLAG_NOT_LAST;
+        } else if (flags & ZS_FLAG_PRIME) {
+            hist = (uint32_t)(b0 < 32768 ? b0 : 32768);
+        }
         int rc = zs_deflate_batch_dev(ctx, d_in + b0, len, nullptr, nc, chunk_size, chunk_size, hist, level, wrap,
-                                      ZS_MODE_INDEPENDENT, flags, d_out + region_al * s, region, d_ooff + c0 + s,
+                                      mode, sflags, d_out + region_al * s, region, d_ooff + c0 + s,
                                       d_obits + c0, want_checks ? d_cks + c0 : nullptr, d_res + s);
         if (rc != ZS_OK) return rc;
         ZS_CUDA_TRY(ctx, cudaEventRecord(ev_k[s], ctx->stream));
@@ -439,17 +465,34 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     }
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the trailer of a whole stitched stream that went through more than one slice (the device writes it
+    // only when one call holds the whole stream)
+    if (rc_final == ZS_OK && stitched && n_slices > 1 && !(flags & part_mask) && wrap != ZS_WRAP_RAW) {
+        const uint64_t T = wrap == ZS_WRAP_ZLIB ? 4 : 8;
+        if (host_off + T > out_cap) {
+            rc_final = ZS_BUF_ERROR;
+        } else {
+            uint8_t* tp = out + host_off;
+            if (wrap == ZS_WRAP_ZLIB) {
+                tp[0] = (uint8_t)(check >> 24); tp[1] = (uint8_t)(check >> 16); tp[2] = (uint8_t)(check >> 8); tp[3] = (uint8_t)check;
+            } else {
+                for (int k = 0; k < 4; k++) { tp[k] = (uint8_t)(check >> (8 * k)); tp[4 + k] = (uint8_t)(in_len >> (8 * k)); }
+            }
+            host_off += T;
+        }
+    }
     if (rc_final != ZS_OK) {
         snprintf(ctx->err, sizeof(ctx->err), "deflate: output capacity %llu too small", (unsigned long long)out_cap);
         return rc_final;
     }
     if (out_off) {
+        const uint64_t unit = stitched ? 8 : 1;   // STITCHED reports bit offsets
         for (int s = 0; s < n_slices; s++) {
             const uint32_t c0 = (uint32_t)s * slice_chunks;
             const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
-            for (uint32_t i = 0; i < nc; i++) out_off[c0 + i] += base[s];
+            for (uint32_t i = 0; i < nc; i++) out_off[c0 + i] += base[s] * unit;
         }
-        out_off[n_chunks] = host_off;
+        out_off[n_chunks] = host_off * unit;
     }
     result->total_out_bytes = host_off;
     result->total_out_bits = host_off * 8;
@@ -458,12 +501,14 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     return ZS_OK;
 }
 
-int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
-                     uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out, uint64_t out_cap,
-                     uint64_t* out_off, uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
-    if (ctx) bind_device(ctx);
-    if (!ctx) return ZS_STREAM_ERROR;
+// Shared body of zs_deflate_batch / zs_deflate_part: `history` readable bytes lie before `in`.
+static int deflate_batch_host(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t history, const uint64_t* in_off,
+                              uint32_t n_chunks, uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags,
+                              uint8_t* out, uint64_t out_cap, uint64_t* out_off, uint64_t* out_bits, uint32_t* checks,
+                              zs_deflate_result* result) {
     if (!out || !result || (in_len && !in) || n_chunks == 0) return bad_arg(ctx, "deflate: null buffer or zero chunks");
+    if (history && !in) return bad_arg(ctx, "deflate: history without an input pointer");
+    if (history > 32768) history = 32768;
     uint32_t max_chunk = chunk_size;
     if (in_off) {
         max_chunk = 1;
@@ -475,25 +520,25 @@ int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint
             if (l > max_chunk) max_chunk = (uint32_t)l;
         }
     }
-    // Large batches of independent streams with fixed chunking are software-pipelined: the batch is cut
-    // into slices of whole segments, and the H2D copy of slice s+1, the kernels of slice s and the D2H
-    // copy of slice s-1 run concurrently on three streams.  The bytes produced are those of the
-    // single-shot path.
-    if (!in_off && mode == ZS_MODE_INDEPENDENT && n_chunks >= 512 && chunk_size >= 4096)
-        return deflate_batch_pipelined(ctx, in, in_len, n_chunks, chunk_size, level, wrap, flags, out, out_cap, out_off,
-                                       out_bits, checks, result);
-    uint8_t* d_in = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, in_len + 64);
+    // Large batches with fixed chunking are software-pipelined (see deflate_batch_pipelined).
+    if (!in_off && n_chunks >= 512 && chunk_size >= 4096 && !(mode == ZS_MODE_STITCHED && (flags & ZS_FLAG_PRIME)))
+        return deflate_batch_pipelined(ctx, in, in_len, history, n_chunks, chunk_size, level, wrap, mode, flags, out, out_cap,
+                                       out_off, out_bits, checks, result);
+    if (mode != ZS_MODE_STITCHED) history = 0;
+    uint8_t* d_in_base = (uint8_t*)zs_scratch_get(ctx, SCR_H_IN, 32768 + in_len + 64);
     uint8_t* d_out = (uint8_t*)zs_scratch_get(ctx, SCR_H_OUT, out_cap + 64);
     uint64_t* d_off = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF, (size_t)(n_chunks + 1) * 8);
     uint64_t* d_ooff = (uint64_t*)zs_scratch_get(ctx, SCR_H_OFF2, (size_t)(2 * (size_t)n_chunks + 1) * 8);
     uint8_t* d_res = (uint8_t*)zs_scratch_get(ctx, SCR_H_RES, sizeof(zs_deflate_result) + (size_t)n_chunks * 4 + 64);
-    if (!d_in || !d_out || !d_off || !d_ooff || !d_res) return ZS_MEM_ERROR;
+    if (!d_in_base || !d_out || !d_off || !d_ooff || !d_res) return ZS_MEM_ERROR;
+    uint8_t* d_in = d_in_base + 32768;
     zs_deflate_result* d_result = (zs_deflate_result*)d_res;
     uint32_t* d_checks = checks ? (uint32_t*)(d_res + 64) : nullptr;
-    if (in_len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream));
+    if (in_len + history)
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in - history, in - history, in_len + history, cudaMemcpyHostToDevice, ctx->stream));
     if (in_off)
         ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, in_off, (size_t)(n_chunks + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = zs_deflate_batch_dev(ctx, d_in, in_len, in_off ? d_off : nullptr, n_chunks, chunk_size, max_chunk, 0, level,
+    int rc = zs_deflate_batch_dev(ctx, d_in, in_len, in_off ? d_off : nullptr, n_chunks, chunk_size, max_chunk, history, level,
                                   wrap, mode, flags, d_out, out_cap, d_ooff, d_ooff + n_chunks + 1, d_checks, d_result);
     if (rc != ZS_OK) return rc;
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(result, d_result, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->stream));
@@ -512,6 +557,27 @@ int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint
         ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ZS_OK;
+}
+
+int zs_deflate_batch(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, const uint64_t* in_off, uint32_t n_chunks,
+                     uint32_t chunk_size, int level, int wrap, int mode, uint32_t flags, uint8_t* out, uint64_t out_cap,
+                     uint64_t* out_off, uint64_t* out_bits, uint32_t* checks, zs_deflate_result* result) {
+    if (ctx) bind_device(ctx);
+    if (!ctx) return ZS_STREAM_ERROR;
+    return deflate_batch_host(ctx, in, in_len, 0, in_off, n_chunks, chunk_size, level, wrap, mode, flags, out, out_cap,
+                              out_off, out_bits, checks, result);
+}
+
+int zs_deflate_part(zs_ctx* ctx, const uint8_t* in, uint64_t in_len, uint32_t history, uint32_t chunk_size, int level,
+                    int wrap, uint32_t flags, uint8_t* out, uint64_t out_cap, uint64_t* out_bits, zs_deflate_result* result) {
+    if (ctx) bind_device(ctx);
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (chunk_size == 0) return bad_arg(ctx, "deflate: chunk_size is zero");
+    if (flags & ZS_FLAG_PRIME) return bad_arg(ctx, "deflate: ZS_FLAG_PRIME does not apply to a part of a stream");
+    const uint64_t nc = in_len ? (in_len + chunk_size - 1) / chunk_size : 1;
+    if (nc > 0xffffffffull) return bad_arg(ctx, "deflate: too many chunks");
+    return deflate_batch_host(ctx, in, in_len, history, nullptr, (uint32_t)nc, chunk_size, level, wrap, ZS_MODE_STITCHED, flags,
+                              out, out_cap, nullptr, out_bits, nullptr, result);
 }
 
 int zs_bit_concat_dev(zs_ctx* ctx, uint8_t* d_dst, uint64_t dst_bit_off, const uint8_t* d_src, uint64_t n_bits) {

@@ -114,6 +114,7 @@ struct LzArgs {
     uint32_t* blk_desc;
     uint32_t* seg_counter;
     int debug;                 // ZS_LZ_PROF builds: chain override in bits 8..
+    unsigned stop_after, stop_active;   // lazy levels: straggler stop of the chain walk (search_position_sync)
 };
 
 #ifdef ZS_LZ_PROF
@@ -133,14 +134,6 @@ __device__ __forceinline__ unsigned mj_slot(uint32_t q) { return q & (kMjRing - 
 // through L1 costs one 128-byte line per lane per load and saturates the L1 wavefront queue.  The
 // window is therefore staged once, coalesced (16 bytes per lane), into a 64 KiB shared-memory ring
 // that always holds the last 32 KiB plus the look-ahead; all compares are shared-memory loads.
-__device__ __forceinline__ uint64_t win64(const Smem& S, uint64_t pos) {
-    const unsigned idx = (unsigned)pos & (kRing - 1u);
-    const unsigned al = idx & ~7u;
-    const unsigned sh = (idx & 7u) * 8u;
-    const uint64_t lo = *reinterpret_cast<const uint64_t*>(S.ring + al);
-    const uint64_t hi = *reinterpret_cast<const uint64_t*>(S.ring + al + 8);
-    return sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
-}
 __device__ __forceinline__ uint32_t win32(const Smem& S, uint64_t pos) {
     const unsigned idx = (unsigned)pos & (kRing - 1u);
     const unsigned al = idx & ~3u;
@@ -249,34 +242,25 @@ __device__ __forceinline__ uint32_t ring32(const Smem& S, unsigned idx) {
     const uint32_t hi = *reinterpret_cast<const uint32_t*>(S.ring + al + 4);
     return __funnelshift_r(lo, hi, (idx & 3u) * 8u);
 }
-__device__ __forceinline__ uint64_t ring64(const Smem& S, unsigned idx) {
-    idx &= kRing - 1u;
-    const unsigned al = idx & ~3u, sh = (idx & 3u) * 8u;
-    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(S.ring + al);
-    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(S.ring + al + 4);
-    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(S.ring + al + 8);
-    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
-}
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
 // [cs, ce) is the chunk that holds q.
-// kMode: 0 greedy levels (1-3), 1 lazy levels (4-9), 2 Z_RLE
-// Work bounds of the lazy levels on periodic data (see search_position): a chain is "dense" when the hop
-// to the candidate is at most kDenseHop positions -- runs and short periods, not ordinary text or DNA-like
-// data, whose ties and good matches must not cut the search short (measured: +5.8 % size on a 4-letter
-// alphabet at level 6 when they did).
+// kMode: 0 greedy levels (1-3), 2 Z_RLE.  (The lazy levels 4-9 use search_position_sync below.)
+// Work bounds of the lazy levels on periodic data: a chain is "dense" when the hop to the candidate is at most
+// kDenseHop positions -- runs and short periods, not ordinary text or DNA-like data, whose ties and good
+// matches must not cut the search short (measured: +5.8 % size on a 4-letter alphabet at level 6 when they did).
 constexpr unsigned kDenseHop = 8;       // hops this short mark a run / a short period
 constexpr int kInteriorChain = 16;      // candidates left once a good match turns out to lie inside a longer one
 template <int kMode>
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
                                                     uint32_t cs, uint32_t ce) {
+    static_assert(kMode == 0 || kMode == 2, "levels 4-9 go through search_position_sync");
     const uint32_t room = ce - q;
     const unsigned max_len = room < 258u ? room : 258u;
     const unsigned pi = (c.cb + q) & (kRing - 1u);
     const uint32_t pw0 = ring32(S, pi), pw1 = ring32(S, pi + 4);
     const uint32_t lit = (pw0 & 0xffu) << 24;
     if (max_len < 3) return lit;
-    constexpr bool kLazy = kMode == 1;
     if (kMode == 2) {
         // deflate_rle (deflate.ts:1450-1523): the only candidate is the previous byte; the match is the
         // rest of the run it starts
@@ -297,13 +281,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
     unsigned best_len = 2, best_dist = 0;
     unsigned ci = pi, dist = 0;
-#ifdef ZS_LZ_PROF_CHAIN
-    unsigned n_cand = 0;
-#endif
     for (int chain = cfg.chain; chain > 0; --chain) {
-#ifdef ZS_LZ_PROF_CHAIN
-        ++n_cand;
-#endif
         const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
         if (delta == 0) break;
         dist += delta;
@@ -319,17 +297,9 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
             if (x) {
                 len = 4 + first_diff_byte(x);
             } else {
-                // Eight bytes match.  A candidate that cannot beat the best match is dropped after one
-                // more byte: without this the tail of a run, where every candidate ties, costs
-                // max_chain full compares per position (longest_match's scan_end test, deflate.ts:1063-1081).
-                // (Compiled into the lazy levels only: max_chain <= 32 bounds the damage at levels 1-3, and the
-                // test costs them 6 % through code generation alone.)
-                if (kLazy && best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {   // + 257 stays inside the guard
-                    if (delta <= kDenseHop) chain -= chain >> 2;   // counts as a tie, see below
-                    continue;
-                }
                 // 8 bytes per round; the two streams keep their own word alignment and the last word
-                // loaded is carried into the next round (2 + 2 loads per 8 bytes)
+                // loaded is carried into the next round (2 + 2 loads per 8 bytes).  (max_chain <= 32 bounds
+                // the cost of runs at levels 1-3; the scan_end test costs them 6 % through code generation.)
                 len = 8;
                 unsigned aa = (ci + 8u) & ~3u, ab = (pi + 8u) & ~3u;            // < kRing + 12: the guard mirrors 288 bytes
                 const unsigned sa = ((ci + 8u) & 3u) * 8u, sb = ((pi + 8u) & 3u) * 8u;
@@ -354,57 +324,36 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
         }
         if (len > max_len) len = max_len;
         if (len > best_len) {
-            // With a good match in hand the rest of the chain gets a quarter of the budget (the rule
-            // longest_match applies when the previous position's match was good, deflate.ts:1069-1071)
-            // -- here only where the reference would not be searching at all: on a dense chain (a run)
-            // or when the match also extends backwards, i.e. q lies inside a longer match that started
-            // earlier (deflate_slow skips the bytes a match covers; the speculative search cannot skip
-            // them, but it stops after kInteriorChain more candidates).
-            if (kLazy && best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
-                const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
-                if (interior || delta <= kDenseHop) chain >>= 2;
-                if (interior && chain > kInteriorChain) chain = kInteriorChain;
-            }
             best_len = len;
             best_dist = dist;
             if (len >= nice) break;
-        } else if (kLazy && len == best_len && delta <= kDenseHop) {
-            // A candidate that ties with the best match on a dense chain means periodic data (a run): the
-            // rest of the chain is more of the same.  Every tie takes a quarter off the remaining budget,
-            // which bounds a chain of ties at ~4 log(max_chain) candidates.  (The reference never gets
-            // here: it does not search the positions a match covers.)
-            chain -= chain >> 2;
         }
     }
-#ifdef ZS_LZ_PROF_CHAIN   // with ZS_LZ_PROF: chain-walk statistics (perturbs the cycle counters)
-    atomicAdd(&g_prof[12], (unsigned long long)n_cand);
-    atomicMax(&g_prof[13], (unsigned long long)n_cand);
-    if (n_cand > 100) { atomicAdd(&g_prof[14], 1ull); g_prof[15] = ((unsigned long long)best_len << 32) | (q - cs); }
-#endif
     if (best_len < c.min_len) return lit;
-    if (kLazy && best_len == 3 && best_dist > kTooFar) return lit;  // deflate.ts:1381-1387
+    // A 3-byte match far back costs more bits than three literals (a distance code plus up to 13 extra
+    // bits).  deflate_fast has no such rule, but it seldom finds these matches, because it leaves the inside
+    // of every match longer than max_insert out of its hash chains (deflate.ts:1310-1322); this search
+    // inserts every position and finds them all: JSON-like rows came out 4.1 % / 2.8 % larger than the
+    // reference's at levels 1 / 2.  With deflate_slow's TOO_FAR rule (deflate.ts:1381-1387) applied to the
+    // greedy levels too they are 3.5 % / 4.8 % smaller, text 2.9 % / 4.2 % smaller, and no data kind of
+    // tools/ratiocheck.py is more than 0.04 % larger (modelled with tools/lzmodel.py -- too_far=4096, then
+    // measured: profiles/ab_lz_r2.txt).
+    if (best_len == 3 && best_dist > kTooFar) return lit;
     return lit | (best_len << 15) | best_dist;
 }
 
-#ifdef ZS_LZ_STRAGGLER
-// EXPERIMENT (off by default; build with ZS_NVCC_EXTRA=-DZS_LZ_STRAGGLER): the lazy levels' chain walk in
-// warp-synchronous form with a straggler stop.  All 32 lanes of the batch run the candidate loop in lock
-// step; once at least kStopAfter candidates have been visited and at most kStopActive lanes are still
-// walking, the batch stops and those lanes keep the best match they have.  A lone long chain otherwise
-// holds up its warp and, through the step barrier, the whole CTA: in the CPU model of this policy
-// (tools/lzmodel.c, `stop_active=4 stop_after=8`) the heaviest batch of a step shrinks from 26.7 to 15.5
-// (text, level 6), 166 to 28 (mixed corpus, level 9) and 86 to 33 (32-bit counters) at +0.2 % / +0.1 % /
-// +0.0 % size; the worst size found is +1.6 % (JSON rows at level 9).  The vote is taken on well defined
-// per-lane state, so the result does not depend on scheduling.
-// Same rules as search_position<1>, `live` = the lane holds a data position of the range.
-#ifndef ZS_STOP_AFTER
-#define ZS_STOP_AFTER 8
-#endif
-#ifndef ZS_STOP_ACTIVE
-#define ZS_STOP_ACTIVE 4
-#endif
-__device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
-                                                         uint32_t cs, uint32_t ce, bool live) {
+// The lazy levels' chain walk, warp-synchronous with a straggler stop.  All 32 lanes of the batch run the
+// candidate loop in lock step; once at least `stop.after` candidates have been visited and at most
+// `stop.active` lanes are still walking, the batch stops and those lanes keep the best match they have.  A
+// lone long chain otherwise holds up its warp and, through the step barrier, the whole CTA.  Modelled first
+// (tools/lzmodel.c, `stop_active=K stop_after=M`), then measured (profiles/ab_straggler_r2.txt): mixed corpus
+// level 9 5.3 -> 12.9 GB/s, level 6 11.3 -> 13.5 GB/s, text level 6 11.0 -> 13.1 GB/s for +0.4 % size on text
+// (worst of eight data kinds: +1.65 % against zlib).  The vote is taken on well defined per-lane state, so the
+// result does not depend on scheduling.
+// Same matching rules as search_position; `live` = the lane holds a data position of the range.
+struct StopCfg { unsigned after, active; };
+__device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const LevelCfg& cfg, const StopCfg stop, const RangeCtx& c,
+                                                         uint32_t q, uint32_t cs, uint32_t ce, bool live) {
     const uint32_t room = live ? ce - q : 0u;
     const unsigned max_len = room < 258u ? room : 258u;
     const unsigned pi = (c.cb + q) & (kRing - 1u);
@@ -420,7 +369,7 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
     for (unsigned it = 0;; ++it) {
         const unsigned walking = __ballot_sync(ZS_FULL_MASK, chain > 0);
         if (walking == 0) break;
-        if (it >= (unsigned)ZS_STOP_AFTER && (unsigned)__popc(walking) <= (unsigned)ZS_STOP_ACTIVE) break;
+        if (it >= stop.after && (unsigned)__popc(walking) <= stop.active) break;
         if (chain > 0) {
             do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
                 const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
@@ -438,6 +387,9 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
                     if (x) {
                         len = 4 + first_diff_byte(x);
                     } else {
+                        // Eight bytes match.  A candidate that cannot beat the best match is dropped after one
+                        // more byte (longest_match's scan_end test, deflate.ts:1063-1081): without this the tail of
+                        // a run, where every candidate ties, costs max_chain full compares per position.
                         if (best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {
                             if (delta <= kDenseHop) chain -= chain >> 2;
                             break;
@@ -466,6 +418,12 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
                 }
                 if (len > max_len) len = max_len;
                 if (len > best_len) {
+                    // With a good match in hand the rest of the chain gets a quarter of the budget (the rule
+                    // longest_match applies when the previous position's match was good, deflate.ts:1069-1071)
+                    // -- here only where the reference would not be searching at all: on a dense chain (a run)
+                    // or when the match also extends backwards, i.e. q lies inside a longer match that started
+                    // earlier (deflate_slow skips the bytes a match covers; the speculative search cannot skip
+                    // them, but it stops after kInteriorChain more candidates).
                     if (best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
                         const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
                         if (interior || delta <= kDenseHop) chain >>= 2;
@@ -475,6 +433,8 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
                     best_dist = dist;
                     if (len >= nice) chain = 0;
                 } else if (len == best_len && delta <= kDenseHop) {
+                    // A candidate that ties with the best match on a dense chain means periodic data (a run): the
+                    // rest of the chain is more of the same.  Every tie takes a quarter off the remaining budget.
                     chain -= chain >> 2;
                 }
             } while (0);
@@ -482,10 +442,9 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
         }
     }
     if (best_len < c.min_len) return lit;
-    if (best_len == 3 && best_dist > kTooFar) return lit;
+    if (best_len == 3 && best_dist > kTooFar) return lit;   // deflate.ts:1381-1387
     return lit | (best_len << 15) | best_dist;
 }
-#endif  // ZS_LZ_STRAGGLER
 
 // ---- stage 4: resolve (wide) -----------------------------------------------------------------------
 // mj[].y layout: exit (9 bits) | is_match << 9 | popc(visited) << 10 (6 bits) | pair exit - 32 << 16
@@ -712,6 +671,8 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const unsigned wid = threadIdx.x >> 5, lane = zs_lane();
     LevelCfg cfg = c_levels[a.level];
+    const StopCfg stop = {a.stop_after, a.stop_active};
+    (void)stop;
 #ifdef ZS_LZ_PROF
     if (a.debug >> 8) cfg.chain = a.debug >> 8;
 #endif
@@ -856,7 +817,6 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                     if (qw + 32u > qd64 && qw < n) {
                         while (qw >= ce_w) { ++js; cs_w = ce_w; ce_w = S.bnd[js + 1]; }   // qw < n: terminates
                         uint32_t r = 0;
-#ifdef ZS_LZ_STRAGGLER
                         if constexpr (kMode == 1) {   // every lane of the batch takes part in the votes
                             const bool live = q >= rc.q_data && q < n;
                             uint32_t cs = cs_w, ce = ce_w;
@@ -864,17 +824,16 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-                            const uint32_t rr = search_position_sync(S, cfg, rc, q, cs, ce, live);
+                            const uint32_t rr = search_position_sync(S, cfg, stop, rc, q, cs, ce, live);
                             r = live ? rr : 0u;
                         } else
-#endif
                         if (q >= rc.q_data && q < n) {
                             uint32_t cs = cs_w, ce = ce_w;
                             if (q >= ce) {   // a boundary inside the batch
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-                            r = search_position<kMode>(S, cfg, rc, q, cs, ce);
+                            r = search_position<kMode == 1 ? 0 : kMode>(S, cfg, rc, q, cs, ce);
                         }
                         if (q < n) S.res[res_slot(q)] = r;
                     }
@@ -1002,6 +961,11 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
     a.blk_desc = p.d_blk_desc;
     a.seg_counter = p.d_seg_counter;
     a.debug = 0;
+    // straggler stop of the lazy levels (policy constants; the environment overrides exist for the A/B tools)
+    a.stop_after = 8;
+    a.stop_active = 8;
+    if (const char* e = getenv("ZS_LZ_STOP_AFTER")) a.stop_after = (unsigned)atoi(e);
+    if (const char* e = getenv("ZS_LZ_STOP_ACTIVE")) a.stop_active = (unsigned)atoi(e);
 #ifdef ZS_LZ_PROF
     if (getenv("ZS_LZ_DEBUG")) a.debug = atoi(getenv("ZS_LZ_DEBUG"));
 #endif

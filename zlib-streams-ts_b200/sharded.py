@@ -111,13 +111,14 @@ def bit_concat_host(parts) -> tuple[bytes, int]:
 
 
 def deflate_sharded(d_all_or_local: torch.Tensor, chunk_size: int, level: int, wrap: int, local_is_shard: bool = False,
-                    history: int = 0, group=None):
+                    history: int = 0, group=None, ctx=None, reuse=None):
     """Deflate this rank's contiguous chunk range of a stream and run the exchange step (GPU).
 
     If `local_is_shard` the tensor is already this rank's range (with `history` valid bytes before
     it in the same storage); otherwise it is the whole input, replicated, and the rank slices it.
     Returns (DeflateBatchDev, DeflateResult, StitchPlan).  The part starts at bit 0 of its own
     buffer; rank 0's part includes the wrapper header; the trailer comes from wrapper_trailer().
+    `reuse` = the DeflateBatchDev of an earlier call with the same shapes (no allocation).
     """
     from . import batch as B
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -131,11 +132,33 @@ def deflate_sharded(d_all_or_local: torch.Tensor, chunk_size: int, level: int, w
         b0, b1 = lo * chunk_size, min(hi * chunk_size, n)
         local, hist = d_all_or_local[b0:b1], min(b0, 32768)
     flags = part_flags(rank, world)
-    res = B.deflate_batch_dev(local, chunk_size, level, wrap, B.MODE_STITCHED, flags, history=hist)
+    res = B.deflate_batch_dev(local, chunk_size, level, wrap, B.MODE_STITCHED, flags, history=hist, ctx=ctx, reuse=reuse)
     rr = res.read_result()
     kind = None if wrap == capi.WRAP_RAW else (capi.KIND_ADLER32 if wrap == capi.WRAP_ZLIB else capi.KIND_CRC32)
     plan = exchange_meta(int(rr.total_out_bits), int(rr.check), local.numel(), kind, 0, device=local.device, group=group)
     return res, rr, plan
+
+
+def deflate_sharded_host(h_buf: torch.Tensor, history: int, chunk_size: int, level: int, wrap: int, h_out: torch.Tensor,
+                         device=None, group=None, ctx=None):
+    """The same step from HOST buffers (what a Node-API caller on each rank does): h_buf holds `history`
+    bytes of the stream followed by this rank's range; the part is deflated through zs_deflate_part (H2D,
+    kernels and D2H pipelined inside the call) into h_out, then the ranks exchange (bits, check, length).
+    Returns (DeflateResult, StitchPlan); the part's bytes are h_out[:result.total_out_bytes]."""
+    import ctypes as C
+
+    from . import batch as B
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ctx = ctx or B.default_context(device.index if device is not None else None)
+    n = h_buf.numel() - history
+    res = capi.DeflateResult()
+    rc = capi.load().zs_deflate_part(ctx.handle, C.c_void_p(h_buf.data_ptr() + history), n, history, chunk_size, level, wrap,
+                                     part_flags(rank, world), C.c_void_p(h_out.data_ptr()), h_out.numel(), None, C.byref(res))
+    ctx.check(rc, "zs_deflate_part")
+    kind = None if wrap == capi.WRAP_RAW else (capi.KIND_ADLER32 if wrap == capi.WRAP_ZLIB else capi.KIND_CRC32)
+    plan = exchange_meta(int(res.total_out_bits), int(res.check), n, kind, 0, device=device, group=group)
+    return res, plan
 
 
 def gather_stream(res, rr, plan: StitchPlan, wrap: int, dst: int = 0, group=None):
