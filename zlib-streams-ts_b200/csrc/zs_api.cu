@@ -15,7 +15,10 @@ enum {
     SCR_I_MISC = 13,
     SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
     SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23, SCR_I_RESUME = 24,
+    // 25..29: zs_inflate_par.cu
+    SCR_P_STATE = 30, SCR_I_STREAM = 31,
 };
+constexpr uint64_t kParMinInput = 128u << 10;   // shorter streams are decoded by one warp
 
 void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
     zs_scratch& s = ctx->scr[slot];
@@ -630,22 +633,52 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
     }
     // test hooks: force the thread-per-stream (1) or the warp-per-stream (-1) kernel
     a.force_tps = getenv("ZS_INFLATE_TPS") ? 1 : getenv("ZS_INFLATE_WARP") ? -1 : 0;
+    a.d_hdr_state = nullptr; a.d_resume = nullptr;
     uint32_t* d_adler = misc + 4 * (size_t)n;
     uint32_t* d_crc = misc + 5 * (size_t)n;
-    int rc = zs_launch_inflate(ctx, a);
+    int rc;
+    // One long stream whose sizes the caller knows on the host: cut it at its flush points and decode the
+    // segments in parallel (zs_inflate_par.cu); inflate_kernel then continues behind them -- the trailer
+    // and the final status, or whatever the parallel part had to leave.
+    const bool par = ctx->par.on && n == 1 && !d64 && ctx->par.in_len >= kParMinInput && ((ctx->par.in_off & 7u) == 0) &&
+                     !getenv("ZS_INFLATE_SERIAL");
+    ctx->par.on = false;
+    const uint64_t par_out_cap = ctx->par.out_cap;
+    if (par) {
+        uint64_t* d_ps = (uint64_t*)zs_scratch_get(ctx, SCR_P_STATE, 16 * 8);
+        if (!d_ps) return ZS_MEM_ERROR;
+        zs_inflate_args h = a;
+        h.d_hdr_state = d_ps;
+        h.d_block_mark = nullptr;
+        rc = zs_launch_inflate(ctx, h);
+        if (rc != ZS_OK) return rc;
+        rc = zs_launch_inflate_parallel(ctx, d_in + ctx->par.in_off, ctx->par.in_len, d_out + ctx->par.out_off, ctx->par.out_cap,
+                                        d_dict ? d_dict + ctx->par.dict_off : nullptr, d_dict ? ctx->par.dict_len : 0, d_ps, d_ps + 8);
+        if (rc != ZS_OK) return rc;
+        a.d_resume = d_ps + 8;
+    }
+    rc = zs_launch_inflate(ctx, a);
     if (rc != ZS_OK) return rc;
     ctx->d_last_detail = a.d_detail;
     ctx->last_detail_n = n;
     // checksum of what was produced (inf_leave / CHECK, inflate.ts:1012-1015,1079-1085)
     const bool want_adler = (wrap & 1) != 0;
     const bool want_crc = (wrap & 2) != 0 || (wrap == 0 && d_checks != nullptr);
-    if (want_adler) {
-        rc = zs_launch_checksum_segments(ctx, 0, d_out, d_out_off, d_out_len, n, d_adler);
+    if (par) {
+        // one long stream: its output is cut into pieces for the checksum too (a warp per stream would take
+        // 0.5 s per GiB)
+        if (want_adler) rc = zs_launch_checksum_stream(ctx, 0, d_out, d_out_off, d_out_len, par_out_cap, d_adler);
+        if (rc == ZS_OK && want_crc) rc = zs_launch_checksum_stream(ctx, 1, d_out, d_out_off, d_out_len, par_out_cap, d_crc);
         if (rc != ZS_OK) return rc;
-    }
-    if (want_crc) {
-        rc = zs_launch_checksum_segments(ctx, 1, d_out, d_out_off, d_out_len, n, d_crc);
-        if (rc != ZS_OK) return rc;
+    } else {
+        if (want_adler) {
+            rc = zs_launch_checksum_segments(ctx, 0, d_out, d_out_off, d_out_len, n, d_adler);
+            if (rc != ZS_OK) return rc;
+        }
+        if (want_crc) {
+            rc = zs_launch_checksum_segments(ctx, 1, d_out, d_out_off, d_out_len, n, d_crc);
+            if (rc != ZS_OK) return rc;
+        }
     }
     return zs_launch_inflate_verify(ctx, n, want_adler ? d_adler : nullptr, want_crc ? d_crc : nullptr, a.d_trailer,
                                     a.d_flags, d_out_len, d_checks, d_status, a.d_detail);
@@ -683,8 +716,15 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
     if (in_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_total, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ioff, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ooff, out_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n == 1) {
+        ctx->par.on = true;
+        ctx->par.in_off = in_off[0]; ctx->par.in_len = in_off[1] - in_off[0];
+        ctx->par.out_off = out_off[0]; ctx->par.out_cap = out_off[1] - out_off[0];
+        ctx->par.dict_off = d_rng ? dict_rng[0] : 0; ctx->par.dict_len = d_rng ? dict_rng[1] - dict_rng[0] : 0;
+    }
     int rc = zs_inflate_batch_dev(ctx, d_in, d_ioff, n, window_bits, d_out, d_ooff, d_olen, d_used, d_checks, d_status,
                                   d_dict, d_rng);
+    ctx->par.on = false;
     if (rc != ZS_OK) return rc;
     if (out_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, out_total, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_olen, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -697,6 +737,26 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
     }
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ZS_OK;
+}
+
+int zs_inflate_stream_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, int window_bits, uint8_t* d_out, uint64_t out_cap,
+                          uint64_t* d_out_len, uint64_t* d_in_used, uint32_t* d_check, int32_t* d_status, const uint8_t* d_dict,
+                          uint64_t dict_len) {
+    if (ctx) bind_device(ctx);
+    if (!ctx) return ZS_STREAM_ERROR;
+    if (!d_in || !d_out || !d_out_len || !d_status) return bad_arg(ctx, "inflate: null buffer");
+    uint64_t* d_o = (uint64_t*)zs_scratch_get(ctx, SCR_I_STREAM, 8 * 8);
+    if (!d_o) return ZS_MEM_ERROR;
+    const uint64_t h[6] = {0, in_len, 0, out_cap, 0, dict_len};
+    // (pageable source: the copy is staged before the call returns)
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_o, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->par.on = true;
+    ctx->par.in_off = 0; ctx->par.in_len = in_len; ctx->par.out_off = 0; ctx->par.out_cap = out_cap;
+    ctx->par.dict_off = 0; ctx->par.dict_len = d_dict ? dict_len : 0;
+    const int rc = zs_inflate_batch_dev(ctx, d_in, d_o, 1, window_bits, d_out, d_o + 2, d_out_len, d_in_used, d_check, d_status,
+                                        d_dict && dict_len ? d_dict : nullptr, d_dict && dict_len ? d_o + 4 : nullptr);
+    ctx->par.on = false;
+    return rc;
 }
 
 int zs_inflate_last_details(zs_ctx* ctx, int32_t* detail, uint32_t n) {

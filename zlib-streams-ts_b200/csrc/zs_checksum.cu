@@ -232,6 +232,15 @@ __global__ void make_offsets_kernel(uint64_t* off, uint64_t len, uint64_t piece,
     }
 }
 
+// the same for a length that only the device knows (the output of one inflated stream), at most max_len
+__global__ void make_offsets_dev_kernel(uint64_t* off, const uint64_t* base, const uint64_t* len, uint64_t piece, uint32_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) {
+        uint64_t v = i * piece;
+        off[i] = *base + (v < *len ? v : *len);
+    }
+}
+
 bool g_tables_ready[64] = {false};
 
 int ensure_tables(zs_ctx* ctx) {
@@ -303,6 +312,26 @@ int zs_launch_checksum_fold(zs_ctx* ctx, int kind, const uint32_t* d_part, const
 }
 
 // Whole-buffer checksum: cut into 64 KiB pieces (one warp each), then fold.
+// Checksum of d_buf[*d_base .. *d_base + *d_len), *d_len <= max_len: 64 KiB pieces in parallel, then the fold.
+int zs_launch_checksum_stream(zs_ctx* ctx, int kind, const uint8_t* d_buf, const uint64_t* d_base, const uint64_t* d_len,
+                              uint64_t max_len, uint32_t* d_result) {
+    const uint64_t piece = 65536;
+    uint64_t n64 = (max_len + piece - 1) / piece;
+    if (n64 == 0) n64 = 1;
+    if (n64 > 0xfffffff0ull) {
+        snprintf(ctx->err, sizeof(ctx->err), "checksum: buffer too large");
+        return ZS_STREAM_ERROR;
+    }
+    const uint32_t n = (uint32_t)n64;
+    uint64_t* d_off = (uint64_t*)zs_scratch_get(ctx, 0, (size_t)(n + 1) * sizeof(uint64_t));
+    uint32_t* d_part = (uint32_t*)zs_scratch_get(ctx, 1, (size_t)n * sizeof(uint32_t));
+    if (!d_off || !d_part) return ZS_MEM_ERROR;
+    ZS_KERNEL(ctx, "make_offsets_dev_kernel", make_offsets_dev_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_off, d_base, d_len, piece, n));
+    int rc = zs_launch_checksum_segments(ctx, kind, d_buf, d_off, nullptr, n, d_part);
+    if (rc != ZS_OK) return rc;
+    return zs_launch_checksum_fold(ctx, kind, d_part, d_off, n, kind ? 0u : 1u, d_result);
+}
+
 int zs_launch_checksum_whole(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, uint32_t init,
                              uint32_t* d_result) {
     const uint64_t piece = 65536;

@@ -35,6 +35,8 @@ struct zs_ctx {
     uint64_t inflate_start_bit = 0;
     uint64_t inflate_mark[2] = {0, 0};
     uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
+    // one-stream inflate with sizes known on the host: lets zs_inflate_batch_dev use the segment-parallel decoder
+    struct { bool on = false; uint64_t in_off = 0, in_len = 0, out_off = 0, out_cap = 0, dict_off = 0, dict_len = 0; } par;
     cudaEvent_t ev[64] = {nullptr};
     // profiling (zs_ctx_profile)
     bool prof_on = false;
@@ -140,6 +142,8 @@ int zs_launch_checksum_segments(zs_ctx* ctx, int kind, const uint8_t* d_buf, con
                                 const uint64_t* d_len, uint32_t n, uint32_t* d_out);
 int zs_launch_checksum_whole(zs_ctx* ctx, int kind, const uint8_t* d_buf, uint64_t len, uint32_t init,
                              uint32_t* d_result);
+int zs_launch_checksum_stream(zs_ctx* ctx, int kind, const uint8_t* d_buf, const uint64_t* d_base, const uint64_t* d_len,
+                              uint64_t max_len, uint32_t* d_result);
 int zs_launch_checksum_fold(zs_ctx* ctx, int kind, const uint32_t* d_part, const uint64_t* d_off, uint32_t n,
                             uint32_t init, uint32_t* d_result);
 uint32_t zs_host_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2);
@@ -168,8 +172,17 @@ struct zs_inflate_args {
     // stream, bytes produced before it) -- the point a later call can resume from
     const uint64_t* d_start_bit;
     uint64_t* d_block_mark;
+    // segment-parallel decode of one stream (zs_inflate_par.cu):
+    //  d_hdr_state != nullptr: parse the wrapper header only and report [5] = bit position of the first block
+    //  (~0 if the header does not parse), [6] = trailer kind (1 zlib, 2 gzip)
+    //  d_resume != nullptr: [4n] per stream = (start bit or ~0 for "from the beginning", bytes already
+    //  produced, trailer kind | 4 = all blocks are decoded, -): continue behind what the parallel part did
+    uint64_t* d_hdr_state;
+    const uint64_t* d_resume;
 };
 int zs_launch_inflate(zs_ctx* ctx, const zs_inflate_args& a);
+int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, uint8_t* d_out, uint64_t out_cap,
+                               const uint8_t* d_hist, uint64_t hist_len, uint64_t* d_state, uint64_t* d_resume);
 int zs_launch_inflate_verify(zs_ctx* ctx, uint32_t n, const uint32_t* d_adler, const uint32_t* d_crc,
                              const uint32_t* d_trailer, const uint32_t* d_flags, const uint64_t* d_out_len,
                              uint32_t* d_checks, int32_t* d_status, int32_t* d_detail);

@@ -6,277 +6,22 @@
 // output bytes, same total_in / total_out, same return code and message.
 //
 // Layout: every warp owns a private decode-table arena in shared memory (852 length + 594 distance
-// entries of 32 bits, the reference's ENOUGH bounds).  The dynamic-block header is parsed and the
-// tables are built by lane 0 (serial by nature: run-length coded code lengths, canonical code
-// assignment); symbol decoding is warp-uniform (every lane tracks the same bit buffer, shared
+// entries of 32 bits, the reference's ENOUGH bounds).  The run-length coded code lengths of a dynamic
+// block header are read by lane 0 (a serial chain); the decode tables are built by the whole warp from the
+// canonical codes (zs_inflate_common.cuh); symbol decoding is warp-uniform (every lane tracks the same bit buffer, shared
 // memory table reads are broadcasts) so that back-reference copies and stored-block copies are
 // executed by all 32 lanes without any hand-off.  Output goes straight to HBM; the history window
 // of the reference (32/64 KiB ring) is the already written output itself plus the optional preset
 // dictionary.
 #include <cstdio>
 
-#include "zs_common.cuh"
+#include "zs_inflate_common.cuh"
 
 namespace {
 
+using namespace zsinf;
+
 constexpr int kWarps = 4;
-constexpr int kEnoughLens = 852;
-constexpr int kEnoughDists = 592;
-constexpr int kEnoughDists9 = 594;
-
-// detail codes -> reference messages (see zs_inflate_message)
-enum {
-    D_NONE = 0, D_HEADER_CHECK, D_METHOD, D_WINDOW, D_HDR_FLAGS, D_HDR_CRC, D_BLOCK_TYPE, D_STORED_LEN,
-    D_TOO_MANY, D_TOO_MANY_9, D_CODE_LENGTHS, D_BIT_REPEAT, D_NO_EOB, D_LITLEN_SET, D_DIST_SET, D_LITLEN_CODE,
-    D_DIST_CODE, D_TOO_FAR, D_DATA_CHECK, D_LENGTH_CHECK
-};
-
-#define E_OP(e) ((e) >> 24)
-#define E_BITS(e) (((e) >> 16) & 0xffu)
-#define E_VAL(e) ((e) & 0xffffu)
-#define E_PACK(op, bits, val) (((uint32_t)(op) << 24) | ((uint32_t)(bits) << 16) | (uint32_t)(val))
-
-struct WarpArena {
-    uint32_t codes[kEnoughLens + kEnoughDists9];
-    uint16_t lens[320];
-    uint16_t work[288];
-};
-
-struct FixedTables {
-    uint32_t len[512];
-    uint32_t dist[32];
-};
-
-// ---- base / extra tables for length and distance symbols (inflate/constants.ts:8-45) -------------
-__device__ __forceinline__ void len_sym(unsigned idx, bool d64, unsigned& base, unsigned& op) {
-    // idx = symbol - 257
-    if (idx < 28) {
-        unsigned eb = idx < 8 ? 0u : (idx - 4u) >> 2;
-        base = 3u + (idx < 8 ? idx : ((4u + (idx & 3u)) << eb));
-        op = (d64 ? 128u : 16u) + eb;
-    } else if (idx == 28) {
-        base = d64 ? 3u : 258u;
-        op = d64 ? 144u : 16u;
-    } else {
-        base = 0;
-        op = 64u;  // invalid code marker (the reference stores 73/200 resp. 72/78: bit 64 set)
-    }
-}
-__device__ __forceinline__ void dist_sym(unsigned idx, bool d64, unsigned& base, unsigned& op) {
-    if (idx < 30) {
-        unsigned eb = idx < 4 ? 0u : (idx - 2u) >> 1;
-        base = 1u + (idx < 4 ? idx : ((2u + (idx & 1u)) << eb));
-        op = (d64 ? 128u : 16u) + eb;
-    } else if (d64) {
-        base = idx == 30 ? 32769u : 49153u;
-        op = 142u;
-    } else {
-        base = 0;
-        op = 64u;
-    }
-}
-
-__device__ __forceinline__ uint32_t table_entry(unsigned sym, unsigned nbits, int type, bool d64) {
-    if (type == 0) return E_PACK(0, nbits, sym);
-    if (type == 1) {
-        if (sym < 256) return E_PACK(0, nbits, sym);
-        if (sym == 256) return E_PACK(96, nbits, 0);
-        unsigned base, op;
-        len_sym(sym - 257, d64, base, op);
-        return E_PACK(op, nbits, base);
-    }
-    unsigned base, op;
-    dist_sym(sym, d64, base, op);
-    return E_PACK(op, nbits, base);
-}
-
-// inflate_table (inftrees.ts:62-277), executed by a single lane.  Returns 0 ok, -1 invalid set,
-// 1 not enough table space.  *index advances by the space used, *bits receives the root bits.
-__device__ int build_table(int type, const uint16_t* lens, unsigned codes, uint32_t* table, unsigned* bits,
-                           uint16_t* work, unsigned* index, bool d64) {
-    unsigned len, sym, mn, mx, root, curr, drop, used, huff, incr, fill, mask, next;
-    int left, low;
-    uint16_t count[16], offs[16];
-    const unsigned enough_d = d64 ? kEnoughDists9 : kEnoughDists;
-
-    for (len = 0; len <= 15; len++) count[len] = 0;
-    for (sym = 0; sym < codes; sym++) count[lens[sym]]++;
-    root = *bits;
-    for (mx = 15; mx >= 1; mx--)
-        if (count[mx] != 0) break;
-    if (root > mx) root = mx;
-    if (mx == 0) {
-        if (!d64) {  // inftrees.ts:113-123
-            table[*index] = E_PACK(64, 1, 0);
-            table[*index + 1] = E_PACK(64, 1, 0);
-            *index += 2;
-            *bits = 1;
-            return 0;
-        }
-        return -1;
-    }
-    for (mn = 1; mn < mx; mn++)
-        if (count[mn] != 0) break;
-    if (root < mn) root = mn;
-    left = 1;
-    for (len = 1; len <= 15; len++) {
-        left <<= 1;
-        left -= count[len];
-        if (left < 0) return -1;
-    }
-    if (left > 0 && (type == 0 || mx != 1)) return -1;
-
-    offs[1] = 0;
-    for (len = 1; len < 15; len++) offs[len + 1] = offs[len] + count[len];
-    for (sym = 0; sym < codes; sym++)
-        if (lens[sym] != 0) work[offs[lens[sym]]++] = (uint16_t)sym;
-
-    huff = 0; sym = 0; len = mn; next = *index; curr = root; drop = 0; low = -1;
-    used = 1u << root;
-    mask = used - 1;
-#define TOO_BIG() ((type == 1 && (d64 ? used >= (unsigned)kEnoughLens : used > (unsigned)kEnoughLens)) || \
-                   (type == 2 && (d64 ? used >= enough_d : used > enough_d)))
-    if (TOO_BIG()) return 1;
-    for (;;) {
-        uint32_t here = table_entry(work[sym], len - drop, type, d64);
-        incr = 1u << (len - drop);
-        fill = 1u << curr;
-        do {
-            fill -= incr;
-            table[next + (huff >> drop) + fill] = here;
-        } while (fill != 0);
-        incr = 1u << (len - 1);
-        while (huff & incr) incr >>= 1;
-        if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
-        sym++;
-        if (--count[len] == 0) {
-            if (len == mx) break;
-            len = lens[work[sym]];
-        }
-        if (len > root && (int)(huff & mask) != low) {
-            if (drop == 0) drop = root;
-            next += 1u << curr;
-            curr = len - drop;
-            left = 1 << curr;
-            while (curr + drop < mx) {
-                left -= count[curr + drop];
-                if (left <= 0) break;
-                curr++;
-                left <<= 1;
-            }
-            used += 1u << curr;
-            if (TOO_BIG()) return 1;
-            low = (int)(huff & mask);
-            table[*index + (unsigned)low] = E_PACK(curr, root, next - *index);
-        }
-    }
-    if (huff != 0) {  // incomplete code (only the single 1-bit code case gets here)
-        uint32_t here = E_PACK(64, len - drop, 0);
-        while (huff != 0) {
-            if (drop != 0 && (int)(huff & mask) != low) {
-                drop = 0; len = root; next = *index; curr = root;
-                here = E_PACK(64, len, 0);
-            }
-            table[next + (huff >> drop)] = here;
-            incr = 1u << (len - 1);
-            while (huff & incr) incr >>= 1;
-            if (incr != 0) { huff &= incr - 1; huff += incr; } else huff = 0;
-        }
-    }
-    *index += used;
-    *bits = root;
-    return 0;
-#undef TOO_BIG
-}
-
-// ---- bit reader over a global buffer ------------------------------------------------------------
-struct BitReader {
-    const uint8_t* base;
-    uint64_t pos, end, safe_end;
-    uint64_t hold;
-    unsigned bits;
-    __device__ __forceinline__ void refill() {
-        if (bits <= 32) {
-            if (end - pos >= 4) {
-                hold |= (uint64_t)zs_ld32(base, pos, safe_end) << bits;
-                bits += 32;
-                pos += 4;
-            } else {
-                while (pos < end && bits <= 56) {
-                    hold |= (uint64_t)__ldg(base + pos) << bits;
-                    bits += 8;
-                    pos++;
-                }
-            }
-        }
-    }
-    __device__ __forceinline__ bool need(unsigned n) {
-        if (bits < n) refill();
-        return bits >= n;
-    }
-    __device__ __forceinline__ unsigned peek(unsigned n) const { return (unsigned)hold & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(unsigned n) { hold >>= n; bits -= n; }
-    __device__ __forceinline__ unsigned take(unsigned n) { unsigned v = peek(n); drop(n); return v; }
-    __device__ __forceinline__ void align_byte() { drop(bits & 7u); }
-    // rewind so that `pos` is the next unread byte and the bit buffer is empty (call when byte aligned)
-    __device__ __forceinline__ void unload() { pos -= bits >> 3; hold = 0; bits = 0; }
-};
-
-__constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-
-// TABLE / LENLENS / CODELENS of inflate() (inflate.ts:673-835); lane 0 only.
-// Returns 0 ok, >0 detail code (data error), -1 truncated input.
-__device__ int read_dynamic_header(BitReader& br, WarpArena& A, bool d64, unsigned& lenbits, unsigned& distbits,
-                                   unsigned& dist_at) {
-    if (!br.need(14)) return -1;
-    unsigned nlen = br.take(5) + 257, ndist = br.take(5) + 1, ncode = br.take(4) + 4;
-    if (nlen > 286 || (!d64 && ndist > 30)) return d64 ? D_TOO_MANY_9 : D_TOO_MANY;
-    unsigned have = 0;
-    while (have < ncode) {
-        if (!br.need(3)) return -1;
-        A.lens[c_bl_order[have++]] = (uint16_t)br.take(3);
-    }
-    while (have < 19) A.lens[c_bl_order[have++]] = 0;
-    unsigned idx = 0, cbits = 7;
-    if (build_table(0, A.lens, 19, A.codes, &cbits, A.work, &idx, d64)) return D_CODE_LENGTHS;
-    have = 0;
-    const unsigned total = nlen + ndist;
-    while (have < total) {
-        br.refill();
-        uint32_t here = A.codes[br.peek(cbits)];
-        if (E_BITS(here) > br.bits) return -1;
-        if (E_OP(here) & 64) return D_CODE_LENGTHS;  // unreachable: the code-length code is complete
-        unsigned v = E_VAL(here);
-        if (v < 16) {
-            br.drop(E_BITS(here));
-            A.lens[have++] = (uint16_t)v;
-        } else {
-            unsigned xb = v == 16 ? 2u : v == 17 ? 3u : 7u;
-            if (E_BITS(here) + xb > br.bits) return -1;
-            br.drop(E_BITS(here));
-            unsigned rep_len = 0, rep;
-            if (v == 16) {
-                if (have == 0) return D_BIT_REPEAT;
-                rep_len = A.lens[have - 1];
-                rep = 3 + br.take(2);
-            } else if (v == 17) {
-                rep = 3 + br.take(3);
-            } else {
-                rep = 11 + br.take(7);
-            }
-            if (have + rep > total) return D_BIT_REPEAT;
-            while (rep--) A.lens[have++] = (uint16_t)rep_len;
-        }
-    }
-    if (A.lens[256] == 0) return D_NO_EOB;
-    idx = 0;
-    lenbits = 9;
-    if (build_table(1, A.lens, nlen, A.codes, &lenbits, A.work, &idx, d64)) return D_LITLEN_SET;
-    dist_at = idx;
-    distbits = 6;
-    if (build_table(2, A.lens + nlen, ndist, A.codes, &distbits, A.work, &idx, d64)) return D_DIST_SET;
-    return 0;
-}
 
 __device__ __forceinline__ uint32_t crc_bitwise(uint32_t crc, unsigned byte) {
     crc ^= byte;
@@ -292,19 +37,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
     const bool d64 = a.deflate64 != 0;
 
     // fixedtables (inflate.ts:218-280): built once per CTA
-    if (wid == 0 && lane == 0) {
-        WarpArena& A = s_arena[0];
-        unsigned sym = 0;
-        while (sym < 144) A.lens[sym++] = 8;
-        while (sym < 256) A.lens[sym++] = 9;
-        while (sym < 280) A.lens[sym++] = 7;
-        while (sym < 288) A.lens[sym++] = 8;
-        unsigned bits = 9, idx = 0;
-        build_table(1, A.lens, 288, s_fixed.len, &bits, A.work, &idx, d64);
-        for (sym = 0; sym < 32; sym++) A.lens[sym] = 5;
-        bits = 5; idx = 0;
-        build_table(2, A.lens, 32, s_fixed.dist, &bits, A.work, &idx, d64);
-    }
+    if (wid == 0) build_fixed_tables(s_fixed, s_arena[0], d64);
     __syncthreads();
 
     WarpArena& A = s_arena[wid];
@@ -335,9 +68,18 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
         uint32_t t_check = 0, t_isize = 0;
 
         uint64_t mark_bit = 0, mark_out = 0;   // where the last block that was begun starts
-        if (a.d_start_bit) {
-            // continuation of a stream whose wrapper and earlier blocks a previous call consumed
-            const uint64_t sb = a.d_start_bit[sidx];
+        bool skip_header = false, blocks_done = false;
+        uint64_t sb = ~0ull;
+        if (a.d_start_bit) sb = a.d_start_bit[sidx];   // continuation of a stream whose wrapper and earlier blocks a previous call consumed
+        if (a.d_resume && a.d_resume[4 * sidx] != ~0ull) {
+            // behind the segments the parallel decoder produced (zs_inflate_par.cu)
+            sb = a.d_resume[4 * sidx];
+            op = a.d_resume[4 * sidx + 1];
+            tflags = (unsigned)(a.d_resume[4 * sidx + 2] & 3u);
+            blocks_done = (a.d_resume[4 * sidx + 2] & 4u) != 0;
+        }
+        if (sb != ~0ull) {
+            skip_header = true;
             br.pos = in_start + (sb >> 3);
             if (br.pos > br.end) br.pos = br.end;
             if (sb & 7u) {
@@ -346,7 +88,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             }
         }
         // ---- wrapper header: HEAD..HCRC / DICTID of inflate() (inflate.ts:377-593) ----
-        if (a.wrap && !a.d_start_bit) {
+        if (a.wrap && !skip_header) {
             if (!br.need(16)) {
                 status = ZS_BUF_ERROR;
             } else {
@@ -412,8 +154,17 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             }
         }
 
+        if (a.d_hdr_state) {
+            // header only: where the blocks start, for the segment-parallel decoder
+            if (lane == 0) {
+                a.d_hdr_state[5] = status == ZS_OK ? (br.pos - in_start) * 8 - br.bits : ~0ull;
+                a.d_hdr_state[6] = tflags;
+            }
+            continue;
+        }
+
         // ---- blocks ----
-        bool last = false;
+        bool last = blocks_done;
         while (status == ZS_OK && !last) {
             mark_bit = (br.pos - in_start) * 8 - br.bits;
             mark_out = op;
@@ -442,18 +193,9 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
             } else if (type == 1) {
                 lcode = s_fixed.len; dcode = s_fixed.dist; lenbits = 9; distbits = 5;
             } else if (type == 2) {
-                int rc = 0;
                 unsigned dist_at = 0;
                 lenbits = distbits = 0;
-                if (lane == 0) rc = read_dynamic_header(br, A, d64, lenbits, distbits, dist_at);
-                __syncwarp();
-                rc = __shfl_sync(ZS_FULL_MASK, rc, 0);
-                br.pos = __shfl_sync(ZS_FULL_MASK, br.pos, 0);
-                br.hold = __shfl_sync(ZS_FULL_MASK, br.hold, 0);
-                br.bits = __shfl_sync(ZS_FULL_MASK, br.bits, 0);
-                lenbits = __shfl_sync(ZS_FULL_MASK, lenbits, 0);
-                distbits = __shfl_sync(ZS_FULL_MASK, distbits, 0);
-                dist_at = __shfl_sync(ZS_FULL_MASK, dist_at, 0);
+                const int rc = read_dynamic_header(br, A, d64, lenbits, distbits, dist_at);
                 if (rc < 0) { status = ZS_BUF_ERROR; break; }
                 if (rc > 0) { status = ZS_DATA_ERROR; detail = rc; break; }
                 lcode = A.codes; dcode = A.codes + dist_at;

@@ -1,0 +1,438 @@
+// zs_inflate_par.cu -- segment-parallel inflate of ONE deflate stream at its flush points.
+//
+// The reference decodes a stream serially (inflate(), src/mod/inflate/inflate.ts:332; inflate_fast,
+// inffast.ts:5); a stream written with Z_SYNC_FLUSH / Z_FULL_FLUSH points (deflate.ts:936-961 -- what this
+// engine's own STITCHED + ZS_FLAG_SYNC deflate, pigz and every flushing writer produce) can be cut at the
+// byte-aligned block boundaries those points leave behind.  Back-references still cross the cuts (only
+// Z_FULL_FLUSH forgets the window), so a segment is decoded against an UNKNOWN 32 KiB window and its
+// output is symbolic until the window is known.  Kernels, all on the context's stream, no host round trip:
+//
+//   par_scan_kernel     candidate cuts: the first byte position in every tile of the input that follows the
+//                       marker 00 00 FF FF (the empty stored block of a flush point).  A candidate is only a
+//                       guess: the pattern also occurs inside stored data and by chance.
+//   par_count_kernel    a warp per candidate decodes from it WITHOUT output (lengths only) until it stands,
+//                       at a block boundary, exactly on a later candidate (or ends the stream, or fails, or
+//                       runs out of input).  A wrong guess decodes garbage and dies or is never reached.
+//   par_plan_kernel     follows the chain from the true start of the stream: segment -> the candidate it
+//                       landed on -> ...; exclusive scan of the output lengths = where every segment writes.
+//   par_decode_kernel   a warp per planned segment decodes again, now writing 16-bit symbols: a byte, or
+//                       256 + w for "byte w of the 32 KiB window before this segment" (copied around like
+//                       any other symbol by later matches).
+//   par_window_kernel   one CTA walks the segments in order: the window after segment k is the resolved tail
+//                       of its symbols (the only serial step, 32 Ki symbols per segment).
+//   par_resolve_kernel  symbols -> bytes, every segment with its own window, all in parallel.
+//   par_finish_kernel   where the serial decoder (inflate_kernel, zs_inflate.cu) takes over: behind the last
+//                       planned segment -- for the trailer and the final status only when the chain reached
+//                       the end of the stream, or for whatever the parallel part could not prove (an error,
+//                       truncated input, output space running out, a distance beyond the start of the
+//                       stream), so that status, message and output prefix stay the reference's.
+#include <cstdio>
+
+#include "zs_inflate_common.cuh"
+
+namespace {
+
+using namespace zsinf;
+
+constexpr int kWarps = 4;
+constexpr unsigned kWin = 32768;            // window of a deflate stream (the parallel path is not used for deflate64)
+constexpr unsigned kMaxPassed = 48;         // candidates a count pass may run over before it gives up
+constexpr uint64_t kMaxTiles = 64;          // ... and tiles of input it may consume
+constexpr uint32_t kEndOfInput = 0xffffffffu;   // next_slot of a segment that ends exactly where the input ends
+
+enum { SEG_LANDED = 0, SEG_FINAL = 1, SEG_STOPPED = 2 };   // STOPPED: error, truncated input, gave up
+
+struct SegInfo {
+    uint64_t end_bit;     // LANDED: bit position of the candidate reached; FINAL: first bit after the last block
+    uint64_t out_len;
+    uint32_t status;
+    uint32_t next_slot;   // LANDED: slot of the candidate reached
+};
+
+struct ParArgs {
+    const uint8_t* in;
+    uint64_t in_len;
+    uint64_t tile;            // bytes per candidate tile
+    uint32_t n_slots;         // 1 + number of tiles: slot 0 is the start of the stream
+    uint64_t* cand;           // [n_slots] bit position of every candidate (~0 = none)
+    SegInfo* seg;             // [n_slots]
+    // plan
+    uint32_t* plan_slot;      // [n_slots]
+    uint64_t* plan_off;       // [n_slots + 1] output offset of every planned segment
+    uint32_t* plan_err;       // [n_slots] set by the decode pass: the segment needs the serial decoder
+    uint64_t* state;          // [8]: 0 n_planned, 1 total_out, 2 resume bit, 3 resume out, 4 blocks done, 5 body bit (in), 6 tflags (in)
+    uint64_t out_cap;
+    uint64_t hist_len;        // bytes of preset dictionary / earlier output before the stream's first byte
+    const uint8_t* hist;      // the last hist_len (<= 32768) bytes before the stream
+    uint16_t* sym;            // [out_cap] symbols
+    uint8_t* windows;         // [n_slots + 1][32768]
+    uint8_t* out;
+    uint64_t* resume;         // [4] record for inflate_kernel: start bit, start out, flags, -
+};
+
+__global__ void par_scan_kernel(ParArgs a) {
+    // one warp per tile: the first marker whose following byte position lies in the tile
+    const unsigned lane = zs_lane();
+    const uint64_t t = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t + 1 >= a.n_slots) return;
+    const uint64_t lo = t * a.tile, hi = lo + a.tile < a.in_len ? lo + a.tile : a.in_len;
+    const uint64_t body = a.state[5] == ~0ull ? ~0ull : (a.state[5] + 7) >> 3;
+    uint64_t found = ~0ull;
+    for (uint64_t p0 = lo; p0 < hi && found == ~0ull; p0 += 32) {
+        const uint64_t p = p0 + lane;   // candidate start: bytes p-4 .. p-1 are the marker
+        bool hit = false;
+        if (p < hi && p >= 4 && p - 4 >= body && body != ~0ull)
+            hit = a.in[p - 4] == 0 && a.in[p - 3] == 0 && a.in[p - 2] == 0xff && a.in[p - 1] == 0xff;
+        const unsigned m = __ballot_sync(ZS_FULL_MASK, hit);
+        if (m) found = p0 + (unsigned)(__ffs((int)m) - 1);
+    }
+    if (lane == 0) a.cand[t + 1] = found == ~0ull ? ~0ull : found * 8;
+    if (t == 0 && lane == 0) a.cand[0] = a.state[5];
+}
+
+// One segment, decoded by a warp from bit `start_bit`.  kWrite = false: lengths only (count pass), stops on a
+// later candidate; true: symbols to a.sym + out_base, stops at end_bit.
+template <bool kWrite>
+__device__ __forceinline__ void decode_segment(const ParArgs& a, WarpArena& A, const FixedTables& F, uint32_t slot, uint64_t start_bit,
+                                               uint64_t stop_bit, uint64_t out_base, uint64_t avail_hist, SegInfo* info, uint32_t* err) {
+    const unsigned lane = zs_lane();
+    BitReader br;
+    br.base = a.in;
+    br.pos = start_bit >> 3;
+    br.end = a.in_len;
+    br.safe_end = (a.in_len + 7) & ~7ull;
+    br.hold = 0;
+    br.bits = 0;
+    bool bad = false;
+    if (start_bit & 7u) {
+        if (!br.need(8)) bad = true;
+        else br.drop((unsigned)(start_bit & 7u));
+    }
+    uint64_t op = 0;
+    uint16_t* sym = kWrite ? a.sym + out_base : nullptr;
+    unsigned passed = 0;
+    uint64_t t_seen = (start_bit >> 3) / a.tile + 1;   // candidate slots up to here have been looked at
+    uint32_t status = SEG_STOPPED;
+    uint64_t end_bit = 0;
+    uint32_t next_slot = 0;
+    bool last = false;
+    while (!bad) {
+        // ---- a block boundary ----
+        const uint64_t here_bit = br.pos * 8 - br.bits;
+        if (kWrite) {
+            if (here_bit >= stop_bit) { status = SEG_LANDED; break; }
+        } else if (here_bit > start_bit) {
+            if (last) { status = SEG_FINAL; end_bit = here_bit; break; }
+            const uint64_t byte = here_bit >> 3;
+            if ((here_bit & 7u) == 0) {
+                if (byte == a.in_len) { status = SEG_LANDED; end_bit = here_bit; next_slot = kEndOfInput; break; }
+                const uint64_t t = byte / a.tile + 1;
+                if (t < a.n_slots && a.cand[t] == here_bit) { status = SEG_LANDED; end_bit = here_bit; next_slot = (uint32_t)t; break; }
+            }
+            // A wrong guess decodes garbage until it fails; bound what it may cost: candidates run over
+            // without standing on one, and input consumed.  (A true segment that long is left to the
+            // serial decoder, together with what follows it.)
+            for (uint64_t t = byte / a.tile + 1; t_seen < t && t_seen + 1 < a.n_slots; ) {
+                ++t_seen;
+                const uint64_t c = a.cand[t_seen];
+                if (c != ~0ull && c < here_bit) ++passed;
+            }
+            if (passed > kMaxPassed || byte - (start_bit >> 3) > kMaxTiles * a.tile) break;
+        }
+        if (kWrite && last) { status = SEG_FINAL; break; }
+        if (!br.need(3)) break;
+        last = br.take(1) != 0;
+        const unsigned type = br.take(2);
+        const uint32_t* lcode;
+        const uint32_t* dcode;
+        unsigned lenbits, distbits;
+        if (type == 0) {
+            br.align_byte();
+            if (!br.need(32)) break;
+            const unsigned w = (unsigned)br.hold;
+            if ((w & 0xffffu) != ((w >> 16) ^ 0xffffu)) break;
+            br.drop(32);
+            br.unload();
+            const uint64_t n = w & 0xffffu;
+            if (n > br.end - br.pos) break;
+            if (kWrite)
+                for (uint64_t j = lane; j < n; j += 32) sym[op + j] = a.in[br.pos + j];
+            br.pos += n;
+            op += n;
+            if (!kWrite && op > a.out_cap) break;
+            continue;
+        } else if (type == 1) {
+            lcode = F.len; dcode = F.dist; lenbits = 9; distbits = 5;
+        } else if (type == 2) {
+            unsigned dist_at = 0;
+            lenbits = distbits = 0;
+            if (read_dynamic_header(br, A, false, lenbits, distbits, dist_at) != 0) break;
+            lcode = A.codes; dcode = A.codes + dist_at;
+        } else {
+            break;
+        }
+        const unsigned lmask = (1u << lenbits) - 1u, dmask = (1u << distbits) - 1u;
+        bool block_ok = false;
+        for (;;) {
+            br.refill();
+            uint32_t here = lcode[(unsigned)br.hold & lmask];
+            unsigned used = E_BITS(here);
+            if (E_OP(here) && (E_OP(here) & 0xf0u) == 0) {
+                const uint32_t first = here;
+                here = lcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                used = E_BITS(first) + E_BITS(here);
+            }
+            if (used > br.bits) break;
+            const unsigned lop = E_OP(here);
+            if (lop == 0) {
+                br.drop(used);
+                if (kWrite && lane == 0) sym[op] = (uint16_t)E_VAL(here);
+                op++;
+                continue;
+            }
+            if (lop & 32) { br.drop(used); block_ok = true; break; }
+            if (lop & 64) break;
+            unsigned xb = lop & 15u;
+            if (used + xb > br.bits) break;
+            br.drop(used);
+            const unsigned len = E_VAL(here) + br.take(xb);
+            br.refill();
+            here = dcode[(unsigned)br.hold & dmask];
+            used = E_BITS(here);
+            if ((E_OP(here) & 0xf0u) == 0) {
+                const uint32_t first = here;
+                here = dcode[E_VAL(first) + (((unsigned)br.hold >> E_BITS(first)) & ((1u << E_OP(first)) - 1u))];
+                used = E_BITS(first) + E_BITS(here);
+            }
+            if (used > br.bits) break;
+            if (E_OP(here) & 64) break;
+            xb = E_OP(here) & 15u;
+            if (used + xb > br.bits) break;
+            br.drop(used);
+            const uint64_t dist = E_VAL(here) + br.take(xb);
+            if (kWrite) {
+                // a distance that reaches before the start of the stream (and its dictionary) is the
+                // reference's "invalid distance too far back": left to the serial decoder
+                if (dist > op + avail_hist) { *err = 1u; break; }
+                __syncwarp();
+                const int64_t s0 = (int64_t)op - (int64_t)dist;
+                for (unsigned j = lane; j < len; j += 32) {
+                    const int64_t si = s0 + (int64_t)(dist >= len ? j : j % dist);
+                    sym[op + j] = si >= 0 ? sym[si] : (uint16_t)(256 + kWin + si);
+                }
+                __syncwarp();
+            }
+            op += len;
+            if (!kWrite && op > a.out_cap) break;
+        }
+        if (!block_ok) break;
+    }
+    if (!kWrite && lane == 0) {
+        SegInfo r;
+        r.end_bit = end_bit; r.out_len = op; r.status = status; r.next_slot = next_slot;
+        *info = r;
+    }
+    if (kWrite && status == SEG_STOPPED) *err = 1u;   // the count pass got through: cannot happen, but never trust it
+    (void)slot;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) par_count_kernel(ParArgs a) {
+    __shared__ WarpArena s_arena[kWarps];
+    __shared__ FixedTables s_fixed;
+    const unsigned wid = threadIdx.x >> 5;
+    if (wid == 0) build_fixed_tables(s_fixed, s_arena[0], false);
+    __syncthreads();
+    for (uint64_t slot = (uint64_t)blockIdx.x * kWarps + wid; slot < a.n_slots; slot += (uint64_t)gridDim.x * kWarps) {
+        const uint64_t start = a.cand[slot];
+        if (start == ~0ull) {
+            if (zs_lane() == 0) { SegInfo r; r.end_bit = 0; r.out_len = 0; r.status = SEG_STOPPED; r.next_slot = 0; a.seg[slot] = r; }
+            continue;
+        }
+        decode_segment<false>(a, s_arena[wid], s_fixed, (uint32_t)slot, start, 0, 0, 0, &a.seg[slot], nullptr);
+        __syncwarp();
+    }
+}
+
+__global__ void par_plan_kernel(ParArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t off = 0, n = 0;
+    uint32_t cur = 0;
+    uint64_t resume_bit = a.cand[0], done = 0;
+    if (resume_bit != ~0ull) {
+        for (;;) {
+            const SegInfo s = a.seg[cur];
+            if (s.status == SEG_STOPPED) break;
+            if (off + s.out_len > a.out_cap) break;          // the serial decoder reports the overflow
+            a.plan_slot[n] = cur;
+            a.plan_off[n] = off;
+            a.plan_err[n] = 0;
+            n++;
+            off += s.out_len;
+            resume_bit = s.end_bit;
+            if (s.status == SEG_FINAL) { done = 1; break; }
+            if (s.next_slot == kEndOfInput) break;            // more input may follow: the serial decoder says so
+            cur = s.next_slot;
+        }
+    }
+    a.plan_off[n] = off;
+    a.state[0] = n;
+    a.state[1] = off;
+    a.state[2] = resume_bit;
+    a.state[3] = off;
+    a.state[4] = done;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) par_decode_kernel(ParArgs a) {
+    __shared__ WarpArena s_arena[kWarps];
+    __shared__ FixedTables s_fixed;
+    const unsigned wid = threadIdx.x >> 5;
+    if (wid == 0) build_fixed_tables(s_fixed, s_arena[0], false);
+    __syncthreads();
+    const uint64_t n = a.state[0];
+    for (uint64_t k = (uint64_t)blockIdx.x * kWarps + wid; k < n; k += (uint64_t)gridDim.x * kWarps) {
+        const uint32_t slot = a.plan_slot[k];
+        const SegInfo s = a.seg[slot];
+        const uint64_t off = a.plan_off[k];
+        const uint64_t avail = off + a.hist_len;
+        decode_segment<true>(a, s_arena[wid], s_fixed, slot, a.cand[slot], s.end_bit, off, avail, nullptr, &a.plan_err[k]);
+        __syncwarp();
+    }
+}
+
+// windows[k] = the 32 KiB before planned segment k, right aligned (bytes that do not exist read as 0 and are
+// never referenced: the decode pass refused such distances).
+__global__ void __launch_bounds__(1024) par_window_kernel(ParArgs a) {
+    extern __shared__ __align__(16) uint8_t s_win_raw[];
+    uint8_t (*s_win)[kWin] = reinterpret_cast<uint8_t (*)[kWin]>(s_win_raw);
+    const unsigned tid = threadIdx.x;
+    const uint64_t n = a.state[0];
+    for (unsigned j = tid; j < kWin; j += 1024) {
+        const uint64_t pad = kWin - a.hist_len;   // hist_len <= 32768
+        const uint8_t v = j >= pad ? a.hist[j - pad] : 0;
+        s_win[0][j] = v;
+        a.windows[j] = v;
+    }
+    __syncthreads();
+    unsigned cur = 0;
+    constexpr int kPer = kWin / 1024;   // elements per thread
+    uint64_t o0 = a.plan_off[0], o1 = n ? a.plan_off[1] : 0;
+    for (uint64_t k = 0; k < n; k++) {
+        const uint64_t o2 = k + 2 <= n ? a.plan_off[k + 2] : 0;   // one iteration ahead: off the critical path
+        const uint64_t off = o0, len = o1 - o0;
+        o0 = o1; o1 = o2;
+        const uint16_t* sym = a.sym + off;
+        uint8_t* next = a.windows + (k + 1) * (uint64_t)kWin;
+        // element j of the next window is symbol j + len - 32768 of this segment, or -- where the segment is
+        // shorter than the window -- byte j + len of the current window.  All loads of a thread are issued
+        // before the first is used: the chain over the segments is latency bound (measured: 16 us per segment
+        // with dependent loads, 6144 segments per GiB).
+        unsigned s[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const unsigned j = tid + 1024u * u;
+            const int64_t t = (int64_t)j + (int64_t)len - (int64_t)kWin;
+            s[u] = t >= 0 ? (unsigned)__ldcs(sym + t) : 0x10000u + (unsigned)(j + len);   // 0x10000 + w: byte w of the current window
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const unsigned j = tid + 1024u * u;
+            const unsigned v = s[u];
+            const uint8_t b = v < 256 ? (uint8_t)v : v < 0x10000u ? s_win[cur][v - 256] : s_win[cur][v - 0x10000u];
+            s_win[cur ^ 1][j] = b;
+            next[j] = b;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) par_resolve_kernel(ParArgs a) {
+    const uint64_t n = a.state[0];
+    for (uint64_t k = blockIdx.x; k < n; k += gridDim.x) {
+        const uint64_t off = a.plan_off[k], len = a.plan_off[k + 1] - off;
+        const uint8_t* win = a.windows + k * (uint64_t)kWin;
+        const uint16_t* sym = a.sym + off;
+        uint8_t* out = a.out + off;
+        for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const unsigned s = sym[i];
+            out[i] = s < 256 ? (uint8_t)s : win[s - 256];
+        }
+    }
+}
+
+__global__ void par_finish_kernel(ParArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint64_t n = a.state[0];
+    uint64_t bit = a.state[2], out = a.state[3], done = a.state[4];
+    for (uint64_t k = 0; k < n; k++) {
+        if (a.plan_err[k]) {   // everything from this segment on is the serial decoder's
+            bit = a.cand[a.plan_slot[k]];
+            out = a.plan_off[k];
+            done = 0;
+            break;
+        }
+    }
+    if (a.cand[0] == ~0ull) {
+        // the wrapper header did not parse: the serial decoder starts over and reports it
+        a.resume[0] = ~0ull; a.resume[1] = 0; a.resume[2] = 0;
+    } else {
+        a.resume[0] = bit; a.resume[1] = out; a.resume[2] = (a.state[6] & 3u) | (done ? 4u : 0u);
+    }
+}
+
+}  // namespace
+
+// scratch slots of zs_api.cu reserved for this path
+enum { SCR_P_CAND = 25, SCR_P_SEG = 26, SCR_P_PLAN = 27, SCR_P_SYM = 28, SCR_P_WIN = 29, SCR_P_STATE = 30 };
+
+int zs_launch_inflate_header(zs_ctx* ctx, const zs_inflate_args& a, uint64_t* d_state);   // zs_inflate.cu
+
+// One stream, wrapper header already located: a.d_resume receives where inflate_kernel continues.
+// d_state: [5] = bit position of the first block (or ~0), [6] = trailer flags, filled by zs_launch_inflate_header.
+int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, uint8_t* d_out, uint64_t out_cap,
+                               const uint8_t* d_hist, uint64_t hist_len, uint64_t* d_state, uint64_t* d_resume) {
+    ParArgs p;
+    p.in = d_in; p.in_len = in_len;
+    uint64_t tile = in_len / 6144;
+    if (tile < (32u << 10)) tile = 32u << 10;
+    tile = (tile + 31) & ~31ull;
+    p.tile = tile;
+    const uint64_t n_tiles = (in_len + tile - 1) / tile;
+    p.n_slots = (uint32_t)(n_tiles + 1);
+    p.cand = (uint64_t*)zs_scratch_get(ctx, SCR_P_CAND, (size_t)p.n_slots * 8);
+    p.seg = (SegInfo*)zs_scratch_get(ctx, SCR_P_SEG, (size_t)p.n_slots * sizeof(SegInfo));
+    uint8_t* plan = (uint8_t*)zs_scratch_get(ctx, SCR_P_PLAN, (size_t)p.n_slots * 16 + 64);
+    p.sym = (uint16_t*)zs_scratch_get(ctx, SCR_P_SYM, (size_t)out_cap * 2 + 64);
+    p.windows = (uint8_t*)zs_scratch_get(ctx, SCR_P_WIN, ((size_t)p.n_slots + 1) * kWin);
+    if (!p.cand || !p.seg || !plan || !p.sym || !p.windows) return ZS_MEM_ERROR;
+    p.plan_off = (uint64_t*)plan;                                   // [n_slots + 1]
+    p.plan_slot = (uint32_t*)(plan + ((size_t)p.n_slots + 1) * 8);  // [n_slots]
+    p.plan_err = p.plan_slot + p.n_slots;                           // [n_slots]  (16 bytes per slot + 8 in all)
+    p.state = d_state;
+    p.out_cap = out_cap;
+    p.hist_len = hist_len > kWin ? kWin : hist_len;
+    p.hist = d_hist + (hist_len > kWin ? hist_len - kWin : 0);
+    p.out = d_out;
+    p.resume = d_resume;
+    const unsigned sms = (unsigned)ctx->sm_count;
+    {
+        const unsigned warps = p.n_slots - 1;
+        if (warps) ZS_KERNEL(ctx, "par_scan_kernel", par_scan_kernel<<<(warps + 7) / 8, 256, 0, ctx->stream>>>(p));
+        else ZS_KERNEL(ctx, "par_scan_kernel", par_scan_kernel<<<1, 32, 0, ctx->stream>>>(p));
+    }
+    unsigned ctas = (p.n_slots + kWarps - 1) / kWarps;
+    if (ctas > sms * 8u) ctas = sms * 8u;
+    ZS_KERNEL(ctx, "par_count_kernel", par_count_kernel<<<ctas, kWarps * 32, 0, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_plan_kernel", par_plan_kernel<<<1, 32, 0, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_decode_kernel", par_decode_kernel<<<ctas, kWarps * 32, 0, ctx->stream>>>(p));
+    static bool attr_set[64] = {false};
+    const int dev_slot = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    if (!attr_set[dev_slot] || ctx->device >= 64) {
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(par_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kWin));
+        attr_set[dev_slot] = true;
+    }
+    ZS_KERNEL(ctx, "par_window_kernel", par_window_kernel<<<1, 1024, 2 * kWin, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_resolve_kernel", par_resolve_kernel<<<sms * 8u, 256, 0, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_finish_kernel", par_finish_kernel<<<1, 32, 0, ctx->stream>>>(p));
+    return ZS_OK;
+}

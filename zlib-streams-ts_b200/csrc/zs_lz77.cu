@@ -106,6 +106,7 @@ struct LzArgs {
     uint64_t data_end;         // one past the last input byte
     const uint64_t* in_off;    // [n_chunks+1] relative to org
     uint32_t n_chunks, seg_chunks, n_seg, max_bpc;
+    uint32_t n_big, seg_small;   // segments [0, n_big) hold seg_chunks chunks, the later ones seg_small (see zs_launch_lz77)
     int level;
     int strategy;              // ZS_STRATEGY_* (FILTERED and RLE act here)
     int cross;                 // 1: matches may reach before the chunk start (PRIME / STITCHED)
@@ -682,8 +683,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
         __syncthreads();
         const uint32_t seg = S.seg;
         if (seg >= a.n_seg) break;
-        const uint32_t c0 = seg * a.seg_chunks;
-        const uint32_t c1 = (c0 + a.seg_chunks < a.n_chunks) ? c0 + a.seg_chunks : a.n_chunks;
+        const bool big = seg < a.n_big;
+        const uint32_t c0 = big ? seg * a.seg_chunks : a.n_big * a.seg_chunks + (seg - a.n_big) * a.seg_small;
+        const uint32_t sc = big ? a.seg_chunks : a.seg_small;
+        const uint32_t c1 = (c0 + sc < a.n_chunks) ? c0 + sc : a.n_chunks;
 
         const uint32_t nc = c1 - c0;
 
@@ -954,8 +957,18 @@ int zs_launch_lz77(zs_ctx* ctx, const zs_deflate_plan& p) {
         seg_chunks = (uint32_t)sc;
     }
     if (a.cross && p.seg_hint) seg_chunks = p.seg_hint < kMaxSegChunks ? p.seg_hint : kMaxSegChunks;
+    // The CTAs claim segments in index order from an atomic counter, so what the kernel waits for at the end
+    // is at most one segment: the last quarter of the chunks is cut into segments a quarter of the size
+    // (measured on 8192 x 256 KiB chunks, level 6: 630 equal segments = 4.26 waves over 148 SMs, 14.5 GB/s;
+    // the whole 16384-chunk batch, 6.9 waves: 16.8 GB/s).  The output does not depend on the segmentation:
+    // every chunk sees the same <= 32 KiB - 2 steps of history whether it is primed or carried.
     a.seg_chunks = seg_chunks;
-    a.n_seg = (p.n_chunks + seg_chunks - 1) / seg_chunks;
+    a.seg_small = seg_chunks >= 4 ? seg_chunks / 4 : 1;
+    a.n_big = (uint32_t)(((uint64_t)p.n_chunks * 3 / 4) / seg_chunks);
+    {
+        const uint32_t rest = p.n_chunks - a.n_big * seg_chunks;
+        a.n_seg = a.n_big + (rest + a.seg_small - 1) / a.seg_small;
+    }
     a.sym = p.d_sym;
     a.chunk_nblk = p.d_chunk_nblk;
     a.blk_desc = p.d_blk_desc;

@@ -578,6 +578,7 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
     for (;;) {
         const uint64_t in_off[2] = {0, st->in.size()}, out_off[2] = {0, st->out_cap_hint};
         // `out` is rebuilt by every attempt; what was queued from it stays in `ready`
+        if (st->out_cap_hint < 4 * st->in.size()) st->out_cap_hint = 4 * st->in.size();   // a typical ratio: fewer re-decodes
         st->out.resize(st->out_cap_hint);
         uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->hist.size()};
         uint32_t check = 0;
@@ -637,7 +638,11 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
     InflateState* st = istate(strm);
     if (!st || !strm->next_out || (!strm->next_in && strm->avail_in != 0)) return ZS_STREAM_ERROR;
     const uint64_t in0 = strm->avail_in, out0 = strm->avail_out;
-    if (!st->done && !st->failed) {
+    // Like inflate(), which stops consuming input when the output buffer is full: while more decoded bytes
+    // are waiting than this call can deliver, no new input is taken (the reference's driver loop,
+    // streams.ts:86 `while (strm.avail_in > 0)`, then keeps calling with fresh output buffers).
+    const bool backlog = st->ready.size() - st->ready_pos > strm->avail_out;
+    if (!st->done && !st->failed && !backlog) {
         // input left over from the previous member is consumed first (inflateReset flow)
         if (!st->leftover.empty() && st->in.empty()) {
             st->in.swap(st->leftover);
@@ -659,7 +664,14 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         if (due && !st->in.empty()) {
             int rc = inflate_attempt(strm, st);
             if (rc != ZS_OK) return rc;
-            st->next_attempt = st->in.size() < (256u << 10) ? st->in.size() + 1 : st->in.size() + st->in.size() / 2;
+            // Short streams are decoded on every call.  A long stream is decoded in growing batches (a quarter of
+            // what has been seen so far, at most 8 MiB): an attempt then holds many flush-point segments and goes
+            // through the segment-parallel decoder (zs_inflate_par.cu) instead of one warp.
+            const size_t seen = (size_t)strm->total_in;
+            size_t grain = seen / 4;
+            if (grain > (8u << 20)) grain = 8u << 20;
+            if (st->in.size() < (256u << 10) && seen < (1u << 20)) st->next_attempt = st->in.size() + 1;
+            else st->next_attempt = st->in.size() + (grain > st->in.size() / 2 ? grain : st->in.size() / 2);
             if (st->need_dict) {
                 strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
                 return ZS_NEED_DICT;
@@ -670,7 +682,11 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
                 strm->next_in -= give;
                 strm->avail_in += give;
                 strm->total_in -= give;
-                st->leftover.resize(st->leftover.size() - give);  // handed back from the tail of the call's input
+                // Bytes behind the end that arrived in EARLIER calls (a long stream is decoded in batches) cannot
+                // be handed back through avail_in any more; total_in stays exact -- it is what the reference's
+                // multi-member flow positions the next member with (test/inflate/test-multistream.ts:50-53).
+                strm->total_in -= st->leftover.size() - give;
+                st->leftover.clear();
             }
         }
     }
@@ -697,6 +713,10 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
     }
     // inf_leave, inflate.ts:1092-1098: no progress, or Z_FINISH without reaching the end
     const bool progress = (in0 != strm->avail_in) || (out0 != strm->avail_out);
+    // Decoded bytes still waiting for output room: Z_OK = "call again with more room", also under Z_FINISH
+    // (the reference never holds decoded bytes back, so it has no such state; streams.ts:139-170 drains with
+    // repeated Z_FINISH calls and treats anything but Z_OK / Z_STREAM_END as fatal).
+    if (!all_out && progress) return ZS_OK;
     if (!progress || flush == ZS_FINISH) return ZS_BUF_ERROR;
     return ZS_OK;
 }
