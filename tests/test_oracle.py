@@ -302,3 +302,53 @@ def test_deflate_level0_byte_exact_with_zlib(oracle):
     part = oracle.deflate(b"xyz" * 30000, 0, 0, flush=oracle.Z_SYNC_FLUSH)
     assert part.endswith(b"\x00\x00\x00\xff\xff")
     assert zlib.decompressobj(-15).decompress(part) == b"xyz" * 30000
+
+
+def _inflate_table(oracle, ctype, lens, root, deflate64=False, room=1024):
+    """inflate_table (inftrees.ts:62) through the oracle: returns (ret, bits, index, table entries)."""
+    import ctypes as C
+    import numpy as np
+    L = oracle.lib()
+    lens_a = np.asarray(lens, dtype=np.uint16)
+    table = np.zeros(room, dtype=np.uint32)
+    work = np.zeros(max(288, lens_a.size), dtype=np.uint16)
+    bits, index = C.c_uint(root), C.c_uint(0)
+    ret = L.zo_inflate_table(ctype, lens_a.ctypes.data, lens_a.size, table.ctypes.data, C.addressof(bits),
+                             work.ctypes.data, C.addressof(index), 1 if deflate64 else 0)
+    return ret, bits.value, index.value, table
+
+
+def test_inflate_table_kats(oracle):
+    """The reference's direct unit tests of inflate_table: test/inflate/test-inftrees-subtable.ts,
+    test/inflate/test-inftrees9-subtable.spec.ts, test/coverage-targets/coverage-inftrees.spec.ts."""
+    CODES, LENS = 0, 1
+    op = lambda e: (int(e) >> 24) & 0xff
+    nbits = lambda e: (int(e) >> 16) & 0xff
+    # test-inftrees-subtable.ts:6-35 -- a root of 3 bits forces sub-tables: some root entry is a pointer.  The
+    # file's own vector [2,3,3,4,4,5,5,6,0,0,0,0] is an incomplete set (Kraft sum 45/64), for which the reference's
+    # code returns -1 (inftrees.ts:141-143); that function is exported but no runner calls it (it would fail).
+    # Pinned here: -1 for the vector as written, and the intended property on the same lengths completed by
+    # codes of 2, 5 and 6 bits.
+    assert _inflate_table(oracle, LENS, [2, 3, 3, 4, 4, 5, 5, 6, 0, 0, 0, 0], 3)[0] == -1
+    ret, root, used, t = _inflate_table(oracle, LENS, [2, 3, 3, 4, 4, 5, 5, 6, 2, 5, 6, 0], 3)
+    assert ret == 0 and root == 3
+    ptrs = [e for e in t[: 1 << root] if nbits(e) == root and op(e) > 0 and (op(e) & 0xf0) == 0]
+    assert ptrs, "expected a sub-table pointer in the root table"
+    assert all((int(e) & 0xffff) >= (1 << root) for e in ptrs) and used > (1 << root)
+    # test-inftrees9-subtable.spec.ts:17-45 -- deflate64 parameters, lens [1,2,3,3], root 2
+    ret, root, used, t = _inflate_table(oracle, LENS, [1, 2, 3, 3], 2, deflate64=True)
+    assert ret == 0 and root == 2
+    assert any(op(e) and (op(e) & 0xf0) == 0 for e in t[: 1 << root])
+    # coverage-inftrees.spec.ts:7-19 -- empty CODES set: 0, bits becomes 1, two invalid-code markers
+    ret, root, used, t = _inflate_table(oracle, CODES, [0], 4)
+    assert ret == 0 and root == 1 and used == 2 and op(t[0]) == 64 and op(t[1]) == 64
+    # coverage-inftrees.spec.ts:21-34 -- sixteen 15-bit codes: -1
+    assert _inflate_table(oracle, LENS, [15] * 16, 1)[0] == -1
+    # coverage-inftrees.spec.ts:36-50 -- incomplete CODES set: -1
+    assert _inflate_table(oracle, CODES, [1, 0, 0], 1)[0] == -1
+    # over-subscribed proper (three 1-bit codes): -1 (inftrees.ts:104-112)
+    assert _inflate_table(oracle, LENS, [1, 1, 1], 1)[0] == -1
+    # a complete LENS set needing more than ENOUGH_LENS entries cannot exist; a DISTS set with one 1-bit code is
+    # the one incomplete set the reference accepts (inftrees.ts:113-130: max == 1)
+    ret, root, used, t = _inflate_table(oracle, 2, [1] + [0] * 29, 6)
+    assert ret == 0 and root == 1

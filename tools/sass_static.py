@@ -24,9 +24,9 @@ def totals():
         m = re.match(r"\s*Function (\S+):", l)
         if m:
             name = m.group(1)
-        m = re.search(r"REG:(\d+).*?SHARED:(\d+).*?LOCAL:(\d+)", l)
-        if m and name:
-            regs[name] = (int(m.group(1)), int(m.group(2)), int(m.group(3)))
+        m = re.search(r"REG:(\d+)\s+STACK:(\d+)\s+SHARED:(\d+)\s+LOCAL:(\d+)", l)
+        if m and name:   # per-thread local memory in use is STACK (the frame: spills and local arrays); LOCAL is static .local data
+            regs[name] = (int(m.group(1)), int(m.group(3)), int(m.group(2)) + int(m.group(4)))
     counts = collections.Counter()
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, check=True, capture_output=True)
@@ -40,7 +40,7 @@ def totals():
                 elif fn and re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+\S", l):
                     counts[fn] += 1
     demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=True, text=True).stdout.split("\n")
-    print(f"{'SASS':>6} {'regs':>5} {'smem':>7} {'local':>6}  kernel")
+    print(f"{'SASS':>6} {'regs':>5} {'smem':>7} {'stack':>6}  kernel   (stack = STACK + LOCAL bytes per thread)")
     for (fn, c), pretty in zip(counts.items(), demangle):
         r = regs.get(fn, (0, 0, 0))
         print(f"{c:6d} {r[0]:5d} {r[1]:7d} {r[2]:6d}  {pretty.replace('(anonymous namespace)::', '')[:100]}")
