@@ -287,3 +287,43 @@ def test_randomised_soak_inflate_and_api(gpu_ctx):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "soak_inflate.py"), "24", "3"], capture_output=True, text=True, timeout=400)
     assert p.returncode == 0 and p.stdout.count("soak ok") == 3, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n_streams", [12000, 40000])
+def test_host_batch_pipelined_equals_unpipelined(gpu_ctx, monkeypatch, n_streams):
+    """zs_inflate_batch slices a large batch (copies overlap the kernels); the results -- output bytes, lengths,
+    consumed input, checksums, status and message of every stream, corrupt ones included -- must be those of the
+    single-shot path (12000 streams: warp per stream; 40000: thread per stream in both)."""
+    rnd = random.Random(n_streams)
+    rec = 8192 if n_streams < 32768 else 2048
+    text = make_text(rec * 512, 21)
+    base = []
+    for i in range(512):
+        d = rnd.randbytes(rec) if i % 19 == 0 else text[i * rec: (i + 1) * rec]
+        co = zlib.compressobj(6, 8, 31)
+        base.append((co.compress(d) + co.flush(), d))
+    streams, caps, want = [], [], []
+    for i in range(n_streams):
+        z, d = base[rnd.randrange(512)]
+        if i % 997 == 5:                      # corrupt the deflate data of some records
+            z = z[:20] + bytes([z[20] ^ 0x55]) + z[21:]
+        if i % 1501 == 7:                     # and give some too little room
+            caps.append(rec // 2)
+        else:
+            caps.append(rec)
+        streams.append(z)
+        want.append(d)
+    assert sum(len(s) for s in streams) + sum(caps) >= 64 << 20
+    r = _run(streams, 31, caps)
+    monkeypatch.setenv("ZS_INFLATE_UNPIPELINED", "1")
+    ref = _run(streams, 31, caps)
+    monkeypatch.delenv("ZS_INFLATE_UNPIPELINED")
+    assert np.array_equal(r.status, ref.status) and np.array_equal(r.out_len, ref.out_len)
+    assert np.array_equal(r.in_used, ref.in_used) and np.array_equal(r.checks, ref.checks)
+    assert np.array_equal(r.details, ref.details)
+    assert all(r.output(i) == ref.output(i) for i in range(n_streams))
+    ok = [i for i in range(n_streams) if i % 997 != 5 and i % 1501 != 7]
+    assert all(int(r.status[i]) == 1 for i in ok)
+    for i in ok[:: max(1, len(ok) // 300)]:
+        assert r.output(i) == want[i] and int(r.checks[i]) == zlib.crc32(want[i])
+    assert any(int(r.status[i]) != 1 for i in range(5, n_streams, 997))

@@ -16,7 +16,7 @@ enum {
     SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
     SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23, SCR_I_RESUME = 24,
     // 25..29: zs_inflate_par.cu
-    SCR_P_STATE = 30, SCR_I_STREAM = 31,
+    SCR_P_STATE = 30, SCR_I_STREAM = 31, SCR_H_DETAIL = 32,
 };
 constexpr uint64_t kParMinInput = 128u << 10;   // shorter streams are decoded by one warp
 
@@ -684,6 +684,84 @@ int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_
                                     a.d_flags, d_out_len, d_checks, d_status, a.d_detail);
 }
 
+// Host-buffer inflate of a large batch, pipelined like deflate_batch_pipelined: the streams are cut into slices
+// of about equal input + output bytes; slice s+1 is copied in while the kernels of slice s run and the output of
+// slice s-1 is copied out (three streams, events between them).  Every slice is decoded by the kernel the
+// whole batch would have used (ctx->inflate_batch_n), so the results are those of the unsliced call.
+static int inflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits,
+                                   uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used,
+                                   uint32_t* checks, int32_t* status, uint8_t* d_in, uint8_t* d_out, uint64_t* d_ioff,
+                                   uint64_t* d_ooff, uint8_t* d_res, const uint8_t* d_dict, const uint64_t* d_rng) {
+    // a slice must still fill the GPU: 32768 streams for the thread-per-stream kernel, one warp per stream and
+    // 32 resident warps per SM otherwise
+    constexpr int kMaxSlices = 8;
+    const uint32_t fill = n >= 32768 ? 32768u : (uint32_t)ctx->sm_count * 32u;
+    int kSlices = (int)(n / fill);
+    kSlices = kSlices < 2 ? 2 : kSlices > kMaxSlices ? kMaxSlices : kSlices;
+    if (!ctx->s_in) {
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_res, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev) ZS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // slice boundaries: stream index at which the running input + output bytes pass s/kSlices of the total
+    uint32_t b[kMaxSlices + 1];
+    const uint64_t total = in_off[n] + out_off[n];
+    b[0] = 0;
+    for (int s = 1; s < kSlices; s++) {
+        const uint64_t want = total / kSlices * s;
+        uint32_t lo = b[s - 1], hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (in_off[mid] + out_off[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        b[s] = lo;
+    }
+    b[kSlices] = n;
+    uint64_t* d_olen = (uint64_t*)d_res;
+    uint64_t* d_used = d_olen + n;
+    uint32_t* d_checks = (uint32_t*)(d_used + n);
+    int32_t* d_status = (int32_t*)(d_checks + n);
+    int32_t* d_det = (int32_t*)zs_scratch_get(ctx, SCR_H_DETAIL, (size_t)n * 4);
+    if (!d_det) return ZS_MEM_ERROR;
+    cudaEvent_t* ev_in = ctx->ev;          // [s] slice s is on the device
+    cudaEvent_t* ev_k = ctx->ev + 16;      // [s] kernels of slice s are done
+    // the offsets (and whatever the caller queued on the context stream) come first
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ioff, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ooff, out_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[48], ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev[48], 0));
+    ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev[48], 0));
+    struct Guard { zs_ctx* c; ~Guard() { c->inflate_batch_n = 0; } } guard{ctx};
+    ctx->inflate_batch_n = n;
+    for (int s = 0; s < kSlices; s++) {
+        const uint32_t lo = b[s], ns = b[s + 1] - b[s];
+        if (ns == 0) continue;
+        // whole 8-byte words around the slice's input (the decoders read aligned words)
+        const uint64_t i0 = in_off[lo] & ~7ull, i1 = in_off[lo + ns];
+        if (i1 > i0) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + i0, in + i0, i1 - i0, cudaMemcpyHostToDevice, ctx->s_in));
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_in[s], ctx->s_in));
+        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        const int rc = zs_inflate_batch_dev(ctx, d_in, d_ioff + lo, ns, window_bits, d_out, d_ooff + lo, d_olen + lo, d_used + lo,
+                                            d_checks + lo, d_status + lo, d_dict, d_rng ? d_rng + 2 * (size_t)lo : nullptr);
+        if (rc != ZS_OK) return rc;
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_det + lo, ctx->d_last_detail, (size_t)ns * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ZS_CUDA_TRY(ctx, cudaEventRecord(ev_k[s], ctx->stream));
+        ZS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ev_k[s], 0));
+        const uint64_t o0 = out_off[lo], o1 = out_off[lo + ns];
+        if (o1 > o0) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_olen, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (in_used) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(in_used, d_used, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (checks) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_out));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d_last_detail = d_det;
+    ctx->last_detail_n = n;
+    return ZS_OK;
+}
+
 int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits, uint8_t* out,
                      const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks, int32_t* status,
                      const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total) {
@@ -713,6 +791,10 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
         ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_dict, dict, dict_total, cudaMemcpyHostToDevice, ctx->stream));
         ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_rng, dict_rng, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
     }
+    // large batches: copies and kernels overlap slice by slice
+    if (n >= 2u * (uint32_t)ctx->sm_count * 32u && in_total + out_total >= (64ull << 20) && !ctx->inflate_resume && !getenv("ZS_INFLATE_UNPIPELINED"))
+        return inflate_batch_pipelined(ctx, in, in_off, n, window_bits, out, out_off, out_len, in_used, checks, status, d_in,
+                                       d_out, d_ioff, d_ooff, d_res, d_dict, d_rng);
     if (in_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_total, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ioff, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ooff, out_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -726,8 +808,15 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
                                   d_dict, d_rng);
     ctx->par.on = false;
     if (rc != ZS_OK) return rc;
-    if (out_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, out_total, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out_len, d_olen, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n == 1 && out_total > (1u << 20)) {
+        // one stream with a generous capacity (the streaming shim asks for 4x its input): bring back what was produced
+        ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint64_t made = out_len[0] < out_total ? out_len[0] : out_total;
+        if (made) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out + out_off[0], d_out + out_off[0], made, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (out_total) {
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (in_used) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(in_used, d_used, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (checks) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(checks, d_checks, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

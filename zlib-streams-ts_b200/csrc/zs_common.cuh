@@ -21,7 +21,7 @@ struct zs_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     // grow-only device scratch, one slot per purpose (see zs_api.cu)
-    zs_scratch scr[32];
+    zs_scratch scr[40];
     // pinned host staging for small results
     void* h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -35,6 +35,7 @@ struct zs_ctx {
     uint64_t inflate_start_bit = 0;
     uint64_t inflate_mark[2] = {0, 0};
     uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
+    uint32_t inflate_batch_n = 0;   // streams of the whole batch while its slices are decoded (kernel choice), 0 = not sliced
     // one-stream inflate with sizes known on the host: lets zs_inflate_batch_dev use the segment-parallel decoder
     struct { bool on = false; uint64_t in_off = 0, in_len = 0, out_off = 0, out_cap = 0, dict_off = 0, dict_len = 0; } par;
     cudaEvent_t ev[64] = {nullptr};

@@ -96,6 +96,8 @@ struct Smem {
     uint2 mj[kMjRing];         // resolve -> parse, emit: (visited mask, packed exits/counts, see resolve) for a parse entering at this lane
     uint32_t bnd[kMaxSegChunks + 1];  // chunk boundaries of the segment, as range offsets (bnd[0] = first data position)
     uint32_t seg;              // segment being processed
+    uint32_t claim[2];         // lazy levels: resolve / emit pairs claimed in this iteration (and the next one's counter, being reset)
+    alignas(8) uint64_t stage_bar;   // mbarrier the bulk copies of the window staging complete on
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
 
@@ -154,6 +156,60 @@ __device__ __forceinline__ void stage_window(Smem& S, const LzArgs& a, uint64_t 
         *reinterpret_cast<uint4*>(S.ring + idx) = v;
         if (idx < kRingGuard) *reinterpret_cast<uint4*>(S.ring + kRing + idx) = v;
     }
+}
+
+// ---- bulk-async staging (Blackwell: the copy engine moves the window, no thread does) ------------
+// Steady state: one elected lane of the thin insert warp arms an mbarrier with the byte count and issues
+// 1-D cp.async.bulk copies global -> shared (UBLKCP in SASS): the step's ~1 KiB of look-ahead goes into
+// the ring without a single LDG/STS on the CTA's critical warp, whose loads used to sit in registers
+// across the thirty head exchanges.  The warp waits for the barrier's phase just before the step
+// barrier, which publishes the bytes to the wide warps.
+#ifndef ZS_LZ_NO_BULK
+#define ZS_LZ_BULK 1
+#endif
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ZS_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ZS_MBAR_DONE;\n"
+        "bra ZS_MBAR_WAIT;\n"
+        "ZS_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+// Issue the copies for input [from, to) (multiples of 16, to - from < kRing, to <= the readable end): the part up to
+// the ring's wrap, the part after it, and the mirror of ring[0, kRingGuard) behind the ring.  One thread calls
+// this; returns the bytes the barrier has to expect.
+__device__ __forceinline__ unsigned bulk_stage(Smem& S, const uint8_t* buf, uint64_t from, uint64_t to) {
+    unsigned total = 0;
+    while (from < to) {
+        const unsigned idx = (unsigned)from & (kRing - 1u);
+        unsigned nb = (unsigned)(to - from);
+        if (idx + nb > kRing) nb = kRing - idx;
+        bulk_g2s(S.ring + idx, buf + from, nb, &S.stage_bar);
+        total += nb;
+        if (idx < kRingGuard) {
+            const unsigned g = idx + nb < kRingGuard ? nb : kRingGuard - idx;
+            bulk_g2s(S.ring + kRing + idx, buf + from, g, &S.stage_bar);
+            total += g;
+        }
+        from += nb;
+    }
+    return total;
 }
 
 __device__ __forceinline__ unsigned hash3(uint32_t w) { return ((w & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
@@ -245,6 +301,46 @@ __device__ __forceinline__ uint32_t ring32(const Smem& S, unsigned idx) {
 }
 __device__ __forceinline__ unsigned first_diff_byte(uint32_t x) { return (unsigned)(__ffs((int)x) - 1) >> 3; }
 
+__device__ __forceinline__ uint2 ring64(const Smem& S, unsigned idx) {
+    idx &= kRing - 1u;
+    const unsigned al = idx & ~3u, sh = (idx & 3u) * 8u;   // al + 11 < kRing + kRingGuard
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(S.ring + al);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(S.ring + al + 4);
+    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(S.ring + al + 8);
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+// Bytes [0, len) of the candidate at ring index ci and of the position at pi are equal: compare on from there, eight
+// bytes per round (the two streams keep their own word alignment, the last word loaded is carried into the next
+// round: 2 + 2 loads per 8 bytes), until a difference or max_len.  The result is not capped at max_len.
+__device__ __forceinline__ unsigned extend_match(const Smem& S, unsigned ci, unsigned pi, unsigned len, unsigned max_len) {
+    unsigned aa = ((ci + len) & (kRing - 1u)) & ~3u, ab = ((pi + len) & (kRing - 1u)) & ~3u;   // the guard mirrors 288 bytes
+    const unsigned sa = ((ci + len) & 3u) * 8u, sb = ((pi + len) & 3u) * 8u;
+    uint32_t a0 = *reinterpret_cast<const uint32_t*>(S.ring + aa);
+    uint32_t b0 = *reinterpret_cast<const uint32_t*>(S.ring + ab);
+    while (len < max_len) {
+        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 4);
+        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 8);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 4);
+        const uint32_t b2 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 8);
+        const uint32_t yl = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+        const uint32_t yh = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+        if (yl | yh) return len + (yl ? first_diff_byte(yl) : 4u + first_diff_byte(yh));
+        a0 = a2; b0 = b2;
+        aa += 8; ab += 8;
+        len += 8;
+    }
+    return len;
+}
+// Length of the match between the candidate at ring index ci and the position at pi (first eight bytes of the
+// position in pw0/pw1), not capped at max_len (the caller clamps); compares stop at max_len rounded up to 8.
+__device__ __forceinline__ unsigned match_length(const Smem& S, unsigned ci, unsigned pi, uint32_t pw0, uint32_t pw1, unsigned max_len) {
+    const uint2 cw = ring64(S, ci);
+    const uint32_t x0 = cw.x ^ pw0, x1 = cw.y ^ pw1;
+    if (x0) return first_diff_byte(x0);
+    if (x1) return 4u + first_diff_byte(x1);
+    return extend_match(S, ci, pi, 8u, max_len);
+}
+
 // [cs, ce) is the chunk that holds q.
 // kMode: 0 greedy levels (1-3), 2 Z_RLE.  (The lazy levels 4-9 use search_position_sync below.)
 // Work bounds of the lazy levels on periodic data: a chain is "dense" when the hop to the candidate is at most
@@ -280,7 +376,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
     const uint32_t back = c.cross ? q + c.pre : q - cs;
     const unsigned max_back = back < kMaxDist ? back : kMaxDist;
-    unsigned best_len = 2, best_dist = 0;
+    unsigned best_len = 2, best_dist = 0, best_ci = pi;
     unsigned ci = pi, dist = 0;
     for (int chain = cfg.chain; chain > 0; --chain) {
         const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
@@ -298,37 +394,25 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
             if (x) {
                 len = 4 + first_diff_byte(x);
             } else {
-                // 8 bytes per round; the two streams keep their own word alignment and the last word
-                // loaded is carried into the next round (2 + 2 loads per 8 bytes).  (max_chain <= 32 bounds
-                // the cost of runs at levels 1-3; the scan_end test costs them 6 % through code generation.)
+                // Eight bytes match.  Inside the chain loop the compare goes on as far as nice_length only (not at
+                // all at level 1, nice_length 8): a match that long ends the search whatever its full length, and
+                // the full length is found after the loop, where the lanes that hold such a match extend them
+                // together -- in the loop that path ran for 1.7 of 32 lanes, up to max_chain times per batch
+                // (mixed corpus, level 1: 25.5 -> 22.1 ms per 512 MiB).
                 len = 8;
-                unsigned aa = (ci + 8u) & ~3u, ab = (pi + 8u) & ~3u;            // < kRing + 12: the guard mirrors 288 bytes
-                const unsigned sa = ((ci + 8u) & 3u) * 8u, sb = ((pi + 8u) & 3u) * 8u;
-                uint32_t a0 = *reinterpret_cast<const uint32_t*>(S.ring + aa);
-                uint32_t b0 = *reinterpret_cast<const uint32_t*>(S.ring + ab);
-                while (len < max_len) {
-                    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 4);
-                    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 8);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 4);
-                    const uint32_t b2 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 8);
-                    const uint32_t yl = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
-                    const uint32_t yh = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
-                    if (yl | yh) {
-                        len += yl ? first_diff_byte(yl) : 4 + first_diff_byte(yh);
-                        break;
-                    }
-                    a0 = a2; b0 = b2;
-                    aa += 8; ab += 8;
-                    len += 8;
-                }
+                if (nice > 8u) len = extend_match(S, ci, pi, 8u, nice);
             }
         }
         if (len > max_len) len = max_len;
         if (len > best_len) {
             best_len = len;
             best_dist = dist;
-            if (len >= nice) break;
+            if (len >= nice) { best_ci = ci; break; }
         }
+    }
+    if (best_len >= nice) {   // bytes [0, nice) are equal: whole 8-byte rounds from there
+        best_len = extend_match(S, best_ci, pi, nice & ~7u, max_len);
+        if (best_len > max_len) best_len = max_len;
     }
     if (best_len < c.min_len) return lit;
     // A 3-byte match far back costs more bits than three literals (a distance code plus up to 13 extra
@@ -437,6 +521,152 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
                     // A candidate that ties with the best match on a dense chain means periodic data (a run): the
                     // rest of the chain is more of the same.  Every tie takes a quarter off the remaining budget.
                     chain -= chain >> 2;
+                }
+            } while (0);
+            --chain;
+        }
+    }
+    if (best_len < c.min_len) return lit;
+    if (best_len == 3 && best_dist > kTooFar) return lit;   // deflate.ts:1381-1387
+    return lit | (best_len << 15) | best_dist;
+}
+
+// ---- the same two searches with the end-window filter (the default) --------------------------------
+// What the warp pays for is not the candidates a lane visits but the code paths any lane takes: with one
+// candidate per lane and iteration, the deep compare used to run in nearly every iteration for the two or
+// three lanes whose candidate got past the 3-byte test (ncu, level 6: a third of the kernel's instructions
+// at 1.5-6 of 32 lanes).  A candidate can only beat the match in hand if it agrees with the position on
+// the four bytes that END at index best_len -- longest_match's scan_end test (deflate.ts:1063-1081) widened
+// to a word -- so that window is compared FIRST: one unaligned word of the ring per candidate, and only
+// candidates that can improve the match reach the compare.  The compare itself starts with one 8-byte
+// round (three aligned words of the ring against the position's first eight bytes in registers).
+#ifndef ZS_LZ_NO_ENDWIN
+#define ZS_LZ_ENDWIN 1
+#endif
+// Greedy levels (1-3): same rules and same result as search_position<0> -- first longest match in chain order,
+// stop at nice_length -- the filter only skips candidates that cannot be longer than the best so far.
+__device__ __forceinline__ uint32_t search_greedy_endwin(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
+                                                         uint32_t cs, uint32_t ce) {
+    const uint32_t room = ce - q;
+    const unsigned max_len = room < 258u ? room : 258u;
+    const unsigned pi = (c.cb + q) & (kRing - 1u);
+    const uint2 pw = ring64(S, pi);
+    const uint32_t lit = (pw.x & 0xffu) << 24;
+    if (max_len < 3) return lit;
+    const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
+    const uint32_t back = c.cross ? q + c.pre : q - cs;
+    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
+    unsigned best_len = 2, best_dist = 0;
+    unsigned ci = pi, dist = 0;
+#ifdef ZS_LZ_DEFER_EXT
+    unsigned best_ci = pi;
+#endif
+    unsigned woff = 0;                       // the window is bytes [woff, woff + 4) = the four bytes ending at best_len
+    uint32_t wown = pw.x, wmask = 0xffffffu; // (three bytes while there is no match yet)
+    for (int chain = cfg.chain; chain > 0; --chain) {
+        const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
+        if (delta == 0) break;
+        dist += delta;
+        if (dist > max_back) break;
+        ci = (ci - delta) & (kRing - 1u);
+        if ((ring32(S, ci + woff) ^ wown) & wmask) continue;   // cannot beat best_len (or a hash collision)
+#ifdef ZS_LZ_DEFER_EXT
+        // Inside the loop a compare goes as far as nice_length only (no further than 8 bytes at level 1): a match
+        // that long ends the search whatever its full length, which is found after the loop, where the lanes
+        // that have such a match extend them together (in the loop that path ran for 1.7 of 32 lanes, up to
+        // max_chain times per batch).
+        unsigned len = match_length(S, ci, pi, pw.x, pw.y, nice);
+        if (len > best_len) {
+            best_dist = dist;
+            if (len >= nice) { best_len = nice; best_ci = ci; break; }
+            best_len = len;
+            woff = len - 3u; wmask = 0xffffffffu;
+            wown = ring32(S, pi + woff);
+        }
+    }
+    if (best_len >= nice && best_dist) {
+        best_len = extend_match(S, best_ci, pi, nice & ~7u, max_len);   // bytes [0, nice) are equal; whole rounds from there
+        if (best_len > max_len) best_len = max_len;
+    }
+#else
+        unsigned len = match_length(S, ci, pi, pw.x, pw.y, max_len);
+        if (len > max_len) len = max_len;
+        if (len > best_len) {
+            best_len = len;
+            best_dist = dist;
+            if (len >= nice) break;
+            woff = len - 3u; wmask = 0xffffffffu;
+            wown = ring32(S, pi + woff);
+        }
+    }
+#endif
+    if (best_len < c.min_len) return lit;
+    if (best_len == 3 && best_dist > kTooFar) return lit;   // see search_position
+    return lit | (best_len << 15) | best_dist;
+}
+
+// Lazy levels (4-9): search_position_sync's loop and rules with the filter in front of the compare.  The two
+// rules that looked at candidates which do not improve the match -- "eight bytes match but the byte at best_len
+// does not" and "ties with the best match", both on dense chains only -- are now decided on the filtered-out
+// candidate's first eight bytes: it agrees with the position on min(best_len, 8) bytes (for best_len < 8 that
+// is exactly a tie, since the window said the byte at best_len differs).
+__device__ __forceinline__ uint32_t search_lazy_endwin(const Smem& S, const LevelCfg& cfg, const StopCfg stop, const RangeCtx& c,
+                                                       uint32_t q, uint32_t cs, uint32_t ce, bool live) {
+    const uint32_t room = live ? ce - q : 0u;
+    const unsigned max_len = room < 258u ? room : 258u;
+    const unsigned pi = (c.cb + q) & (kRing - 1u);
+    uint2 pw = make_uint2(0, 0);
+    if (live) pw = ring64(S, pi);
+    const uint32_t lit = (pw.x & 0xffu) << 24;
+    const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
+    const uint32_t back = c.cross ? q + c.pre : q - cs;
+    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
+    unsigned best_len = 2, best_dist = 0;
+    unsigned ci = pi, dist = 0;
+    unsigned woff = 0;
+    uint32_t wown = pw.x, wmask = 0xffffffu;
+    int chain = (live && max_len >= 3) ? cfg.chain : 0;
+    for (unsigned it = 0;; ++it) {
+        const unsigned walking = __ballot_sync(ZS_FULL_MASK, chain > 0);
+        if (walking == 0) break;
+        if (it >= stop.after && (unsigned)__popc(walking) <= stop.active) break;
+#ifdef ZS_LZ_VOTE2   // two candidates per vote: the vote and its tests are a tenth of the kernel at level 6
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep)
+#endif
+        if (chain > 0) {
+            do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
+                const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
+                if (delta == 0) { chain = 0; break; }
+                dist += delta;
+                if (dist > max_back) { chain = 0; break; }
+                ci = (ci - delta) & (kRing - 1u);
+                if ((ring32(S, ci + woff) ^ wown) & wmask) {
+                    if (delta <= kDenseHop && best_len >= 3) {   // a run or a short period: is this a tie / an 8-byte match?
+                        const uint2 cw = ring64(S, ci);
+                        const uint32_t x0 = cw.x ^ pw.x, x1 = cw.y ^ pw.y;
+                        const unsigned m = x0 ? first_diff_byte(x0) : x1 ? 4u + first_diff_byte(x1) : 8u;
+                        if (m >= (best_len < 8u ? best_len : 8u)) chain -= chain >> 2;
+                    }
+                    break;
+                }
+                unsigned len = match_length(S, ci, pi, pw.x, pw.y, max_len);
+                if (len > max_len) len = max_len;
+                if (len > best_len) {
+                    // see search_position_sync: a good match in hand cuts the rest of the chain on dense chains and
+                    // inside a longer match
+                    if (best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
+                        const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
+                        if (interior || delta <= kDenseHop) chain >>= 2;
+                        if (interior && chain > kInteriorChain) chain = kInteriorChain;
+                    }
+                    best_len = len;
+                    best_dist = dist;
+                    if (len >= nice) { chain = 0; break; }
+                    woff = len - 3u; wmask = 0xffffffffu;
+                    wown = ring32(S, pi + woff);
+                } else if (len == best_len && delta <= kDenseHop) {
+                    chain -= chain >> 2;   // only with best_len == max_len's neighbours: a tie that passed the window
                 }
             } while (0);
             --chain;
@@ -678,6 +908,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
     if (a.debug >> 8) cfg.chain = a.debug >> 8;
 #endif
 
+#ifdef ZS_LZ_BULK
+    if (threadIdx.x == 0) mbar_init(&S.stage_bar, 1);   // published by the first __syncthreads of the segment loop
+#endif
     for (;;) {
         if (threadIdx.x == 0) S.seg = atomicAdd(a.seg_counter, 1u);
         __syncthreads();
@@ -691,6 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
         const uint32_t nc = c1 - c0;
 
         // fresh tables per segment: the output never depends on which CTA ran which segment
+        if (threadIdx.x == 0) S.claim[0] = 0;
         {
             uint4* z = reinterpret_cast<uint4*>(S.head);
             const unsigned nz = (sizeof(S.head) + sizeof(S.prev)) / sizeof(uint4);
@@ -721,17 +955,26 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
             rc.tail = tail < 0xffffffffull ? (uint32_t)tail : 0xffffffffu;
         }
         for (unsigned j = threadIdx.x; j <= nc; j += kThreads) S.bnd[j] = (uint32_t)(a.in_off[c0 + j] - off0) + rc.q_data;
-        uint64_t staged_end = prime0 & ~15ull;  // [staged_end - 64 KiB, staged_end) is in the ring
-        {   // look-ahead for the first two steps of the range
-            const uint64_t target = (prime0 + 2ull * kStep + kRingGuard + 15) & ~15ull;
-            stage_window(S, a, staged_end, target, threadIdx.x, kThreads);
-            staged_end = target;
-        }
+        // Staging addresses positions relative to base16 (the 16-byte line that holds the range's first byte):
+        // after iteration k the ring holds everything below stage_rel(k + 1) = q_prep + 3 steps + guard, rounded up.
+        const uint64_t base16 = prime0 & ~15ull;
+        const uint32_t p0lo = (uint32_t)prime0 & 15u;
+        const uint32_t safe_rel = [&] {   // first line past the end of the input, saturating
+            const uint64_t d = ((a.data_end + 15) & ~15ull) - base16;
+            return d < 0xfffffff0ull ? (uint32_t)d : 0xfffffff0u;
+        }();
+        // look-ahead for the first two steps of the range
+        stage_window(S, a, base16, base16 + ((p0lo + 2u * kStep + kRingGuard + 15u) & ~15u), threadIdx.x, kThreads);
         __syncthreads();
 
         const uint32_t n = rc.n;
         const uint32_t nsteps = (n + kStep - 1) / kStep;
         const uint32_t n_iter = nsteps + 6;
+        // The staging barrier completes one phase per step; a segment uses an even number of them (one empty phase
+        // more after an odd number of steps), so the parity to wait for is k & 1 in every segment.  (Re-initialising
+        // the barrier per segment -- mbarrier.inval + init -- was tried first: waits of later segments never returned.)
+        const uint32_t nwait = (nsteps + 1u) & ~1u;
+        (void)nwait;
         const uint32_t qd64 = rc.q_data & ~63u;   // the pair of batches that holds the first data position
         ParseState ps;
         ps.ppos = qd64; ps.skip = rc.q_data - qd64; ps.nsym = 0; ps.blk = 0; ps.blk_sym0 = 0; ps.blk_pos0 = rc.q_data;
@@ -758,23 +1001,39 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
             const unsigned s_link = s_ins == 0 ? 2u : s_ins - 1u;      // (k - 2) % 3
             if (wid == kWarpInsert) {
                 // Bytes the next iteration reads (prep of step k+1, look-ahead of the search of step
-                // k-2) replace positions 64 KiB older, which nobody reads any more.  The global
-                // loads are issued first and stored last so that their latency hides behind the
+                // k-2) replace positions 64 KiB older, which nobody reads any more.
+                const uint32_t stage_from = (p0lo + q_prep + 2u * kStep + kRingGuard + 15u) & ~15u;
+                const uint32_t stage_to = k < nsteps ? (p0lo + q_prep + 3u * kStep + kRingGuard + 15u) & ~15u : stage_from;
+#ifdef ZS_LZ_BULK
+                // The copy engine stages the readable part; it is started first and awaited last, so the
+                // transfer runs behind the table updates.
+                const uint32_t bulk_to = stage_to < safe_rel ? stage_to : safe_rel;
+                if (k < nwait && lane == 0) {
+                    unsigned total = 0;
+                    if (stage_from < bulk_to) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring slots were last written by ordinary stores
+                        // expect_tx is given the total first: a copy may complete before a later arrive
+                        const unsigned i0 = ((uint32_t)base16 + stage_from) & (kRing - 1u), nb = bulk_to - stage_from;
+                        total = nb;
+                        // the mirrored part: ring indices [0, kRingGuard) inside [i0, i0 + nb), before and after the wrap
+                        if (i0 < kRingGuard) total += (i0 + nb < kRingGuard ? nb : kRingGuard - i0);
+                        if (i0 + nb > kRing) total += (i0 + nb - kRing < kRingGuard ? i0 + nb - kRing : kRingGuard);
+                    }
+                    mbar_expect_tx(&S.stage_bar, total);
+                    if (total) bulk_stage(S, a.buf, base16 + stage_from, base16 + bulk_to);
+                }
+#else
+                // The global loads are issued first and stored last so that their latency hides behind the
                 // table updates.
                 constexpr int kStageVec = (kStep + 16 + 511) / 512;   // 16-byte vectors per lane and step
                 uint4 sv[kStageVec];
-                uint64_t stage_from = staged_end, stage_to = staged_end;
-                if (k < nsteps) {
-                    const uint64_t target = (prime0 + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
-                    if (target > staged_end) stage_to = target;
-                }
-                const uint64_t safe16 = (a.data_end + 15) & ~15ull;
 #pragma unroll
                 for (int v = 0; v < kStageVec; ++v) {
-                    const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
+                    const uint32_t pos = stage_from + 16u * (lane + 32 * v);
                     sv[v] = make_uint4(0, 0, 0, 0);
-                    if (pos < stage_to && pos < safe16) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + pos));
+                    if (pos < stage_to && pos < safe_rel) sv[v] = __ldg(reinterpret_cast<const uint4*>(a.buf + base16 + pos));
                 }
+#endif
                 if (k >= 1 && k - 1 < nsteps) {
                     const uint32_t p16 = rc.cb + q_prep - kStep;
                     const uint32_t* pw = S.prep + s_ins * kStep;
@@ -782,17 +1041,44 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
 #pragma unroll 8
                     for (int u = 0; u < kSearchWarps; ++u) head_exchange(S, p16 + 32u * u, pw[32 * u + lane], oh + 32 * u);
                 }
+#ifdef ZS_LZ_BULK
+                // past the end of the input the window reads as zeros (the last steps of the last segment only)
+                if (stage_to > safe_rel) {
+                    for (uint32_t pos = (stage_from > safe_rel ? stage_from : safe_rel) + 16u * lane; pos < stage_to; pos += 512u) {
+                        const unsigned idx = ((uint32_t)base16 + pos) & (kRing - 1u);
+                        *reinterpret_cast<uint4*>(S.ring + idx) = make_uint4(0, 0, 0, 0);
+                        if (idx < kRingGuard) *reinterpret_cast<uint4*>(S.ring + kRing + idx) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+#ifdef ZS_LZ_BULK_DEBUG   // a wait that does not end reports where it stands and gives up
+                if (k < nwait) {
+                    unsigned tries = 0, ok = 0;
+                    while (!ok && tries < 200000u) {
+                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                                     : "=r"(ok) : "r"(smem_addr(&S.stage_bar)), "r"(k & 1u) : "memory");
+                        ++tries;
+                    }
+                    if (!ok && lane == 0)
+                        printf("[lz77 bulk] wait timed out: cta %u seg %u k %u of %u from %u to %u bulk_to %u safe %u p0lo %u base16 %llu\n",
+                               blockIdx.x, seg, k, nsteps, stage_from, stage_to, bulk_to, safe_rel, p0lo, (unsigned long long)base16);
+                }
+#else
+                if (k < nwait) mbar_wait(&S.stage_bar, k & 1u);
+#endif
+#else
 #pragma unroll
                 for (int v = 0; v < kStageVec; ++v) {
-                    const uint64_t pos = stage_from + 16ull * (lane + 32 * v);
+                    const uint32_t pos = stage_from + 16u * (lane + 32 * v);
                     if (pos < stage_to) {
-                        const unsigned idx = (unsigned)pos & (kRing - 1u);
+                        const unsigned idx = ((uint32_t)base16 + pos) & (kRing - 1u);
                         *reinterpret_cast<uint4*>(S.ring + idx) = sv[v];
                         if (idx < kRingGuard) *reinterpret_cast<uint4*>(S.ring + kRing + idx) = sv[v];
                     }
                 }
                 // anything beyond kStageVec vectors per lane (never with the fixed 3-step look-ahead)
-                if (stage_to > stage_from + 512ull * kStageVec) stage_window(S, a, stage_from + 512ull * kStageVec, stage_to, lane, 32);
+                if (stage_to > stage_from + 512u * kStageVec)
+                    stage_window(S, a, base16 + stage_from + 512u * kStageVec, base16 + stage_to, lane, 32);
+#endif
             } else if (wid == kWarpParse) {
                 while (ps.ppos < r1) {
                     int np = (int)((r1 - ps.ppos + 63) / 64);
@@ -827,7 +1113,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
+#ifdef ZS_LZ_ENDWIN
+                            const uint32_t rr = search_lazy_endwin(S, cfg, stop, rc, q, cs, ce, live);
+#else
                             const uint32_t rr = search_position_sync(S, cfg, stop, rc, q, cs, ce, live);
+#endif
                             r = live ? rr : 0u;
                         } else
                         if (q >= rc.q_data && q < n) {
@@ -836,7 +1126,12 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
+#ifdef ZS_LZ_GREEDY_ENDWIN   // measured: the filter costs the greedy levels 7 % on text (chains of 4: nothing to filter)
+                            if constexpr (kMode == 2) r = search_position<2>(S, cfg, rc, q, cs, ce);
+                            else r = search_greedy_endwin(S, cfg, rc, q, cs, ce);
+#else
                             r = search_position<kMode == 1 ? 0 : kMode>(S, cfg, rc, q, cs, ce);
+#endif
                         }
                         if (q < n) S.res[res_slot(q)] = r;
                     }
@@ -845,6 +1140,30 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 // emits (one pair each): both are ~150 instructions per pair, so the halves stay balanced.
                 // (Claiming the pairs dynamically from a shared counter was measured: slower at level 1.)
                 constexpr unsigned kHalf = kSearchWarps / 2;
+#ifndef ZS_LZ_NO_CLAIM
+                // Lazy levels: the search of a batch takes anything from a few to 128 lock-step candidates, and the step
+                // ends with its slowest warp (ncu: the barrier is the first stall reason at level 6).  The resolve and
+                // emit pairs are therefore claimed from a counter by whoever is done searching: a warp that is late
+                // does none, the early ones share them.  (At the greedy levels the searches are short and even and the
+                // static split below is faster.)
+                if constexpr (kMode == 1) {
+                    const unsigned nr = r0 > r1 ? (r0 - r1 + 63u) >> 6 : 0u, ne = r2 > r3 ? (r2 - r3 + 63u) >> 6 : 0u;
+                    if (threadIdx.x == 0) S.claim[(k + 1u) & 1u] = 0;   // next iteration's counter: nobody touches it now
+                    for (;;) {
+                        unsigned item = 0;
+                        if (lane == 0) item = atomicAdd(&S.claim[k & 1u], 1u);
+                        item = __shfl_sync(ZS_FULL_MASK, item, 0);
+                        if (item >= nr + ne) break;
+                        if (item < nr) {
+                            resolve_pair<kMode>(S, cfg, n, r1 + 64u * item);
+                        } else {
+                            const uint32_t q0 = r3 + 64u * (item - nr);
+                            emit_batch(S, a, off0, n, q0);
+                            if (q0 + 32 < r2) emit_batch(S, a, off0, n, q0 + 32);
+                        }
+                    }
+                } else
+#endif
                 if (wid < kHalf) {
                     // resolve the pairs whose successor was searched before this iteration
                     for (uint32_t q0 = r1 + 64u * wid; q0 < r0; q0 += 64u * kHalf) resolve_pair<kMode>(S, cfg, n, q0);
@@ -867,10 +1186,6 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 }
             }
 #endif
-            if (k < nsteps) {
-                const uint64_t target = (prime0 + (uint64_t)q_prep + 3ull * kStep + kRingGuard + 15) & ~15ull;
-                if (target > staged_end) staged_end = target;
-            }
             // the search of step k-3 ran in this iteration
             if (k >= 3) searched = searched + kStep < n ? searched + kStep : n;
             q_prep += kStep;
