@@ -10,7 +10,6 @@ corpus = importlib.import_module("zlib-streams-ts_b200.corpus")
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ctx = B.default_context(0)
 host = corpus.text_numpy(mib << 20, 5)
-bench.stream_api_bench(ctx, host[: 4 << 20], capi)   # warm-up (allocations, tables)
 ctx.profile(True); ctx.profile_read()
 t0 = time.perf_counter()
 out = bench.stream_api_bench(ctx, host, capi)

@@ -22,6 +22,7 @@ constexpr uint64_t kParMinInput = 128u << 10;   // shorter streams are decoded b
 
 void* zs_scratch_get(zs_ctx* ctx, int slot, size_t bytes) {
     zs_scratch& s = ctx->scr[slot];
+    if (slot == SCR_H_OUT) ctx->h_out_gen++;
     if (bytes == 0) bytes = 16;
     if (s.cap >= bytes) return s.p;
     if (s.p) {
@@ -173,6 +174,7 @@ int zs_ctx_profile_read(zs_ctx* ctx, char* buf, uint64_t cap) {
     for (auto& r : pr->recs) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
+        if (getenv("ZS_PROF_LIST")) fprintf(stderr, "[zs prof] %s %.3f ms\n", r.name, ms);   // every launch, in order
         bool found = false;
         for (auto& g : agg)
             if (!strcmp(g.name, r.name)) { g.ms += ms; g.n++; found = true; break; }
@@ -798,6 +800,7 @@ int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
     if (in_total) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, in_total, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ioff, in_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_ooff, out_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_inflate_out = n == 1 ? d_out + out_off[0] : nullptr;
     if (n == 1) {
         ctx->par.on = true;
         ctx->par.in_off = in_off[0]; ctx->par.in_len = in_off[1] - in_off[0];

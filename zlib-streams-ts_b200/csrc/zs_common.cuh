@@ -34,6 +34,8 @@ struct zs_ctx {
     bool inflate_resume = false;
     uint64_t inflate_start_bit = 0;
     uint64_t inflate_mark[2] = {0, 0};
+    uint64_t h_out_gen = 0;                      // bumped whenever the host-path output scratch is handed out again
+    const uint8_t* last_inflate_out = nullptr;   // device copy of the output of the last one-stream zs_inflate_batch (valid until the next call)
     uint32_t seg_hint = 0;   // segment size (chunks) forced for the next deflate calls (slices of one batch)
     uint32_t inflate_batch_n = 0;   // streams of the whole batch while its slices are decoded (kernel choice), 0 = not sliced
     // one-stream inflate with sizes known on the host: lets zs_inflate_batch_dev use the segment-parallel decoder

@@ -18,6 +18,7 @@
 //    resumes there in raw mode.  Bytes decoded so far are handed out immediately, Z_STREAM_END gives
 //    back the unused input; the wrapper trailer of a stream decoded in several attempts is checked here.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -41,8 +42,45 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// Host byte buffer that grows without initialising what it grows by (std::vector::resize zero-fills: the
+// inflate shim asks for four times its input as output room on every attempt).
+struct RawBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { free(p); }
+    uint8_t* data() { return p; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+    bool resize(size_t want) {
+        if (want > cap) {
+            size_t c = cap + (cap >> 1);
+            if (c < want) c = want;
+            uint8_t* q = (uint8_t*)realloc(p, c ? c : 1);
+            if (!q) return false;
+            p = q;
+            cap = c;
+        }
+        n = want;
+        return true;
+    }
+    void clear() { n = 0; }
+    void erase_front(size_t k) {
+        if (k >= n) { n = 0; return; }
+        memmove(p, p + k, n - k);
+        n -= k;
+    }
+};
+
 enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
 constexpr size_t kPartThreshold = 16u << 20;
+// inflate: streams shorter than this are decoded on every call, so the call that brings the last byte of the
+// stream returns Z_STREAM_END and hands back what follows it through avail_in, exactly like the reference.
+// Longer streams are decoded in batches (see zs_stream_inflate): the end may be found in a later call, when
+// input that arrived earlier can only be accounted for in total_in ("Streaming inflate").
+constexpr size_t kEveryCallBelow = 256u << 10;
 
 struct DeflateState {
     uint32_t magic = 0x44464c54;  // 'DFLT'
@@ -71,7 +109,9 @@ struct InflateState {
     // starts; the blocks before that point are final, their input is dropped and the next attempt
     // resumes there in raw mode with the last 64 KiB of output as its window.
     std::vector<uint8_t> in;        // input not yet consumed: from the byte that holds the next block header on
-    std::vector<uint8_t> out;       // output of the latest attempt (from the resume point)
+    RawBuf out;                     // output of the latest attempt (from the resume point)
+    bool out_on_device = false;     // `out` is byte for byte what the last attempt left on the device ...
+    uint64_t out_gen = 0;           // ... as long as the context has not handed that scratch out again (h_out_gen)
     std::vector<uint8_t> ready;     // decoded, not yet delivered
     std::vector<uint8_t> hist;      // window: the last <= 64 KiB of final output, or the preset dictionary
     std::vector<uint8_t> leftover;  // input after the end of the stream that could not be handed back
@@ -519,9 +559,17 @@ static void fill_gz_header(InflateState* st) {
 // Everything of `out` below `upto` that has not been queued for delivery yet goes to `ready`.
 static void push_ready(InflateState* st, size_t upto) {
     if (upto > st->out_pushed) {
-        st->ready.insert(st->ready.end(), st->out.begin() + st->out_pushed, st->out.begin() + upto);
+        st->ready.insert(st->ready.end(), st->out.data() + st->out_pushed, st->out.data() + upto);
         st->out_pushed = upto;
     }
+}
+
+// Running checksum continued over the first n bytes of `out`.  The attempt that produced them has just run: its
+// output is still on the device (ctx->last_inflate_out), so the bytes are not uploaded a second time.
+static int out_checksum(InflateState* st, size_t n, uint32_t* result) {
+    const int kind = st->trailer == 1 ? 0 : 1;
+    if (st->out_on_device && st->out_gen == st->ctx->h_out_gen && st->ctx->last_inflate_out) return zs_checksum_dev(st->ctx, kind, st->ctx->last_inflate_out, n, st->run_check, result);
+    return zs_checksum(st->ctx, kind, st->out.data(), n, st->run_check, result);
 }
 
 // The blocks before (mark_bit, mark_out) are final: fold their output into the running checksum and
@@ -529,12 +577,13 @@ static void push_ready(InflateState* st, size_t upto) {
 static int advance_to_mark(InflateState* st, uint64_t mark_bit, uint64_t mark_out) {
     if (mark_out) {
         push_ready(st, (size_t)mark_out);
-        int rc = zs_checksum(st->ctx, st->trailer == 1 ? 0 : 1, st->out.data(), mark_out, st->run_check, &st->run_check);
+        int rc = out_checksum(st, (size_t)mark_out, &st->run_check);
         if (rc != ZS_OK) return rc;
         st->run_len += mark_out;
-        st->hist.insert(st->hist.end(), st->out.begin(), st->out.begin() + (size_t)mark_out);
+        st->hist.insert(st->hist.end(), st->out.data(), st->out.data() + (size_t)mark_out);
         if (st->hist.size() > 65536) st->hist.erase(st->hist.begin(), st->hist.end() - 65536);
-        st->out.erase(st->out.begin(), st->out.begin() + (size_t)mark_out);
+        st->out.erase_front((size_t)mark_out);
+        st->out_on_device = false;
         st->out_pushed -= (size_t)mark_out;
     }
     const size_t bytes = (size_t)(mark_bit >> 3);
@@ -551,7 +600,7 @@ static int finish_stream(InflateState* st) {
     if (st->in.size() < st->trailer_pos + T) { st->await_trailer = true; return ZS_OK; }
     st->await_trailer = false;
     uint32_t total = st->run_check;
-    int rc = zs_checksum(st->ctx, st->trailer == 1 ? 0 : 1, st->out.data(), st->out.size(), st->run_check, &total);
+    int rc = out_checksum(st, st->out.size(), &total);
     if (rc != ZS_OK) return rc;
     const uint64_t total_len = st->run_len + st->out.size();
     const uint8_t* t = st->in.data() + st->trailer_pos;
@@ -580,7 +629,7 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
         const uint64_t in_off[2] = {0, st->in.size()}, out_off[2] = {0, st->out_cap_hint};
         // `out` is rebuilt by every attempt; what was queued from it stays in `ready`
         if (st->out_cap_hint < 4 * st->in.size()) st->out_cap_hint = 4 * st->in.size();   // a typical ratio: fewer re-decodes
-        st->out.resize(st->out_cap_hint);
+        if (!st->out.resize(st->out_cap_hint)) return ZS_MEM_ERROR;
         uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->hist.size()};
         uint32_t check = 0;
         int32_t status = 0, detail = 0;
@@ -597,6 +646,8 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
         }
         const uint64_t mark_bit = ctx->inflate_mark[0], mark_out = ctx->inflate_mark[1];
         st->out.resize(out_len);
+        st->out_on_device = true;
+        st->out_gen = ctx->h_out_gen;
         if (status == ZS_STREAM_END) {
             if (!st->body) {
                 // the whole stream in one attempt: wrapper and trailer were checked on the device
@@ -678,7 +729,7 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
             const size_t seen = (size_t)strm->total_in;
             size_t grain = seen;
             if (grain > (64u << 20)) grain = 64u << 20;
-            if (seen < (64u << 10)) st->next_attempt = st->in.size() + 1;
+            if (seen < kEveryCallBelow) st->next_attempt = st->in.size() + 1;
             else st->next_attempt = st->in.size() + (grain > st->in.size() / 2 ? grain : st->in.size() / 2);
             if (st->need_dict) {
                 strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
