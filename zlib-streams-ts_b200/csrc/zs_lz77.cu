@@ -63,6 +63,7 @@ constexpr int kWarpInsert = kSearchWarps + 1;
 constexpr int kThreads = 32 * (kSearchWarps + 2);
 constexpr int kStep = 32 * kSearchWarps;               // positions per pipeline step
 constexpr unsigned kMaxDist = 32768u - 2u * kStep;      // see header comment
+constexpr unsigned kNoPrev = 0xffffu;                   // ZS_LZ_PREV_DELTA: prev[] entry of a position without predecessor
 constexpr unsigned kSymLimit = 16383u;                  // symbols per block, deflate.ts:336
 constexpr unsigned kTooFar = 4096u;                     // deflate/constants.ts (TOO_FAR)
 constexpr unsigned kHashBits = ZS_HASH_BITS;
@@ -278,6 +279,16 @@ __device__ __forceinline__ void link_batch(Smem& S, const RangeCtx& c, uint32_t 
     if (w & PREP_VALID) {
         const uint32_t q = q0 + zs_lane();
         const unsigned p16 = (c.cb + q) & 0xffffu;
+#ifdef ZS_LZ_PREV_DELTA
+        unsigned hop = kNoPrev;
+        if (w & PREP_HAS_PRED) {
+            hop = zs_lane() - ((w >> 16) & 31u);
+        } else {
+            const unsigned delta = (p16 - old) & 0xffffu;
+            if (delta != 0 && delta <= kMaxDist && delta <= q + c.pre) hop = delta;
+        }
+        S.prev[p16 & 32767u] = (uint16_t)hop;
+#else
         unsigned pred = p16;
         if (w & PREP_HAS_PRED) {
             pred = (c.cb + q0 + ((w >> 16) & 31u)) & 0xffffu;
@@ -286,8 +297,31 @@ __device__ __forceinline__ void link_batch(Smem& S, const RangeCtx& c, uint32_t 
             if (delta != 0 && delta <= kMaxDist && delta <= q + c.pre) pred = (p16 - delta) & 0xffffu;
         }
         S.prev[p16 & 32767u] = (uint16_t)pred;
+#endif
     }
 }
+
+// One hop along the hash chain: from ring index ci to its predecessor, `dist` = distance from the searching position.
+// Returns false when the chain ends (no predecessor, or further back than max_back).
+#ifdef ZS_LZ_PREV_DELTA
+// prev[] holds the hop itself (0xffff = none: no distance survives adding it), so a hop is one load, one add, one test.
+__device__ __forceinline__ bool chain_hop(const Smem& S, unsigned& ci, unsigned& dist, unsigned max_back, unsigned& delta) {
+    delta = S.prev[ci & 32767u];
+    dist += delta;
+    if (dist > max_back) return false;
+    ci = (ci - delta) & (kRing - 1u);
+    return true;
+}
+#else
+__device__ __forceinline__ bool chain_hop(const Smem& S, unsigned& ci, unsigned& dist, unsigned max_back, unsigned& delta) {
+    delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
+    if (delta == 0) return false;
+    dist += delta;
+    if (dist > max_back) return false;
+    ci = (ci - delta) & (kRing - 1u);
+    return true;
+}
+#endif
 
 // ---- stage 3: search (wide), one lane per position -----------------------------------------------
 // All arithmetic is on 16-bit ring indices and 32-bit distances (the ring is a multiple of the
@@ -379,11 +413,8 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     unsigned best_len = 2, best_dist = 0, best_ci = pi;
     unsigned ci = pi, dist = 0;
     for (int chain = cfg.chain; chain > 0; --chain) {
-        const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
-        if (delta == 0) break;
-        dist += delta;
-        if (dist > max_back) break;
-        ci = (ci - delta) & (kRing - 1u);
+        unsigned delta;
+        if (!chain_hop(S, ci, dist, max_back, delta)) break;
         uint32_t x = ring32(S, ci) ^ pw0;
         if ((x & 0xffffffu) != 0) continue;  // hash collision
         unsigned len;
@@ -457,11 +488,8 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
         if (it >= stop.after && (unsigned)__popc(walking) <= stop.active) break;
         if (chain > 0) {
             do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
-                const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
-                if (delta == 0) { chain = 0; break; }
-                dist += delta;
-                if (dist > max_back) { chain = 0; break; }
-                ci = (ci - delta) & (kRing - 1u);
+                unsigned delta;
+                if (!chain_hop(S, ci, dist, max_back, delta)) { chain = 0; break; }
                 uint32_t x = ring32(S, ci) ^ pw0;
                 if ((x & 0xffffffu) != 0) break;  // hash collision
                 unsigned len;
@@ -564,11 +592,8 @@ __device__ __forceinline__ uint32_t search_greedy_endwin(const Smem& S, const Le
     unsigned woff = 0;                       // the window is bytes [woff, woff + 4) = the four bytes ending at best_len
     uint32_t wown = pw.x, wmask = 0xffffffu; // (three bytes while there is no match yet)
     for (int chain = cfg.chain; chain > 0; --chain) {
-        const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
-        if (delta == 0) break;
-        dist += delta;
-        if (dist > max_back) break;
-        ci = (ci - delta) & (kRing - 1u);
+        unsigned delta;
+        if (!chain_hop(S, ci, dist, max_back, delta)) break;
         if ((ring32(S, ci + woff) ^ wown) & wmask) continue;   // cannot beat best_len (or a hash collision)
 #ifdef ZS_LZ_DEFER_EXT
         // Inside the loop a compare goes as far as nice_length only (no further than 8 bytes at level 1): a match
@@ -636,11 +661,8 @@ __device__ __forceinline__ uint32_t search_lazy_endwin(const Smem& S, const Leve
 #endif
         if (chain > 0) {
             do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
-                const unsigned delta = (ci - S.prev[ci & 32767u]) & 0xffffu;
-                if (delta == 0) { chain = 0; break; }
-                dist += delta;
-                if (dist > max_back) { chain = 0; break; }
-                ci = (ci - delta) & (kRing - 1u);
+                unsigned delta;
+                if (!chain_hop(S, ci, dist, max_back, delta)) { chain = 0; break; }
                 if ((ring32(S, ci + woff) ^ wown) & wmask) {
                     if (delta <= kDenseHop && best_len >= 3) {   // a run or a short period: is this a tie / an 8-byte match?
                         const uint2 cw = ring64(S, ci);
@@ -928,7 +950,15 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
         {
             uint4* z = reinterpret_cast<uint4*>(S.head);
             const unsigned nz = (sizeof(S.head) + sizeof(S.prev)) / sizeof(uint4);
+#ifdef ZS_LZ_PREV_DELTA
+            const unsigned nh = sizeof(S.head) / sizeof(uint4);   // prev[] follows head[]: "no predecessor" is 0xffff there
+            for (unsigned i = threadIdx.x; i < nz; i += kThreads) {
+                const unsigned v = i < nh ? 0u : 0xffffffffu;
+                z[i] = make_uint4(v, v, v, v);
+            }
+#else
             for (unsigned i = threadIdx.x; i < nz; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+#endif
         }
         // The range starts with the dictionary (deflateSetDictionary, deflate.ts:367-424): the
         // <= 32 KiB before the first chunk go through prep + insert + link only.
