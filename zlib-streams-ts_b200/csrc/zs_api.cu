@@ -370,10 +370,34 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     seg = seg < 1 ? 1 : seg > 16 ? 16 : seg;
     const uint32_t n_seg = (n_chunks + seg - 1) / seg;
     const uint32_t wave = (uint32_t)ctx->sm_count;
-    const uint32_t waves_per_slice = (n_seg + wave * kMaxSlices - 1) / (wave * kMaxSlices);
-    const uint32_t slice_chunks = seg * wave * (waves_per_slice < 1 ? 1 : waves_per_slice);
-    const int n_slices = (int)((n_chunks + slice_chunks - 1) / slice_chunks);
-    if (n_slices > kMaxSlices) return bad_arg(ctx, "deflate: internal slicing error");
+    uint32_t waves_per_slice = (n_seg + wave * kMaxSlices - 1) / (wave * kMaxSlices);
+    if (waves_per_slice < 1) waves_per_slice = 1;
+    if (const char* e = getenv("ZS_SLICE_WAVES")) {   // A/B hook: at least this many waves per slice
+        const uint32_t w = (uint32_t)atoi(e);
+        if (w > waves_per_slice) waves_per_slice = w;
+    }
+    // Slice s covers chunks [cb[s], cb[s + 1]).  Greedy levels: equal slices of whole waves (measured on configs[1]:
+    // one wave per slice 45.8 ms, two 47.2, three 49.5 -- the searches are even, so a one-wave launch loses little and
+    // the first copy is short).  Lazy levels: the search time of a segment varies, a one-wave launch is as slow as its
+    // slowest segment (configs[2] shape, 1 GiB: device 68.9 ms, five one-wave slices 95 ms), so the slices GROW -- one
+    // wave first, so that the kernels start as soon as a sixteenth of the input is there, then two, four, ... waves,
+    // by which time the copies (three times as fast as the kernels) are far ahead.
+    uint32_t cb[kMaxSlices + 1];
+    int n_slices = 0;
+    cb[0] = 0;
+    {
+        const bool grow = level >= 4 && !getenv("ZS_SLICE_WAVES");
+        uint32_t w = waves_per_slice;
+        while (cb[n_slices] < n_chunks) {
+            if (n_slices >= kMaxSlices) return bad_arg(ctx, "deflate: internal slicing error");
+            uint64_t next = (uint64_t)cb[n_slices] + (uint64_t)seg * wave * w;
+            if (next > n_chunks || n_slices + 1 == kMaxSlices) next = n_chunks;
+            cb[++n_slices] = (uint32_t)next;
+            if (grow) w *= 2;
+        }
+    }
+    uint32_t slice_chunks = 0;   // the largest slice: sizes the per-slice output regions
+    for (int i = 0; i < n_slices; i++) slice_chunks = cb[i + 1] - cb[i] > slice_chunks ? cb[i + 1] - cb[i] : slice_chunks;
     if (!ctx->s_in) {
         ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         ZS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -412,8 +436,8 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     if (history) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in - history, in - history, history, cudaMemcpyHostToDevice, ctx->s_in));
     const uint32_t part_mask = ZS_FLAG_NOT_FIRST | ZS_FLAG_NOT_LAST;
     for (int s = 0; s < n_slices; s++) {
-        const uint32_t c0 = (uint32_t)s * slice_chunks;
-        const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+        const uint32_t c0 = cb[s];
+        const uint32_t nc = cb[s + 1] - cb[s];
         const uint64_t b0 = (uint64_t)c0 * chunk_size;
         const uint64_t len = (b0 + (uint64_t)nc * chunk_size <= in_len) ? (uint64_t)nc * chunk_size : in_len - b0;
         if (len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + b0, in + b0, len, cudaMemcpyHostToDevice, ctx->s_in));
@@ -445,8 +469,8 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     bool have_check = false;
     int rc_final = ZS_OK;
     for (int s = 0; s < n_slices; s++) {
-        const uint32_t c0 = (uint32_t)s * slice_chunks;
-        const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+        const uint32_t c0 = cb[s];
+        const uint32_t nc = cb[s + 1] - cb[s];
         const uint64_t b0 = (uint64_t)c0 * chunk_size;
         const uint64_t len = (b0 + (uint64_t)nc * chunk_size <= in_len) ? (uint64_t)nc * chunk_size : in_len - b0;
         ZS_CUDA_TRY(ctx, cudaEventSynchronize(ev_r[s]));
@@ -493,8 +517,8 @@ static int deflate_batch_pipelined(zs_ctx* ctx, const uint8_t* in, uint64_t in_l
     if (out_off) {
         const uint64_t unit = stitched ? 8 : 1;   // STITCHED reports bit offsets
         for (int s = 0; s < n_slices; s++) {
-            const uint32_t c0 = (uint32_t)s * slice_chunks;
-            const uint32_t nc = c0 + slice_chunks <= n_chunks ? slice_chunks : n_chunks - c0;
+            const uint32_t c0 = cb[s];
+            const uint32_t nc = cb[s + 1] - cb[s];
             for (uint32_t i = 0; i < nc; i++) out_off[c0 + i] += base[s] * unit;
         }
         out_off[n_chunks] = host_off * unit;
