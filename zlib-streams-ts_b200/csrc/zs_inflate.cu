@@ -18,6 +18,9 @@
 #include "zs_inflate_common.cuh"
 
 namespace {
+// ceil(2^16 / d) for d = 1 .. 31 (index 0 unused): lane % d == lane - d * ((lane * c_inv16[d]) >> 16) for lane < 32
+__constant__ uint32_t c_inv16[32] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
+
 
 using namespace zsinf;
 
@@ -218,6 +221,12 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                     uint32_t out_rem = out_left > 0xffffffffull ? 0xffffffffu : (uint32_t)out_left;
                     uint8_t* wp = out + op;
                     uint32_t made = 0;     // bytes written by the fast path since `op` was last updated
+                    // How far back a match may reach, in 32 bits: what has been produced (own0) plus the dictionary
+                    // (back0), both capped far above the largest distance (65538).  `made` stays below 2^32 - 2^21
+                    // in any stream shorter than 4 GiB; beyond that a wrapped sum sends the pair to the careful loop,
+                    // which decides with 64-bit arithmetic.
+                    const uint32_t own0 = op < (1u << 20) ? (uint32_t)op : (1u << 20);
+                    const uint32_t back0 = own0 + (dict_len < (1u << 20) ? (uint32_t)dict_len : (1u << 20));
                     // input window: the 128 bytes from the current position, one word per lane (two coalesced
                     // loads and a funnel shift per lane when the position is not word aligned); a refill is a
                     // register shuffle.  woff = offset of the next unread byte inside the window, a multiple of 4.
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         }
                         xb = E_OP(here) & 15u;
                         const unsigned dist = E_VAL(here) + (((unsigned)(br.hold >> used)) & ((1u << xb) - 1u));
-                        if ((E_OP(here) & 64u) || (uint64_t)dist > op + made + dict_len || len > out_rem) {
+                        if ((E_OP(here) & 64u) || dist > back0 + made || len > out_rem) {
                             // invalid distance code, a distance too far back, or a match that does not fit: undo the pair
                             br.hold = hold0; br.bits = bits0;
                             win_base = wb0; woff = woff0;
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                         __syncwarp();
                         const uint8_t* sp = wp + made - dist;
                         uint8_t* dp = wp + made;
-                        if ((uint64_t)dist > op + made) {
+                        if (dist > own0 + made) {
                             // the match starts in the preset dictionary (inflate.ts:951-975)
                             const int64_t s0 = (int64_t)(op + made) - (int64_t)dist;
                             for (unsigned j = lane; j < len; j += 32) {
@@ -300,7 +309,10 @@ __global__ void __launch_bounds__(kWarps * 32) inflate_kernel(zs_inflate_args a)
                             }
                             __syncwarp();
                         } else if (len <= 32u) {
-                            if (lane < len) pend_v = sp[dist >= len ? lane : lane % dist];
+                            // lane % dist for an overlapping copy (dist < len <= 32) without the division: dist is
+                            // warp-uniform, so the reciprocal is one constant-memory read (ceil(2^16 / dist), exact for
+                            // lane < 32); the generic 32-bit modulo was 9 % of this kernel's instructions
+                            if (lane < len) pend_v = sp[dist >= len ? lane : lane - dist * ((lane * c_inv16[dist]) >> 16)];
                             pend_dp = dp;
                             pend_n = len;
                         } else if (dist >= len) {

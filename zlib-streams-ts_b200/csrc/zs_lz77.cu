@@ -13,8 +13,10 @@
 // Work decomposition (B200: 148 SMs, 227 KB shared memory per CTA):
 //   * one persistent CTA (1024 threads) per SM pulls *segments* (runs of consecutive chunks) from
 //     an atomic counter.  Everything the per-byte loop touches lives in shared memory: a 64 KiB
-//     ring of the window (staged from HBM once, 16 bytes per lane, coalesced), the hash-chain
-//     tables prev[32768] (16-bit positions like the reference's) and head[16384] (one bit less than
+//     ring of the window (staged from HBM once: the first look-ahead of a segment with 16-byte
+//     loads, every step after that by the copy engine -- 1-D cp.async.bulk on an mbarrier), the
+//     hash-chain tables prev[32768] (16-bit hop distances to the previous position with the same
+//     hash; the reference stores positions) and head[16384] (one bit less than
 //     the reference's hash so that 30 wide warps fit; measured cost: +0.8 % size at level 6), and
 //     ~60 KB of rings between the pipeline stages.  Tables and ring are carried from chunk to chunk
 //     inside a segment, so dictionary priming costs one 32 KiB insert-only pass per segment.
@@ -31,10 +33,15 @@
 //        search  (wide) : one lane per position walks that position's chain (<= max_chain
 //                         candidates, compares in the shared-memory ring, 16-bit ring indices);
 //                         every position is searched speculatively, which is what makes the
-//                         chain walk 960-wide;
+//                         chain walk 960-wide.  Greedy levels: compares stop at nice_length inside
+//                         the loop, the winners are extended together behind it.  Lazy levels: the
+//                         batch walks in lock step with a straggler stop, and a candidate is first
+//                         tested on the four bytes that end at index best_len;
 //        resolve (wide) : greedy / lazy rule per position, 5 rounds of pointer doubling per batch
 //                         (for every possible entry lane: visited positions, exit, symbol count),
-//                         then two adjacent batches are composed into one 64-position hop;
+//                         then two adjacent batches are composed into one 64-position hop (lazy
+//                         levels: resolve and emit pairs are claimed from a counter by the warps
+//                         that are done searching);
 //        parse   (thin) : chains the 64-position hops with register shuffles (entry of the next
 //                         hop = exit of this one), counts symbols, cuts blocks every <= 16383
 //                         symbols (lit_bufsize - 1, deflate.ts:323,336);
@@ -121,7 +128,7 @@ struct LzArgs {
     uint32_t* blk_desc;
     uint32_t* seg_counter;
     int debug;                 // ZS_LZ_PROF builds: chain override in bits 8..
-    unsigned stop_after, stop_active;   // lazy levels: straggler stop of the chain walk (search_position_sync)
+    unsigned stop_after, stop_active;   // lazy levels: straggler stop of the chain walk (search_lazy_endwin)
 };
 
 #ifdef ZS_LZ_PROF
@@ -381,7 +388,7 @@ __device__ __forceinline__ unsigned match_length(const Smem& S, unsigned ci, uns
 }
 
 // [cs, ce) is the chunk that holds q.
-// kMode: 0 greedy levels (1-3), 2 Z_RLE.  (The lazy levels 4-9 use search_position_sync below.)
+// kMode: 0 greedy levels (1-3), 2 Z_RLE.  (The lazy levels 4-9 use search_lazy_endwin below.)
 // Work bounds of the lazy levels on periodic data: a chain is "dense" when the hop to the candidate is at most
 // kDenseHop positions -- runs and short periods, not ordinary text or DNA-like data, whose ties and good
 // matches must not cut the search short (measured: +5.8 % size on a 4-letter alphabet at level 6 when they did).
@@ -390,7 +397,7 @@ constexpr int kInteriorChain = 16;      // candidates left once a good match tur
 template <int kMode>
 __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
                                                     uint32_t cs, uint32_t ce) {
-    static_assert(kMode == 0 || kMode == 2, "levels 4-9 go through search_position_sync");
+    static_assert(kMode == 0 || kMode == 2, "levels 4-9 go through search_lazy_endwin");
     const uint32_t room = ce - q;
     const unsigned max_len = room < 258u ? room : 258u;
     const unsigned pi = (c.cb + q) & (kRing - 1u);
@@ -463,7 +470,7 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
     return lit | (best_len << 15) | best_dist;
 }
 
-// The lazy levels' chain walk, warp-synchronous with a straggler stop.  All 32 lanes of the batch run the
+// The lazy levels' chain walk is warp-synchronous with a straggler stop.  All 32 lanes of the batch run the
 // candidate loop in lock step; once at least `stop.after` candidates have been visited and at most
 // `stop.active` lanes are still walking, the batch stops and those lanes keep the best match they have.  A
 // lone long chain otherwise holds up its warp and, through the step barrier, the whole CTA.  Modelled first
@@ -471,100 +478,9 @@ __device__ __forceinline__ uint32_t search_position(const Smem& S, const LevelCf
 // level 9 5.3 -> 12.9 GB/s, level 6 11.3 -> 13.5 GB/s, text level 6 11.0 -> 13.1 GB/s for +0.4 % size on text
 // (worst of eight data kinds: +1.65 % against zlib).  The vote is taken on well defined per-lane state, so the
 // result does not depend on scheduling.
-// Same matching rules as search_position; `live` = the lane holds a data position of the range.
 struct StopCfg { unsigned after, active; };
-__device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const LevelCfg& cfg, const StopCfg stop, const RangeCtx& c,
-                                                         uint32_t q, uint32_t cs, uint32_t ce, bool live) {
-    const uint32_t room = live ? ce - q : 0u;
-    const unsigned max_len = room < 258u ? room : 258u;
-    const unsigned pi = (c.cb + q) & (kRing - 1u);
-    uint32_t pw0 = 0, pw1 = 0;
-    if (live) { pw0 = ring32(S, pi); pw1 = ring32(S, pi + 4); }
-    const uint32_t lit = (pw0 & 0xffu) << 24;
-    const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
-    const uint32_t back = c.cross ? q + c.pre : q - cs;
-    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
-    unsigned best_len = 2, best_dist = 0;
-    unsigned ci = pi, dist = 0;
-    int chain = (live && max_len >= 3) ? cfg.chain : 0;
-    for (unsigned it = 0;; ++it) {
-        const unsigned walking = __ballot_sync(ZS_FULL_MASK, chain > 0);
-        if (walking == 0) break;
-        if (it >= stop.after && (unsigned)__popc(walking) <= stop.active) break;
-        if (chain > 0) {
-            do {   // one candidate; `break` = next candidate, chain = 0 = this lane is done
-                unsigned delta;
-                if (!chain_hop(S, ci, dist, max_back, delta)) { chain = 0; break; }
-                uint32_t x = ring32(S, ci) ^ pw0;
-                if ((x & 0xffffffu) != 0) break;  // hash collision
-                unsigned len;
-                if (x) {
-                    len = 3;
-                } else {
-                    x = ring32(S, ci + 4) ^ pw1;
-                    if (x) {
-                        len = 4 + first_diff_byte(x);
-                    } else {
-                        // Eight bytes match.  A candidate that cannot beat the best match is dropped after one
-                        // more byte (longest_match's scan_end test, deflate.ts:1063-1081): without this the tail of
-                        // a run, where every candidate ties, costs max_chain full compares per position.
-                        if (best_len >= 8 && S.ring[ci + best_len] != S.ring[pi + best_len]) {
-                            if (delta <= kDenseHop) chain -= chain >> 2;
-                            break;
-                        }
-                        len = 8;
-                        unsigned aa = (ci + 8u) & ~3u, ab = (pi + 8u) & ~3u;
-                        const unsigned sa = ((ci + 8u) & 3u) * 8u, sb = ((pi + 8u) & 3u) * 8u;
-                        uint32_t a0 = *reinterpret_cast<const uint32_t*>(S.ring + aa);
-                        uint32_t b0 = *reinterpret_cast<const uint32_t*>(S.ring + ab);
-                        while (len < max_len) {
-                            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 4);
-                            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(S.ring + aa + 8);
-                            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 4);
-                            const uint32_t b2 = *reinterpret_cast<const uint32_t*>(S.ring + ab + 8);
-                            const uint32_t yl = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
-                            const uint32_t yh = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
-                            if (yl | yh) {
-                                len += yl ? first_diff_byte(yl) : 4 + first_diff_byte(yh);
-                                break;
-                            }
-                            a0 = a2; b0 = b2;
-                            aa += 8; ab += 8;
-                            len += 8;
-                        }
-                    }
-                }
-                if (len > max_len) len = max_len;
-                if (len > best_len) {
-                    // With a good match in hand the rest of the chain gets a quarter of the budget (the rule
-                    // longest_match applies when the previous position's match was good, deflate.ts:1069-1071)
-                    // -- here only where the reference would not be searching at all: on a dense chain (a run)
-                    // or when the match also extends backwards, i.e. q lies inside a longer match that started
-                    // earlier (deflate_slow skips the bytes a match covers; the speculative search cannot skip
-                    // them, but it stops after kInteriorChain more candidates).
-                    if (best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
-                        const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
-                        if (interior || delta <= kDenseHop) chain >>= 2;
-                        if (interior && chain > kInteriorChain) chain = kInteriorChain;
-                    }
-                    best_len = len;
-                    best_dist = dist;
-                    if (len >= nice) chain = 0;
-                } else if (len == best_len && delta <= kDenseHop) {
-                    // A candidate that ties with the best match on a dense chain means periodic data (a run): the
-                    // rest of the chain is more of the same.  Every tie takes a quarter off the remaining budget.
-                    chain -= chain >> 2;
-                }
-            } while (0);
-            --chain;
-        }
-    }
-    if (best_len < c.min_len) return lit;
-    if (best_len == 3 && best_dist > kTooFar) return lit;   // deflate.ts:1381-1387
-    return lit | (best_len << 15) | best_dist;
-}
 
-// ---- the same two searches with the end-window filter (the default) --------------------------------
+// ---- the lazy levels' search: end-window filter in front of the compare ------------------------------
 // What the warp pays for is not the candidates a lane visits but the code paths any lane takes: with one
 // candidate per lane and iteration, the deep compare used to run in nearly every iteration for the two or
 // three lanes whose candidate got past the 3-byte test (ncu, level 6: a third of the kernel's instructions
@@ -573,70 +489,8 @@ __device__ __forceinline__ uint32_t search_position_sync(const Smem& S, const Le
 // to a word -- so that window is compared FIRST: one unaligned word of the ring per candidate, and only
 // candidates that can improve the match reach the compare.  The compare itself starts with one 8-byte
 // round (three aligned words of the ring against the position's first eight bytes in registers).
-#ifndef ZS_LZ_NO_ENDWIN
-#define ZS_LZ_ENDWIN 1
-#endif
-// Greedy levels (1-3): same rules and same result as search_position<0> -- first longest match in chain order,
-// stop at nice_length -- the filter only skips candidates that cannot be longer than the best so far.
-__device__ __forceinline__ uint32_t search_greedy_endwin(const Smem& S, const LevelCfg& cfg, const RangeCtx& c, uint32_t q,
-                                                         uint32_t cs, uint32_t ce) {
-    const uint32_t room = ce - q;
-    const unsigned max_len = room < 258u ? room : 258u;
-    const unsigned pi = (c.cb + q) & (kRing - 1u);
-    const uint2 pw = ring64(S, pi);
-    const uint32_t lit = (pw.x & 0xffu) << 24;
-    if (max_len < 3) return lit;
-    const unsigned nice = (unsigned)cfg.nice < max_len ? (unsigned)cfg.nice : max_len;
-    const uint32_t back = c.cross ? q + c.pre : q - cs;
-    const unsigned max_back = back < kMaxDist ? back : kMaxDist;
-    unsigned best_len = 2, best_dist = 0;
-    unsigned ci = pi, dist = 0;
-#ifdef ZS_LZ_DEFER_EXT
-    unsigned best_ci = pi;
-#endif
-    unsigned woff = 0;                       // the window is bytes [woff, woff + 4) = the four bytes ending at best_len
-    uint32_t wown = pw.x, wmask = 0xffffffu; // (three bytes while there is no match yet)
-    for (int chain = cfg.chain; chain > 0; --chain) {
-        unsigned delta;
-        if (!chain_hop(S, ci, dist, max_back, delta)) break;
-        if ((ring32(S, ci + woff) ^ wown) & wmask) continue;   // cannot beat best_len (or a hash collision)
-#ifdef ZS_LZ_DEFER_EXT
-        // Inside the loop a compare goes as far as nice_length only (no further than 8 bytes at level 1): a match
-        // that long ends the search whatever its full length, which is found after the loop, where the lanes
-        // that have such a match extend them together (in the loop that path ran for 1.7 of 32 lanes, up to
-        // max_chain times per batch).
-        unsigned len = match_length(S, ci, pi, pw.x, pw.y, nice);
-        if (len > best_len) {
-            best_dist = dist;
-            if (len >= nice) { best_len = nice; best_ci = ci; break; }
-            best_len = len;
-            woff = len - 3u; wmask = 0xffffffffu;
-            wown = ring32(S, pi + woff);
-        }
-    }
-    if (best_len >= nice && best_dist) {
-        best_len = extend_match(S, best_ci, pi, nice & ~7u, max_len);   // bytes [0, nice) are equal; whole rounds from there
-        if (best_len > max_len) best_len = max_len;
-    }
-#else
-        unsigned len = match_length(S, ci, pi, pw.x, pw.y, max_len);
-        if (len > max_len) len = max_len;
-        if (len > best_len) {
-            best_len = len;
-            best_dist = dist;
-            if (len >= nice) break;
-            woff = len - 3u; wmask = 0xffffffffu;
-            wown = ring32(S, pi + woff);
-        }
-    }
-#endif
-    if (best_len < c.min_len) return lit;
-    if (best_len == 3 && best_dist > kTooFar) return lit;   // see search_position
-    return lit | (best_len << 15) | best_dist;
-}
-
-// Lazy levels (4-9): search_position_sync's loop and rules with the filter in front of the compare.  The two
-// rules that looked at candidates which do not improve the match -- "eight bytes match but the byte at best_len
+// Lazy levels (4-9): the lock-step candidate loop with the filter in front of the compare.  The two
+// rules that look at candidates which do not improve the match -- "eight bytes match but the byte at best_len
 // does not" and "ties with the best match", both on dense chains only -- are now decided on the filtered-out
 // candidate's first eight bytes: it agrees with the position on min(best_len, 8) bytes (for best_len < 8 that
 // is exactly a tie, since the window said the byte at best_len differs).
@@ -676,8 +530,11 @@ __device__ __forceinline__ uint32_t search_lazy_endwin(const Smem& S, const Leve
                 unsigned len = match_length(S, ci, pi, pw.x, pw.y, max_len);
                 if (len > max_len) len = max_len;
                 if (len > best_len) {
-                    // see search_position_sync: a good match in hand cuts the rest of the chain on dense chains and
-                    // inside a longer match
+                    // With a good match in hand the rest of the chain gets a quarter of the budget (the rule longest_match
+                    // applies when the previous position's match was good, deflate.ts:1069-1071) -- here only where the
+                    // reference would not be searching at all: on a dense chain (a run) or when the match also extends
+                    // backwards, i.e. q lies inside a longer match that started earlier (deflate_slow skips the bytes a
+                    // match covers; the speculative search cannot, but it stops after kInteriorChain more candidates).
                     if (best_len < (unsigned)cfg.good && len >= (unsigned)cfg.good) {
                         const bool interior = S.ring[(ci - 1u) & (kRing - 1u)] == S.ring[(pi - 1u) & (kRing - 1u)];
                         if (interior || delta <= kDenseHop) chain >>= 2;
@@ -1144,11 +1001,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-#ifdef ZS_LZ_ENDWIN
                             const uint32_t rr = search_lazy_endwin(S, cfg, stop, rc, q, cs, ce, live);
-#else
-                            const uint32_t rr = search_position_sync(S, cfg, stop, rc, q, cs, ce, live);
-#endif
                             r = live ? rr : 0u;
                         } else
                         if (q >= rc.q_data && q < n) {
@@ -1157,12 +1010,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                                 unsigned jl = js;
                                 do { ++jl; cs = ce; ce = S.bnd[jl + 1]; } while (q >= ce);
                             }
-#ifdef ZS_LZ_GREEDY_ENDWIN   // measured: the filter costs the greedy levels 7 % on text (chains of 4: nothing to filter)
-                            if constexpr (kMode == 2) r = search_position<2>(S, cfg, rc, q, cs, ce);
-                            else r = search_greedy_endwin(S, cfg, rc, q, cs, ce);
-#else
+                            // (the end-window filter of the lazy levels costs the greedy levels 7 % on text: chains of 4
+                            // have nothing to filter)
                             r = search_position<kMode == 1 ? 0 : kMode>(S, cfg, rc, q, cs, ce);
-#endif
                         }
                         if (q < n) S.res[res_slot(q)] = r;
                     }
