@@ -27,6 +27,12 @@ __constant__ uint32_t c_xpow[48];
 // on the host once and kept in global memory; [20..22]: x^(8*k), x^(8*256*k), x^(8*65536*k) mod P
 // for k = 0..255, which make x^(8*n) two multiplications for n < 2^24.
 __device__ uint32_t g_crc_tab[23][256];
+// The staggered tables of crc32_segments_kernel: g_crc_tt[e][s] is entry e of the table of byte position s & 31 of a
+// 32-byte macro unit (bytes 0-15: a lane's unit of row k, premultiplied by x^(8*512); bytes 16-31: its unit of row
+// k + 1), every table stored twice (s and s + 32) so that lane l can address position l + t without wrapping;
+// g_crc_s2[j][b]: (b << 8j) * x^(8*1024) mod P, the running remainder carried over two rows.
+__device__ uint32_t g_crc_tt[256][64];
+__device__ uint32_t g_crc_s2[4][256];
 
 // ---- GF(2)[x] mod P helpers (host + device) -----------------------------------------------------
 __host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
@@ -185,6 +191,105 @@ __global__ void __launch_bounds__(256) checksum_segments_kernel(const uint8_t* _
     }
 }
 
+// ---- crc32, conflict-free table lookups -------------------------------------------------------------
+// Slicing-by-16 costs one table lookup per byte; with every lane of a load instruction indexing the SAME 1 KB
+// table at a random entry, a lookup instruction is ~2.8 shared-memory wavefronts (ncu, round 1: L1/TEX 92 %
+// busy, 40 % of the HBM copy bandwidth).  Here the lookups of a warp are staggered: a lane takes two units at a
+// time (its 16 bytes of row k and of row k + 1, a 32-byte macro unit), rotates them left by `lane` bytes in
+// registers, and at step t looks up byte position (t + lane) mod 32 -- so in one instruction the 32 lanes use
+// 32 DIFFERENT tables.  The tables are interleaved entry-major (g_crc_tt[e][position]): the table of a position
+// lives in one bank, lane l only ever touches bank (l + t) mod 32, and a lookup instruction is exactly one
+// wavefront whatever the data is.  crc is linear, so the order in which a lane XORs its 32 contributions does
+// not matter; the remainder carried in (two rows = x^(8*1024)) is four more lookups.
+constexpr int kCrcThreads = 512;
+struct CrcSmem {
+    uint32_t TT[256][64];
+    uint32_t S2[4][256];
+    uint32_t T[23][256];
+};
+
+__device__ __forceinline__ uint32_t crc_pair(uint32_t c, const uint4 va, const uint4 vb, const CrcSmem& M, unsigned lane) {
+    uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = vb.x, w5 = vb.y, w6 = vb.z, w7 = vb.w;
+    // rotate the eight words left by lane >> 2 words (barrel: 1, 2, 4) ...
+    if (lane & 4u) { const uint32_t t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; w7 = t; }
+    if (lane & 8u) { const uint32_t t0 = w0, t1 = w1; w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; w6 = t0; w7 = t1; }
+    if (lane & 16u) {
+        uint32_t t;
+        t = w0; w0 = w4; w4 = t; t = w1; w1 = w5; w5 = t; t = w2; w2 = w6; w6 = t; t = w3; w3 = w7; w7 = t;
+    }
+    // ... and the bytes by lane & 3
+    const unsigned sh = (lane & 3u) * 8u;
+    uint32_t d[8];
+    d[0] = __funnelshift_r(w0, w1, sh); d[1] = __funnelshift_r(w1, w2, sh); d[2] = __funnelshift_r(w2, w3, sh);
+    d[3] = __funnelshift_r(w3, w4, sh); d[4] = __funnelshift_r(w4, w5, sh); d[5] = __funnelshift_r(w5, w6, sh);
+    d[6] = __funnelshift_r(w6, w7, sh); d[7] = __funnelshift_r(w7, w0, sh);
+    uint32_t acc = M.S2[0][c & 0xffu] ^ M.S2[1][(c >> 8) & 0xffu] ^ M.S2[2][(c >> 16) & 0xffu] ^ M.S2[3][c >> 24];
+    const uint32_t* A = &M.TT[0][lane];   // entry e of the table of position lane + t: A[64 * e + t]
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        const unsigned e = (d[t >> 2] >> (8 * (t & 3))) & 0xffu;
+        acc ^= A[64u * e + t];
+    }
+    return acc;
+}
+
+// One warp per segment, grid-stride; same decomposition of a segment as checksum_segments_kernel.
+__global__ void __launch_bounds__(kCrcThreads) crc32_segments_kernel(const uint8_t* __restrict__ buf, const uint64_t* __restrict__ off,
+                                                                    const uint64_t* __restrict__ seg_len, uint32_t n,
+                                                                    uint32_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char crc_smem_raw[];
+    CrcSmem& M = *reinterpret_cast<CrcSmem*>(crc_smem_raw);
+    {
+        uint4* dst = reinterpret_cast<uint4*>(&M);
+        const uint4* tt = reinterpret_cast<const uint4*>(&g_crc_tt[0][0]);
+        const uint4* s2 = reinterpret_cast<const uint4*>(&g_crc_s2[0][0]);
+        const uint4* tb = reinterpret_cast<const uint4*>(&g_crc_tab[0][0]);
+        constexpr unsigned n_tt = sizeof(M.TT) / 16, n_s2 = sizeof(M.S2) / 16, n_tb = sizeof(M.T) / 16;
+        for (unsigned i = threadIdx.x; i < n_tt + n_s2 + n_tb; i += blockDim.x)
+            dst[i] = i < n_tt ? tt[i] : i < n_tt + n_s2 ? s2[i - n_tt] : tb[i - n_tt - n_s2];
+        __syncthreads();
+    }
+    const uint32_t (*T)[256] = M.T;
+    const unsigned lane = zs_lane();
+    const unsigned warps_per_cta = blockDim.x >> 5;
+    for (uint64_t seg = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); seg < n; seg += (uint64_t)gridDim.x * warps_per_cta) {
+        const uint64_t beg = off[seg];
+        const uint64_t len = seg_len ? seg_len[seg] : off[seg + 1] - beg;
+        const uint8_t* p = buf + beg;
+        uint64_t head = (16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u;
+        if (head > len) head = len;
+        const uint64_t units = (len - head) >> 4;
+        const unsigned tail = (unsigned)(len - head - (units << 4));
+        const uint4* q = reinterpret_cast<const uint4*>(p + head);
+        const uint64_t mine = units > lane ? (units - lane + 31) >> 5 : 0;
+        uint32_t c = 0;
+        uint64_t k = 0;
+        // two macro units (four rows) in flight per lane
+        for (; k + 4 <= mine; k += 4) {
+            const uint4 v0 = __ldg(q + lane + 32 * k), v1 = __ldg(q + lane + 32 * (k + 1));
+            const uint4 v2 = __ldg(q + lane + 32 * (k + 2)), v3 = __ldg(q + lane + 32 * (k + 3));
+            c = crc_pair(c, v0, v1, M, lane);
+            c = crc_pair(c, v2, v3, M, lane);
+        }
+        if (k + 2 <= mine) {
+            const uint4 v0 = __ldg(q + lane + 32 * k), v1 = __ldg(q + lane + 32 * (k + 1));
+            c = crc_pair(c, v0, v1, M, lane);
+            k += 2;
+        }
+        if (k < mine) c = crc_step16(crc_skip496(c, T), __ldg(q + lane + 32 * k), T);
+        uint32_t r = 0;
+        if (mine) {
+            const uint64_t end = head + ((lane + 32 * (mine - 1) + 1) << 4);   // end of this lane's last unit
+            r = len - end ? gf2_mulmod(crc_xpow(len - end, T), c) : c;
+        }
+        if (lane == 0 && head) r ^= gf2_mulmod(crc_xpow(len - head, T), crc_bytes(p, (unsigned)head, T));
+        if (lane == 1 && tail) r ^= crc_bytes(p + len - tail, tail, T);
+        if (lane == 2) r ^= gf2_mulmod(crc_xpow(len, T), 0xffffffffu);   // the 0xffffffff preset: a term in front of the segment
+        for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(ZS_FULL_MASK, r, o);
+        if (lane == 0) out[seg] = ~r;
+    }
+}
+
 // Fold n per-segment checksums (segment i covers off[i+1]-off[i] bytes) into one value continuing
 // from `init`.  Single CTA; each thread folds a contiguous run, then a shared-memory tree.
 template <int KIND>
@@ -271,6 +376,18 @@ int ensure_tables(zs_ctx* ctx) {
         xp[k] = sq;
         sq = gf2_mulmod(sq, sq);
     }
+    static uint32_t tt[256][64], s2[4][256];
+    const uint32_t x512 = host_xpow8n(512), x1024 = host_xpow8n(1024);
+    for (unsigned e = 0; e < 256; e++)
+        for (unsigned sl = 0; sl < 64; sl++) {
+            const unsigned pos = sl & 31u;   // byte position inside the macro unit
+            tt[e][sl] = pos < 16 ? gf2_mulmod(tab[15 - pos][e], x512) : tab[15 - (pos - 16)][e];
+        }
+    for (int j = 0; j < 4; j++)
+        for (unsigned b = 0; b < 256; b++) s2[j][b] = gf2_mulmod((uint32_t)b << (8 * j), x1024);
+    ZS_CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_crc_tt, tt, sizeof(tt), 0, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_crc_s2, s2, sizeof(s2), 0, cudaMemcpyHostToDevice, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CrcSmem)));
     ZS_CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_crc_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_xpow, xp, sizeof(xp), 0, cudaMemcpyHostToDevice, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `tab`/`xp` are host temporaries
@@ -293,7 +410,13 @@ int zs_launch_checksum_segments(zs_ctx* ctx, int kind, const uint8_t* d_buf, con
     unsigned ctas = (n + 7) / 8;
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;
-    if (kind)
+    if (kind && !getenv("ZS_CRC_OLD")) {
+        // 16 warps per CTA share one copy of the tables (91 KB: two CTAs per SM)
+        unsigned g = (n + 15) / 16;
+        if (g > (unsigned)ctx->sm_count * 2u) g = (unsigned)ctx->sm_count * 2u;
+        ZS_KERNEL(ctx, "checksum_segments_kernel",
+                  crc32_segments_kernel<<<g, kCrcThreads, sizeof(CrcSmem), ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
+    } else if (kind)
         ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<1><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
     else
         ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<0><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
