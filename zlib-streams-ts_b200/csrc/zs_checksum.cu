@@ -8,10 +8,10 @@
 // memory share -- capped adler32 at 64 % and crc32 at 27 % of the HBM copy bandwidth).  Both
 // checksums are linear enough for that: adler32's b is a position-weighted sum, so a unit at
 // position p adds (len - p) * sum(d) - sum(i * d_i); for crc32 a lane's running remainder is
-// advanced over the 496 bytes it skips with four more table lookups (multiplication by
-// x^(8*496) mod P, byte-sliced) before the slicing-by-16 step of its next unit.  The 32 lane
-// results are merged with the combine algebra (crc: multiply by x^(8*bytes_after) mod P).
-// HBM-bound by design: algorithmic traffic = 1 read of every input byte.
+// advanced over the bytes it skips by table lookups (multiplication by a power of x mod P,
+// byte-sliced) and the slicing tables are looked up staggered and conflict free (see
+// crc32_segments_kernel).  The 32 lane results are merged with the combine algebra (crc: multiply
+// by x^(8*bytes_after) mod P).  Algorithmic traffic = 1 read of every input byte.
 #include <cstdio>
 
 #include "zs_common.cuh"
@@ -100,17 +100,11 @@ __device__ inline uint32_t crc_bytes(const uint8_t* __restrict__ p, unsigned n, 
     return c;
 }
 
-// One warp per segment, grid-stride.  KIND 0 adler32, 1 crc32.
-template <int KIND>
-__global__ void __launch_bounds__(256) checksum_segments_kernel(const uint8_t* __restrict__ buf,
+// adler32: one warp per segment, grid-stride.
+__global__ void __launch_bounds__(256) adler32_segments_kernel(const uint8_t* __restrict__ buf,
                                                                 const uint64_t* __restrict__ off,
                                                                 const uint64_t* __restrict__ seg_len, uint32_t n,
                                                                 uint32_t* __restrict__ out) {
-    __shared__ uint32_t T[KIND ? 23 : 1][256];
-    if (KIND) {
-        for (unsigned i = threadIdx.x; i < 23 * 256; i += blockDim.x) T[i >> 8][i & 255] = g_crc_tab[i >> 8][i & 255];
-        __syncthreads();
-    }
     const unsigned lane = zs_lane();
     const unsigned warps_per_cta = blockDim.x >> 5;
     for (uint64_t seg = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); seg < n;
@@ -127,28 +121,7 @@ __global__ void __launch_bounds__(256) checksum_segments_kernel(const uint8_t* _
         const uint4* q = reinterpret_cast<const uint4*>(p + head);
         // units of this lane: lane, lane + 32, ...; `mine` of them
         const uint64_t mine = units > lane ? (units - lane + 31) >> 5 : 0;
-        if (KIND) {
-            uint32_t c = 0;
-            uint64_t k = 0;
-            // two rows in flight per lane
-            for (; k + 2 <= mine; k += 2) {
-                const uint4 v0 = __ldg(q + lane + 32 * k), v1 = __ldg(q + lane + 32 * (k + 1));
-                c = crc_step16(crc_skip496(c, T), v0, T);
-                c = crc_step16(crc_skip496(c, T), v1, T);
-            }
-            if (k < mine) c = crc_step16(crc_skip496(c, T), __ldg(q + lane + 32 * k), T);
-            uint32_t r = 0;
-            if (mine) {
-                const uint64_t end = head + ((lane + 32 * (mine - 1) + 1) << 4);   // end of this lane's last unit
-                r = len - end ? gf2_mulmod(crc_xpow(len - end, T), c) : c;
-            }
-            if (lane == 0 && head) r ^= gf2_mulmod(crc_xpow(len - head, T), crc_bytes(p, (unsigned)head, T));
-            if (lane == 1 && tail) r ^= crc_bytes(p + len - tail, tail, T);
-            // the 0xffffffff preset behaves like a term in front of the whole segment
-            if (lane == 2) r ^= gf2_mulmod(crc_xpow(len, T), 0xffffffffu);
-            for (int o = 16; o; o >>= 1) r ^= __shfl_xor_sync(ZS_FULL_MASK, r, o);
-            if (lane == 0) out[seg] = ~r;
-        } else {
+        {
             // A = 1 + sum d_j, B = len + sum (len - j) d_j   (mod 65521)
             uint64_t A = 0, Bq = 0;
             uint32_t w = (uint32_t)((len - head - 16ull * lane) % kAdlerBase);   // (len - position of the unit) mod BASE
@@ -233,7 +206,7 @@ __device__ __forceinline__ uint32_t crc_pair(uint32_t c, const uint4 va, const u
     return acc;
 }
 
-// One warp per segment, grid-stride; same decomposition of a segment as checksum_segments_kernel.
+// One warp per segment, grid-stride; same decomposition of a segment as adler32_segments_kernel.
 __global__ void __launch_bounds__(kCrcThreads) crc32_segments_kernel(const uint8_t* __restrict__ buf, const uint64_t* __restrict__ off,
                                                                     const uint64_t* __restrict__ seg_len, uint32_t n,
                                                                     uint32_t* __restrict__ out) {
@@ -410,16 +383,15 @@ int zs_launch_checksum_segments(zs_ctx* ctx, int kind, const uint8_t* d_buf, con
     unsigned ctas = (n + 7) / 8;
     unsigned cap = (unsigned)ctx->sm_count * 8u;
     if (ctas > cap) ctas = cap;
-    if (kind && !getenv("ZS_CRC_OLD")) {
+    if (kind) {
         // 16 warps per CTA share one copy of the tables (91 KB: two CTAs per SM)
         unsigned g = (n + 15) / 16;
         if (g > (unsigned)ctx->sm_count * 2u) g = (unsigned)ctx->sm_count * 2u;
         ZS_KERNEL(ctx, "checksum_segments_kernel",
                   crc32_segments_kernel<<<g, kCrcThreads, sizeof(CrcSmem), ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
-    } else if (kind)
-        ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<1><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
-    else
-        ZS_KERNEL(ctx, "checksum_segments_kernel", checksum_segments_kernel<0><<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
+    } else {
+        ZS_KERNEL(ctx, "checksum_segments_kernel", adler32_segments_kernel<<<ctas, 256, 0, ctx->stream>>>(d_buf, d_off, d_len, n, d_out));
+    }
     return ZS_OK;
 }
 
