@@ -1027,11 +1027,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_kernel(LzArgs a) {
                 // emit pairs are therefore claimed from a counter by whoever is done searching: a warp that is late
                 // does none, the early ones share them.  (At the greedy levels the searches are short and even and the
                 // static split below is faster.)
-#ifdef ZS_LZ_CLAIM_GREEDY
-                if constexpr (true) {
-#else
                 if constexpr (kMode == 1) {
-#endif
                     const unsigned nr = r0 > r1 ? (r0 - r1 + 63u) >> 6 : 0u, ne = r2 > r3 ? (r2 - r3 + 63u) >> 6 : 0u;
                     if (threadIdx.x == 0) S.claim[(k + 1u) & 1u] = 0;   // next iteration's counter: nobody touches it now
                     for (;;) {
