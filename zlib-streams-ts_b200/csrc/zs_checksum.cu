@@ -201,6 +201,9 @@ __device__ __forceinline__ uint32_t crc_pair(uint32_t c, const uint4 va, const u
 #pragma unroll
     for (int t = 0; t < 32; ++t) {
         const unsigned e = (d[t >> 2] >> (8 * (t & 3))) & 0xffu;
+#ifdef ZS_DEBUG_HOOKS
+        if (64u * e + t + lane >= 256u * 64u) __trap();
+#endif
         acc ^= A[64u * e + t];
     }
     return acc;

@@ -211,10 +211,16 @@ __device__ __forceinline__ unsigned bulk_stage(Smem& S, const uint8_t* buf, uint
         const unsigned idx = (unsigned)from & (kRing - 1u);
         unsigned nb = (unsigned)(to - from);
         if (idx + nb > kRing) nb = kRing - idx;
+#ifdef ZS_DEBUG_HOOKS   // compute-sanitizer is closed on the pool: the copy engine's targets are checked here
+        if (idx + nb > kRing || (nb & 15u) || (idx & 15u) || ((uintptr_t)(buf + from) & 15u)) { printf("[lz77 bulk] bad copy idx %u nb %u\n", idx, nb); __trap(); }
+#endif
         bulk_g2s(S.ring + idx, buf + from, nb, &S.stage_bar);
         total += nb;
         if (idx < kRingGuard) {
             const unsigned g = idx + nb < kRingGuard ? nb : kRingGuard - idx;
+#ifdef ZS_DEBUG_HOOKS
+            if (idx + g > kRingGuard || (g & 15u)) { printf("[lz77 bulk] bad guard copy idx %u g %u\n", idx, g); __trap(); }
+#endif
             bulk_g2s(S.ring + kRing + idx, buf + from, g, &S.stage_bar);
             total += g;
         }
