@@ -297,6 +297,35 @@ def test_incremental_inflate_of_a_long_stream(gpu_ctx, wbits):
     assert time.time() - t0 < 60                 # linear: a restart-from-scratch decoder needs minutes here
 
 
+def test_inflate_without_finish_reaches_stream_end(gpu_ctx):
+    """A caller that never sends Z_FINISH (the classic zlib loop: refill, inflate(Z_NO_FLUSH), until
+    Z_STREAM_END): a long stream is decoded in batches, so after the last piece some input is still waiting for
+    its attempt -- a call that brings no new input must decode it instead of answering Z_BUF_ERROR for ever."""
+    Z = _Z()
+    data = make_text(3 << 20, 91)
+    for wbits in (15, 31, -15):
+        co = zlib.compressobj(6, zlib.DEFLATED, wbits)
+        stream = co.compress(data) + co.flush()
+        assert len(stream) > (512 << 10)          # beyond the every-call threshold of the shim
+        s = Z.createInflateStream()
+        assert Z.inflateInit2_(s, wbits) == Z.Z_OK
+        out = bytearray()
+        pos, r, idle = 0, Z.Z_OK, 0
+        while r != Z.Z_STREAM_END:
+            piece = stream[pos: pos + 32768]      # empty once the input is exhausted
+            s.next_in, s.next_in_index, s.avail_in = piece, 0, len(piece)
+            buf = bytearray(1 << 16)
+            s.next_out, s.next_out_index, s.avail_out = buf, 0, len(buf)
+            r = Z.inflate(s, Z.Z_NO_FLUSH)
+            assert r in (Z.Z_OK, Z.Z_STREAM_END, Z.Z_BUF_ERROR), (r, s.msg)
+            out += buf[: s.next_out_index]
+            pos += len(piece) - s.avail_in
+            idle = idle + 1 if (not piece and s.next_out_index == 0) else 0
+            assert idle < 4, "no progress although undecoded input is buffered"
+        assert bytes(out) == data and s.total_in == len(stream)
+        assert Z.inflateEnd(s) == Z.Z_OK
+
+
 def test_incremental_inflate_truncated(gpu_ctx):
     Z = _Z()
     data = make_text(900000, 79)
