@@ -641,8 +641,8 @@ def stream_api_bench(ctx, host, capi, warm=True):
                 if flush != 4 and zs.avail_in == 0 and zs.avail_out != 0:
                     break
     out = {}
-    if warm:   # one untimed pass over 4 MiB: the first use of the stream paths allocates their device scratch
-        stream_api_bench(ctx, host[: 4 << 20], capi, warm=False)
+    if warm:   # one untimed pass: the first use of the stream paths grows their device scratch to this stream's size
+        stream_api_bench(ctx, host, capi, warm=False)
     for level in (1, 6):
         zs = capi.ZStream()
         rc = lib.zs_stream_deflate_init(ctx.handle, C.byref(zs), level, 8, 31, 8, 0)
