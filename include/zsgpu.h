@@ -199,7 +199,9 @@ ZS_API int zs_inflate_batch_dev(zs_ctx* ctx, const uint8_t* d_in, const uint64_t
                          const uint64_t* d_dict_rng);
 
 /* Host-buffer variant (what the addon binds for inflateBatch). `in_total` = in_off[n],
- * out capacity = out_off[n].  dict / dict_rng may be NULL. */
+ * out capacity = out_off[n].  dict / dict_rng may be NULL.  A large batch (thousands of streams, >= 64 MiB of
+ * input + output) is cut into slices of streams whose copies overlap the kernels of their neighbours; the
+ * results are those of the unsliced call.  Pinned host buffers make the copies asynchronous. */
 ZS_API int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t n, int window_bits,
                      uint8_t* out, const uint64_t* out_off, uint64_t* out_len, uint64_t* in_used, uint32_t* checks,
                      int32_t* status, const uint8_t* dict, const uint64_t* dict_rng, uint64_t dict_total);
