@@ -1,6 +1,6 @@
 """GPU parity of the segment-parallel decoder of ONE stream (csrc/zs_inflate_par.cu): whatever the stream --
 its own STITCHED + SYNC deflate, C zlib streams with Z_SYNC_FLUSH / Z_FULL_FLUSH points, streams without any
-flush point, corrupted, truncated, too little output room, stored data full of marker look-alikes -- the
+flush point (cut at speculatively located block headers), corrupted, truncated, too little output room, stored data full of marker look-alikes -- the
 result (output, total_in, status, message, checksum) equals the oracle restatement of inflate()
 (src/mod/inflate/inflate.ts:332) and the engine's own serial decoder (ZS_INFLATE_SERIAL=1)."""
 import os
@@ -106,6 +106,46 @@ def test_stream_without_flush_points_and_tiny_segments(gpu_ctx, oracle):
     z = _flushed(data[: 1 << 20], 6, 15, 100, zlib.Z_SYNC_FLUSH)
     p = _check(oracle, z, 15, (1 << 20) + 64)
     assert p.output(0) == data[: 1 << 20]
+
+
+def test_streams_without_flush_points_are_cut_speculatively(gpu_ctx, oracle):
+    """Ordinary one-shot streams (zlib.compress / gzip / raw, every level incl. stored and fixed blocks): no
+    marker to cut at, so the cuts are dynamic block headers found by par_spec_kernel.  Same results as the serial
+    decoder and the oracle -- also when the stream is truncated or corrupted behind the first cuts, when the output
+    room runs out, and with a preset dictionary -- and the parallel path really ran."""
+    data = make_text(5 << 20, 31) + make_mixed(5 << 20, 32) + rand_bytes(300000, 33) + make_text(2 << 20, 34)
+    for wbits in (15, 31, -15):
+        for level, strategy in ((6, 0), (1, 0), (9, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (0, 0)):
+            co = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+            z = co.compress(data) + co.flush()
+            p = _check(oracle, z, wbits, len(data) + 64, oracle_too=(level == 6 and strategy == 0))
+            assert int(p.status[0]) == 1 and p.output(0) == data, (wbits, level, strategy)
+    z = zlib.compress(data, 6)
+    # the parallel kernels decoded it, the serial decoder only finished it
+    gpu_ctx.profile(True)
+    gpu_ctx.profile_read()
+    p = _inflate(z, 15, len(data) + 64)
+    prof = gpu_ctx.profile_read()
+    gpu_ctx.profile(False)
+    assert p.output(0) == data
+    assert "par_spec_kernel" in prof and prof["par_decode_kernel"][1] < 100.0 and prof["inflate_kernel"][1] < 50.0, prof
+    # damage behind the first cuts, truncation, too little room: verdict, message and output prefix of the serial decoder
+    rng = random.Random(6)
+    for _ in range(6):
+        bad = bytearray(z)
+        at = rng.randrange(len(z) // 3, len(z) - 8)
+        bad[at] ^= 1 << rng.randrange(8)
+        _check(oracle, bytes(bad), 15, len(data) + 64)
+    for cut in (len(z) // 2, len(z) - 3, len(z) - 1):
+        _check(oracle, z[:cut], 15, len(data) + 64)
+    _check(oracle, z, 15, len(data) // 2)
+    _check(oracle, z + b"trailing bytes", 15, len(data) + 64)
+    # raw stream with a preset dictionary: the first segments reach into it
+    zd = data[: 30000]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, 0, zd)
+    zr = co.compress(data[30000:]) + co.flush()
+    p = _check(oracle, zr, -15, len(data), dictionary=zd)
+    assert p.output(0) == data[30000:]
 
 
 def test_marker_lookalikes_in_stored_data(gpu_ctx, oracle):

@@ -62,3 +62,8 @@ d_in = torch.frombuffer(bytearray(z + bytes(8)), dtype=torch.uint8).to(dev)
 d_out = torch.empty(m + 64, dtype=torch.uint8, device=dev)
 out_len, status = run(d_in, len(z), 15, d_out, f"C zlib stream, sync flush every 128 KiB, {m >> 20} MiB")
 print("   bit exact:", status == 1 and bytes(d_out[:m].cpu().numpy()) == host, flush=True)
+# the same data written in one go (no flush points): cut at speculatively located dynamic block headers
+t0 = time.time(); z2 = zlib.compress(host, 6); print(f"C zlib deflate of {m >> 20} MiB in one go: {time.time() - t0:.1f} s", flush=True)
+d_in2 = torch.frombuffer(bytearray(z2 + bytes(8)), dtype=torch.uint8).to(dev)
+out_len, status = run(d_in2, len(z2), 15, d_out, f"C zlib stream without flush points, {m >> 20} MiB")
+print("   bit exact:", status == 1 and bytes(d_out[:m].cpu().numpy()) == host, flush=True)

@@ -56,6 +56,8 @@ struct ParArgs {
     uint64_t tile;            // bytes per candidate tile
     uint32_t n_slots;         // 1 + number of tiles: slot 0 is the start of the stream
     uint64_t* cand;           // [n_slots] bit position of every candidate (~0 = none)
+    uint64_t* spec;           // [n_slots] speculative candidates of par_spec_kernel (~0 = none), merged into cand
+    const uint64_t* marker_count;   // = &state[7] as par_scan_kernel left it
     SegInfo* seg;             // [n_slots]
     // plan
     uint32_t* plan_slot;      // [n_slots]
@@ -92,6 +94,134 @@ __global__ void par_scan_kernel(ParArgs a) {
     if (t == 0 && lane == 0) a.cand[0] = a.state[5];
 }
 
+// ---- speculative cuts: streams without flush points ---------------------------------------------------
+// A stream written in one go (zlib.deflateSync, gzip -- the streams a DecompressionStream usually gets) has no
+// markers to cut at, and one warp decodes it at 25-30 MB/s.  Its blocks still end somewhere: par_spec_kernel
+// looks, in every tile that has no marker candidate, for the first BIT position at which a non-final dynamic
+// block with a well-formed header begins -- HLIT/HDIST in range (inflate.ts:684-690), a complete code-length
+// code, run-length coded lengths that neither over-subscribe nor overrun, complete literal/length and distance
+// sets (or the reference's one-code / no-code distance sets, inftrees.ts:104-130), an end-of-block code.  Every
+// lane tests its own bit position; what a random position survives is the 17-bit test (1 in 9), then the
+// completeness of the code-length code (about 1 in 100 of those), then a few dozen decoded lengths before the
+// running Kraft sum overflows.  A position that passes everything by chance is harmless: the count pass only
+// trusts a candidate that an earlier segment LANDS on, bit exact, at a block boundary of its own decode.
+__device__ __forceinline__ uint64_t peek_bits57(const uint8_t* in, uint64_t safe_end, uint64_t bitpos) {   // >= 57 bits from bitpos
+    const uint64_t byte = bitpos >> 3;
+    const uint64_t lo = zs_ld32(in, byte, safe_end), hi = zs_ld32(in, byte + 4, safe_end);
+    return (lo | (hi << 32)) >> (bitpos & 7u);
+}
+
+__device__ bool spec_header_ok(const uint8_t* in, uint64_t in_len, uint64_t safe_end, uint64_t p) {
+    if ((p >> 3) + 40 > in_len) return false;                 // too close to the end for a whole header
+    const uint64_t w = peek_bits57(in, safe_end, p);
+    // BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29
+    if ((w & 7u) != 4u) return false;
+    const unsigned hlit = (unsigned)(w >> 3) & 31u, hdist = (unsigned)(w >> 8) & 31u, hclen = (unsigned)(w >> 13) & 15u;
+    if (hlit > 29u || hdist > 29u) return false;
+    const unsigned ncode = hclen + 4u;
+    // the code-length code: ncode 3-bit lengths, complete (inflate_table for CODES refuses anything else)
+    const uint64_t c = peek_bits57(in, safe_end, p + 17);     // 57 bits = 19 lengths
+    unsigned kraft = 0;
+    uint8_t cl[19];
+#pragma unroll
+    for (int i = 0; i < 19; i++) {
+        const unsigned l = i < (int)ncode ? (unsigned)(c >> (3 * i)) & 7u : 0u;
+        cl[c_bl_order[i]] = (uint8_t)l;
+        kraft += l ? 128u >> l : 0u;
+    }
+    if (kraft != 128u) return false;
+    // canonical code-length code: counts, first codes, symbols sorted by (length, symbol)
+    unsigned cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, offs[8];
+    for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+    cnt[0] = 0;
+    offs[1] = 0;
+    for (int l = 1; l < 7; l++) offs[l + 1] = offs[l] + cnt[l];
+    uint8_t sorted[19];
+    for (int i = 0; i < 19; i++)
+        if (cl[i]) sorted[offs[cl[i]]++] = (uint8_t)i;
+    // the run-length coded lengths (inflate.ts:729-790), judged on the fly
+    BitReader br;
+    br.base = in; br.end = in_len; br.safe_end = safe_end;
+    const uint64_t q = p + 17 + 3ull * ncode;
+    br.pos = q >> 3; br.hold = 0; br.bits = 0;
+    if (!br.need(8)) return false;
+    br.drop((unsigned)(q & 7u));
+    const unsigned nlen = hlit + 257u, total = nlen + hdist + 1u;
+    unsigned have = 0, prev = 0, kl = 0, kd = 0, nd = 0, d1 = 0, eob = 0;   // Kraft sums in units of 2^-15
+    while (have < total) {
+        br.refill();
+        if (br.bits < 14) return false;                      // input ends inside the header
+        // one symbol of the code-length code, bit by bit (<= 7 bits)
+        unsigned code = 0, first = 0, index = 0, sym = 19, used = 0;
+        for (unsigned l = 1; l <= 7; l++) {
+            code |= (unsigned)(br.hold >> (l - 1)) & 1u;
+            const unsigned n = cnt[l];
+            if (code - first < n) { sym = sorted[index + (code - first)]; used = l; break; }
+            index += n; first += n; first <<= 1; code <<= 1;
+        }
+        if (sym > 18) return false;
+        br.drop(used);
+        unsigned rep = 1, len = sym;
+        if (sym == 16) { if (have == 0) return false; len = prev; rep = 3 + br.take(2); }
+        else if (sym == 17) { len = 0; rep = 3 + br.take(3); }
+        else if (sym == 18) { len = 0; rep = 11 + br.take(7); }
+        if (have + rep > total) return false;
+        prev = len;
+        if (len) {
+            const unsigned unit = 32768u >> len;
+            for (unsigned r = 0; r < rep; r++) {
+                const unsigned i = have + r;
+                if (i < nlen) { kl += unit; if (i == 256) eob = 1; }
+                else { kd += unit; nd++; d1 = len == 1; }
+            }
+            if (kl > 32768u || kd > 32768u) return false;     // over-subscribed
+        }
+        have += rep;
+    }
+    if (!eob || kl != 32768u) return false;                   // (a one-code literal/length set is legal and useless)
+    if (!(kd == 32768u || nd == 0 || (nd == 1 && d1))) return false;
+    return true;
+}
+
+constexpr unsigned kSpecWarpsPerTile = 4;
+__global__ void __launch_bounds__(128) par_spec_kernel(ParArgs a) {
+    // few markers for the size of the input?  (a stream with flush points needs no guessing)
+    if (a.state[5] == ~0ull || a.marker_count[0] * (256ull << 10) >= a.in_len) return;
+    const unsigned lane = zs_lane();
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t t = w / kSpecWarpsPerTile, part = w % kSpecWarpsPerTile;
+    if (t + 1 >= a.n_slots || a.cand[t + 1] != ~0ull) return;   // (markers were found by par_scan_kernel, which ran before)
+    const uint64_t tile_bits = a.tile * 8, part_bits = tile_bits / kSpecWarpsPerTile;
+    uint64_t lo = t * tile_bits + part * part_bits, hi = lo + part_bits;
+    const uint64_t body = a.state[5];
+    if (lo <= body) lo = body + 1;                            // slot 0 is the true start
+    if (hi > a.in_len * 8) hi = a.in_len * 8;
+    const uint64_t safe_end = (a.in_len + 7) & ~7ull;
+    for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
+        const uint64_t p = p0 + lane;
+        const bool ok = p < hi && spec_header_ok(a.in, a.in_len, safe_end, p);
+        const unsigned m = __ballot_sync(ZS_FULL_MASK, ok);
+        if (m) {
+            if (lane == 0) {
+                const unsigned long long found = p0 + (unsigned)(__ffs((int)m) - 1);
+                const unsigned long long old = atomicMin((unsigned long long*)&a.spec[t + 1], found);
+                (void)old;
+            }
+            break;
+        }
+    }
+}
+// the speculative finds become candidates (kept apart until every part of a tile has reported its first)
+__global__ void par_spec_merge_kernel(ParArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t + 1 >= a.n_slots) return;
+    const uint64_t s = a.spec[t + 1];
+    if (s != ~0ull && a.cand[t + 1] == ~0ull) {
+        a.cand[t + 1] = s;
+        atomicAdd((unsigned long long*)&a.state[7], 1ull);
+    }
+}
+
 // One segment, decoded by a warp from bit `start_bit`.  kWrite = false: lengths only (count pass), stops on a
 // later candidate; true: symbols to a.sym + out_base, stops at end_bit.
 template <bool kWrite>
@@ -126,8 +256,8 @@ __device__ __forceinline__ void decode_segment(const ParArgs& a, WarpArena& A, c
         } else if (here_bit > start_bit) {
             if (last) { status = SEG_FINAL; end_bit = here_bit; break; }
             const uint64_t byte = here_bit >> 3;
-            if ((here_bit & 7u) == 0) {
-                if (byte == a.in_len) { status = SEG_LANDED; end_bit = here_bit; next_slot = kEndOfInput; break; }
+            if ((here_bit & 7u) == 0 && byte == a.in_len) { status = SEG_LANDED; end_bit = here_bit; next_slot = kEndOfInput; break; }
+            {   // a candidate of this tile at exactly this bit (markers are byte aligned, speculative cuts are not)
                 const uint64_t t = byte / a.tile + 1;
                 if (t < a.n_slots && a.cand[t] == here_bit) { status = SEG_LANDED; end_bit = here_bit; next_slot = (uint32_t)t; break; }
             }
@@ -408,7 +538,9 @@ int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len
     p.tile = tile;
     const uint64_t n_tiles = (in_len + tile - 1) / tile;
     p.n_slots = (uint32_t)(n_tiles + 1);
-    p.cand = (uint64_t*)zs_scratch_get(ctx, SCR_P_CAND, (size_t)p.n_slots * 8);
+    p.cand = (uint64_t*)zs_scratch_get(ctx, SCR_P_CAND, (size_t)p.n_slots * 16);   // candidates, then the speculative finds
+    p.spec = p.cand ? p.cand + p.n_slots : nullptr;
+    p.marker_count = d_state + 7;
     p.seg = (SegInfo*)zs_scratch_get(ctx, SCR_P_SEG, (size_t)p.n_slots * sizeof(SegInfo));
     uint8_t* plan = (uint8_t*)zs_scratch_get(ctx, SCR_P_PLAN, (size_t)p.n_slots * 16 + 64);
     p.sym = (uint16_t*)zs_scratch_get(ctx, SCR_P_SYM, (size_t)out_cap * 2 + 64);
@@ -429,6 +561,12 @@ int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len
         const unsigned warps = p.n_slots - 1;
         if (warps) ZS_KERNEL(ctx, "par_scan_kernel", par_scan_kernel<<<(warps + 7) / 8, 256, 0, ctx->stream>>>(p));
         else ZS_KERNEL(ctx, "par_scan_kernel", par_scan_kernel<<<1, 32, 0, ctx->stream>>>(p));
+    }
+    if (p.n_slots > 1 && !getenv("ZS_INFLATE_NO_SPEC")) {
+        ZS_CUDA_TRY(ctx, cudaMemsetAsync(p.spec, 0xff, (size_t)p.n_slots * 8, ctx->stream));
+        const uint64_t warps = (uint64_t)(p.n_slots - 1) * kSpecWarpsPerTile;
+        ZS_KERNEL(ctx, "par_spec_kernel", par_spec_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(p));
+        ZS_KERNEL(ctx, "par_spec_merge_kernel", par_spec_merge_kernel<<<(p.n_slots + 255) / 256, 256, 0, ctx->stream>>>(p));
     }
     unsigned ctas = (p.n_slots + kWarps - 1) / kWarps;
     if (ctas > sms * 8u) ctas = sms * 8u;
