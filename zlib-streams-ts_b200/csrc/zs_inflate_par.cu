@@ -18,8 +18,10 @@
 //   par_decode_kernel   a warp per planned segment decodes again, now writing 16-bit symbols: a byte, or
 //                       256 + w for "byte w of the 32 KiB window before this segment" (copied around like
 //                       any other symbol by later matches).
-//   par_window_kernel   one CTA walks the segments in order: the window after segment k is the resolved tail
-//                       of its symbols (the only serial step, 32 Ki symbols per segment).
+//   par_win*_kernel     the window after segment k is the resolved tail of its symbols: a chain over the
+//                       segments, made short by composing it per group of 32 segments (par_wingroup_kernel, all
+//                       groups in parallel, symbolic), linking the groups (par_winlink_kernel, the only serial
+//                       step: 32 Ki elements per GROUP) and filling in every window (par_window_kernel, parallel).
 //   par_resolve_kernel  symbols -> bytes, every segment with its own window, all in parallel.
 //   par_finish_kernel   where the serial decoder (inflate_kernel, zs_inflate.cu) takes over: behind the last
 //                       planned segment -- for the trailer and the final status only when the chain reached
@@ -69,6 +71,7 @@ struct ParArgs {
     const uint8_t* hist;      // the last hist_len (<= 32768) bytes before the stream
     uint16_t* sym;            // [out_cap] symbols
     uint8_t* windows;         // [n_slots + 1][32768]
+    uint16_t* gmap;           // [ceil(n_slots / kWinGroup)][32768] symbolic window maps of the segment groups
     uint8_t* out;
     uint64_t* resume;         // [4] record for inflate_kernel: start bit, start out, flags, -
 };
@@ -436,7 +439,58 @@ __global__ void __launch_bounds__(kWarps * 32) par_decode_kernel(ParArgs a) {
 
 // windows[k] = the 32 KiB before planned segment k, right aligned (bytes that do not exist read as 0 and are
 // never referenced: the decode pass refused such distances).
-__global__ void __launch_bounds__(1024) par_window_kernel(ParArgs a) {
+//
+// The window after segment k is the resolved tail of its symbols -- a chain over the segments, 32 Ki elements per
+// link.  One CTA walking all of it was the largest item of a long stream (6.5 us per segment: 29 ms of the 70 ms
+// of a 256 MiB stream with 4400 segments).  The chain is a composition of maps ("element j of the next window is a
+// literal, or element w of the current one"), and maps compose: the segments are taken in groups of kWinGroup,
+//   par_wingroup_kernel  every group, in parallel: the window after its last segment as a SYMBOLIC map of the
+//                        window before its first (16-bit entries: a byte, or 256 + index into that window);
+//   par_winlink_kernel   one CTA: the window before every group, by applying the groups' maps in order
+//                        (n / kWinGroup links instead of n);
+//   par_window_kernel    every group, in parallel: the concrete windows of its segments from its first one.
+constexpr unsigned kWinGroup = 32;
+constexpr int kWinPer = kWin / 1024;   // elements per thread
+
+// element j of the window after a segment of `len` symbols at `sym`: symbol j + len - 32768, or -- where the segment
+// is shorter than the window -- element j + len of the window before it (returned as 0x10000 + index).  All loads of
+// a thread are issued before the first is used: the chain is latency bound.
+__device__ __forceinline__ void window_tail(const uint16_t* sym, uint64_t len, unsigned tid, unsigned (&s)[kWinPer]) {
+#pragma unroll
+    for (int u = 0; u < kWinPer; u++) {
+        const unsigned j = tid + 1024u * u;
+        const int64_t t = (int64_t)j + (int64_t)len - (int64_t)kWin;
+        s[u] = t >= 0 ? (unsigned)__ldcs(sym + t) : 0x10000u + (unsigned)(j + len);
+    }
+}
+
+__global__ void __launch_bounds__(1024) par_wingroup_kernel(ParArgs a) {
+    extern __shared__ __align__(16) uint8_t s_win_raw[];
+    uint16_t (*s_map)[kWin] = reinterpret_cast<uint16_t (*)[kWin]>(s_win_raw);
+    const unsigned tid = threadIdx.x;
+    const uint64_t n = a.state[0];
+    const uint64_t k0 = (uint64_t)blockIdx.x * kWinGroup, k1 = k0 + kWinGroup < n ? k0 + kWinGroup : n;
+    if (k0 >= n) return;
+    for (unsigned j = tid; j < kWin; j += 1024) s_map[0][j] = (uint16_t)(256u + j);   // the identity: the window before the group
+    __syncthreads();
+    unsigned cur = 0;
+    for (uint64_t k = k0; k < k1; k++) {
+        const uint64_t off = a.plan_off[k], len = a.plan_off[k + 1] - off;
+        unsigned s[kWinPer];
+        window_tail(a.sym + off, len, tid, s);
+#pragma unroll
+        for (int u = 0; u < kWinPer; u++) {
+            const unsigned v = s[u];
+            s_map[cur ^ 1][tid + 1024u * u] = v < 256 ? (uint16_t)v : v < 0x10000u ? s_map[cur][v - 256] : s_map[cur][v - 0x10000u];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    uint16_t* g = a.gmap + (uint64_t)blockIdx.x * kWin;
+    for (unsigned j = tid; j < kWin; j += 1024) g[j] = s_map[cur][j];
+}
+
+__global__ void __launch_bounds__(1024) par_winlink_kernel(ParArgs a) {
     extern __shared__ __align__(16) uint8_t s_win_raw[];
     uint8_t (*s_win)[kWin] = reinterpret_cast<uint8_t (*)[kWin]>(s_win_raw);
     const unsigned tid = threadIdx.x;
@@ -449,27 +503,45 @@ __global__ void __launch_bounds__(1024) par_window_kernel(ParArgs a) {
     }
     __syncthreads();
     unsigned cur = 0;
-    constexpr int kPer = kWin / 1024;   // elements per thread
-    uint64_t o0 = a.plan_off[0], o1 = n ? a.plan_off[1] : 0;
-    for (uint64_t k = 0; k < n; k++) {
-        const uint64_t o2 = k + 2 <= n ? a.plan_off[k + 2] : 0;   // one iteration ahead: off the critical path
-        const uint64_t off = o0, len = o1 - o0;
-        o0 = o1; o1 = o2;
-        const uint16_t* sym = a.sym + off;
-        uint8_t* next = a.windows + (k + 1) * (uint64_t)kWin;
-        // element j of the next window is symbol j + len - 32768 of this segment, or -- where the segment is
-        // shorter than the window -- byte j + len of the current window.  All loads of a thread are issued
-        // before the first is used: the chain over the segments is latency bound (measured: 16 us per segment
-        // with dependent loads, 6144 segments per GiB).
-        unsigned s[kPer];
+    const uint64_t ng = (n + kWinGroup - 1) / kWinGroup;
+    for (uint64_t g = 0; g + 1 < ng; g++) {   // the window before group g + 1
+        const uint16_t* m = a.gmap + g * kWin;
+        uint8_t* next = a.windows + (g + 1) * kWinGroup * (uint64_t)kWin;
+        unsigned v[kWinPer];
 #pragma unroll
-        for (int u = 0; u < kPer; u++) {
+        for (int u = 0; u < kWinPer; u++) v[u] = __ldcs(m + tid + 1024u * u);
+#pragma unroll
+        for (int u = 0; u < kWinPer; u++) {
             const unsigned j = tid + 1024u * u;
-            const int64_t t = (int64_t)j + (int64_t)len - (int64_t)kWin;
-            s[u] = t >= 0 ? (unsigned)__ldcs(sym + t) : 0x10000u + (unsigned)(j + len);   // 0x10000 + w: byte w of the current window
+            const uint8_t b = v[u] < 256 ? (uint8_t)v[u] : s_win[cur][v[u] - 256];
+            s_win[cur ^ 1][j] = b;
+            next[j] = b;
         }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(1024) par_window_kernel(ParArgs a) {
+    extern __shared__ __align__(16) uint8_t s_win_raw[];
+    uint8_t (*s_win)[kWin] = reinterpret_cast<uint8_t (*)[kWin]>(s_win_raw);
+    const unsigned tid = threadIdx.x;
+    const uint64_t n = a.state[0];
+    const uint64_t k0 = (uint64_t)blockIdx.x * kWinGroup, k1 = k0 + kWinGroup < n ? k0 + kWinGroup : n;
+    if (k0 >= n) return;
+    {
+        const uint8_t* w0 = a.windows + k0 * (uint64_t)kWin;
+        for (unsigned j = tid; j < kWin; j += 1024) s_win[0][j] = w0[j];
+    }
+    __syncthreads();
+    unsigned cur = 0;
+    for (uint64_t k = k0; k < k1; k++) {
+        const uint64_t off = a.plan_off[k], len = a.plan_off[k + 1] - off;
+        uint8_t* next = a.windows + (k + 1) * (uint64_t)kWin;
+        unsigned s[kWinPer];
+        window_tail(a.sym + off, len, tid, s);
 #pragma unroll
-        for (int u = 0; u < kPer; u++) {
+        for (int u = 0; u < kWinPer; u++) {
             const unsigned j = tid + 1024u * u;
             const unsigned v = s[u];
             const uint8_t b = v < 256 ? (uint8_t)v : v < 0x10000u ? s_win[cur][v - 256] : s_win[cur][v - 0x10000u];
@@ -518,7 +590,7 @@ __global__ void par_finish_kernel(ParArgs a) {
 }  // namespace
 
 // scratch slots of zs_api.cu reserved for this path
-enum { SCR_P_CAND = 25, SCR_P_SEG = 26, SCR_P_PLAN = 27, SCR_P_SYM = 28, SCR_P_WIN = 29, SCR_P_STATE = 30 };
+enum { SCR_P_CAND = 25, SCR_P_SEG = 26, SCR_P_PLAN = 27, SCR_P_SYM = 28, SCR_P_WIN = 29, SCR_P_STATE = 30, SCR_P_GMAP = 33 };
 
 int zs_launch_inflate_header(zs_ctx* ctx, const zs_inflate_args& a, uint64_t* d_state);   // zs_inflate.cu
 
@@ -545,7 +617,9 @@ int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len
     uint8_t* plan = (uint8_t*)zs_scratch_get(ctx, SCR_P_PLAN, (size_t)p.n_slots * 16 + 64);
     p.sym = (uint16_t*)zs_scratch_get(ctx, SCR_P_SYM, (size_t)out_cap * 2 + 64);
     p.windows = (uint8_t*)zs_scratch_get(ctx, SCR_P_WIN, ((size_t)p.n_slots + 1) * kWin);
-    if (!p.cand || !p.seg || !plan || !p.sym || !p.windows) return ZS_MEM_ERROR;
+    const unsigned n_groups = (p.n_slots + kWinGroup - 1) / kWinGroup;
+    p.gmap = (uint16_t*)zs_scratch_get(ctx, SCR_P_GMAP, (size_t)n_groups * kWin * 2);
+    if (!p.cand || !p.seg || !plan || !p.sym || !p.windows || !p.gmap) return ZS_MEM_ERROR;
     p.plan_off = (uint64_t*)plan;                                   // [n_slots + 1]
     p.plan_slot = (uint32_t*)(plan + ((size_t)p.n_slots + 1) * 8);  // [n_slots]
     p.plan_err = p.plan_slot + p.n_slots;                           // [n_slots]  (16 bytes per slot + 8 in all)
@@ -576,10 +650,14 @@ int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len
     static bool attr_set[64] = {false};
     const int dev_slot = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
     if (!attr_set[dev_slot] || ctx->device >= 64) {
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(par_wingroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kWin));
+        ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(par_winlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kWin));
         ZS_CUDA_TRY(ctx, cudaFuncSetAttribute(par_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kWin));
         attr_set[dev_slot] = true;
     }
-    ZS_KERNEL(ctx, "par_window_kernel", par_window_kernel<<<1, 1024, 2 * kWin, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_wingroup_kernel", par_wingroup_kernel<<<n_groups, 1024, 4 * kWin, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_winlink_kernel", par_winlink_kernel<<<1, 1024, 2 * kWin, ctx->stream>>>(p));
+    ZS_KERNEL(ctx, "par_window_kernel", par_window_kernel<<<n_groups, 1024, 2 * kWin, ctx->stream>>>(p));
     ZS_KERNEL(ctx, "par_resolve_kernel", par_resolve_kernel<<<sms * 8u, 256, 0, ctx->stream>>>(p));
     ZS_KERNEL(ctx, "par_finish_kernel", par_finish_kernel<<<1, 32, 0, ctx->stream>>>(p));
     return ZS_OK;
