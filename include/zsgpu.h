@@ -211,8 +211,9 @@ ZS_API int zs_inflate_batch(zs_ctx* ctx, const uint8_t* in, const uint64_t* in_o
  * src/mod/inflate/inflate.ts:332 for a whole stream -- same output, status, message -- decoded in parallel
  * where the stream has flush points (Z_SYNC_FLUSH / Z_FULL_FLUSH markers, deflate.ts:936-961): the stream is
  * cut at the byte-aligned block boundaries behind the markers, the segments are decoded concurrently against
- * a symbolic 32 KiB window and resolved in order (csrc/zs_inflate_par.cu).  A stream without flush points,
- * and raw deflate64 (-16), are decoded by one warp.  The host-buffer call zs_inflate_batch with n = 1 and the
+ * a symbolic 32 KiB window and resolved in order (csrc/zs_inflate_par.cu).  A stream without flush points is
+ * cut at dynamic block headers located by search (trusted only when the segment before lands on them bit
+ * exact); raw deflate64 (-16) is decoded by one warp.  The host-buffer call zs_inflate_batch with n = 1 and the
  * streaming shim take the same path.  d_dict: optional preset dictionary / earlier output (raw streams). */
 ZS_API int zs_inflate_stream_dev(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len, int window_bits, uint8_t* d_out,
                           uint64_t out_cap, uint64_t* d_out_len, uint64_t* d_in_used, uint32_t* d_check,
