@@ -9,7 +9,9 @@ N > 1  (config.workload = configs[2], the north-star multi-GPU split, STRONG sca
        stream (sharded.deflate_sharded), then the ranks all_gather (compressed bit length, adler32, length)
        -> exclusive scan (global bit offsets) -> adler32_combine (sharded.exchange_meta).  After the timed
        region the parts are gathered once on rank 0 (sharded.gather_stream, timed separately), decoded by C
-       zlib and compared with the corpus (`verified`).
+       zlib and compared with the corpus (`verified`).  `inflate` holds the decode side of the same run: the
+       stream inflated where it lies (every rank its own part, sharded.inflate_sharded) and configs[3], the
+       corpus as independent 4 KiB gzip records block-partitioned over the ranks.
 
 A step is one pass of the hot path over the whole corpus.
   value  input GB/s with the corpus resident in HBM (CUDA events on the launching stream, max over ranks)
@@ -474,6 +476,19 @@ def extras(args, torch, dev, ctx, data, bufs, n, n_chunks, h_in, h_out):
         g = B.deflate_batch_dev(mixed[: 32 << 20], CHUNK2, LEVEL2, B.WRAP_ZLIB, B.MODE_STITCHED, 0, ctx=ctx)
         gs = bytes(g.out[: g.read_result().total_out_bytes].cpu().numpy())
         c2["decodes_with_c_zlib"] = bool(d.decompress(gs) + d.flush() == s and d.eof)
+    # the same stream decoded again on this GPU: ONE stream without flush points, cut at located block headers
+    try:
+        S = pkg("sharded")
+        zb = int(rr6.total_out_bytes)
+        ip = S.inflate_part(r6.out, zb, m, B.WRAP_ZLIB, True, ctx=ctx)
+        ms = timed(torch, lambda: S.inflate_part(r6.out, zb, m, B.WRAP_ZLIB, True, ctx=ctx, reuse=ip), 2)
+        ip = S.inflate_part(r6.out, zb, m, B.WRAP_ZLIB, True, ctx=ctx, reuse=ip)
+        c2["inflate_one_stream_output_GBps"] = m / (ms / 1e3) / 1e9
+        c2["inflate_one_stream_bit_exact"] = bool(ip.status == 1 and ip.out_len == m and ip.in_used == zb
+                                                  and torch.equal(ip.out[:m], mixed) and ip.check == int(rr6.check))
+        del ip
+    except Exception as e:
+        c2["inflate_one_stream_error"] = repr(e)
     extra["configs2_single_gpu"] = c2
     # the same level-6 plan on the headline's text corpus (what round 1 reported as deflate_level6_input_GBps)
     view = data[: min(n, 512 << 20)]
@@ -608,78 +623,137 @@ def extras(args, torch, dev, ctx, data, bufs, n, n_chunks, h_in, h_out):
 
 def stream_api_bench(ctx, host, capi, warm=True):
     """zs_stream_deflate / zs_stream_inflate driven like src/mod/streams.ts drives deflate()/inflate(): input in
-    32 KiB slices (Z_NO_FLUSH, then Z_FINISH), output through 64 KiB buffers."""
+    32 KiB slices (Z_NO_FLUSH, then Z_FINISH), output through 64 KiB buffers.  The loop itself is C
+    (bindings/c/stream_pump.c: a Node-API call costs ~1 us, a ctypes call from Python 30-50 us, which at 32 KiB per
+    call would cap the measurement near 1 GB/s whatever the library does)."""
     import ctypes as C
     import numpy as np
+    from tools import streampump
     lib = capi.load()
-    IN, OUT = 32 * 1024, 64 * 1024
     n = host.size
-    obuf = np.empty(OUT, dtype=np.uint8)
+    big = np.empty(n + (n >> 3) + (1 << 20), dtype=np.uint8)
 
-    def pump(zs, fn, src, total):
-        chunks = []
-        pos = 0
-        while True:
-            take = min(IN, total - pos)
-            zs.next_in = src.ctypes.data + pos
-            zs.avail_in = take
-            pos += take
-            flush = 4 if pos >= total else 0   # Z_FINISH with the last slice, Z_NO_FLUSH before
-            while True:
-                zs.next_out = obuf.ctypes.data
-                zs.avail_out = OUT
-                rc = fn(C.byref(zs), flush)
-                made = OUT - zs.avail_out
-                if made:
-                    chunks.append(obuf[:made].tobytes())
-                if rc == 1:
-                    return b"".join(chunks), rc
-                if rc == -5 and flush != 4:
-                    break                       # nothing more to do with this slice
-                if rc != 0:
-                    raise RuntimeError(f"stream call failed: {rc} {zs.msg}")
-                if flush != 4 and zs.avail_in == 0 and zs.avail_out != 0:
-                    break
-    out = {}
+    def run(init, fn, end, src):
+        zs = capi.ZStream()
+        assert init(zs) == 0
+        t0 = time.perf_counter()
+        rc, made, calls = streampump.pump(fn, zs, src, big)
+        dt = time.perf_counter() - t0
+        end(C.byref(zs))
+        if rc != 1:
+            raise RuntimeError(f"stream call failed: {rc}")
+        return big[:made].copy(), dt, calls
+
+    out = {"loop": "C (bindings/c/stream_pump.c), 32 KiB in / 64 KiB out"}
     if warm:   # one untimed pass: the first use of the stream paths grows their device scratch to this stream's size
         stream_api_bench(ctx, host, capi, warm=False)
     for level in (1, 6):
-        zs = capi.ZStream()
-        rc = lib.zs_stream_deflate_init(ctx.handle, C.byref(zs), level, 8, 31, 8, 0)
-        assert rc == 0
-        t0 = time.perf_counter()
-        comp, rc = pump(zs, lib.zs_stream_deflate, host, n)
-        dt = time.perf_counter() - t0
-        lib.zs_stream_deflate_end(C.byref(zs))
+        comp, dt, calls = run(lambda zs: lib.zs_stream_deflate_init(ctx.handle, C.byref(zs), level, 8, 31, 8, 0),
+                              lib.zs_stream_deflate, lib.zs_stream_deflate_end, host)
         out[f"CompressionStream_gzip_level{level}_input_GBps"] = n / dt / 1e9
-        out[f"level{level}_ratio"] = len(comp) / n
-        ok = zlib.decompress(comp, 31) == host.tobytes()
-        out[f"level{level}_decodes_with_c_zlib"] = ok
-        zs = capi.ZStream()
-        rc = lib.zs_stream_inflate_init(ctx.handle, C.byref(zs), 31)
-        assert rc == 0
-        carr = np.frombuffer(comp, dtype=np.uint8)
-        t0 = time.perf_counter()
-        back, rc = pump(zs, lib.zs_stream_inflate, carr, carr.size)
-        dt = time.perf_counter() - t0
-        lib.zs_stream_inflate_end(C.byref(zs))
+        out[f"level{level}_ratio"] = comp.size / n
+        out[f"level{level}_deflate_calls"] = calls
+        out[f"level{level}_decodes_with_c_zlib"] = zlib.decompress(comp.tobytes(), 31) == host.tobytes()
+        back, dt, calls = run(lambda zs: lib.zs_stream_inflate_init(ctx.handle, C.byref(zs), 31),
+                              lib.zs_stream_inflate, lib.zs_stream_inflate_end, comp)
         out[f"DecompressionStream_own_level{level}_output_GBps"] = n / dt / 1e9
-        out[f"level{level}_roundtrip_ok"] = back == host.tobytes()
+        out[f"level{level}_roundtrip_ok"] = bool(np.array_equal(back, host))
     # a C-zlib stream without flush points: cut at speculatively located block headers
-    m = n
-    cz = np.frombuffer(zlib.compress(host[:m].tobytes(), 6), dtype=np.uint8)
-    zs = capi.ZStream()
-    lib.zs_stream_inflate_init(ctx.handle, C.byref(zs), 15)
-    t0 = time.perf_counter()
-    back, rc = pump(zs, lib.zs_stream_inflate, cz, cz.size)
-    dt = time.perf_counter() - t0
-    lib.zs_stream_inflate_end(C.byref(zs))
-    out["DecompressionStream_czlib_noflush_output_GBps"] = m / dt / 1e9
-    out["czlib_noflush_ok"] = back == host[:m].tobytes()
+    cz = np.frombuffer(zlib.compress(host.tobytes(), 6), dtype=np.uint8)
+    back, dt, calls = run(lambda zs: lib.zs_stream_inflate_init(ctx.handle, C.byref(zs), 15),
+                          lib.zs_stream_inflate, lib.zs_stream_inflate_end, cz)
+    out["DecompressionStream_czlib_noflush_output_GBps"] = n / dt / 1e9
+    out["czlib_noflush_ok"] = bool(np.array_equal(back, host))
     t0 = time.perf_counter()
     zlib.decompress(cz.tobytes())
-    out["c_zlib_one_core_inflate_GBps"] = m / (time.perf_counter() - t0) / 1e9
+    out["c_zlib_one_core_inflate_GBps"] = n / (time.perf_counter() - t0) / 1e9
     out["bytes"] = n
+    return out
+
+
+def sharded_inflate_legs(args, torch, dist, dev, rank, world, ctx, buf, hist, local, res, part_bytes, plan, total):
+    """The inflate side of the multi-GPU run (outside the deflate line's timed region, same timing rules: barrier +
+    synchronize on both sides, device events, max over ranks).
+    (1) the stream deflate_sharded just produced, decoded where it lies: every rank inflates its own part with the
+        32 KiB before its range as preset dictionary (each part goes through the segment-parallel decoder of one
+        stream), the ranks fold adler32 and length with the exchange step, every rank compares its output with its
+        shard of the corpus;
+    (2) configs[3]: total / 4 KiB independent gzip records (1 M for the 4 GiB corpus), block-partitioned over the
+        ranks with no communication, inflate + crc32 of every record checked on the device."""
+    B, S = pkg("batch"), pkg("sharded")
+    n = local.numel()
+    out = {}
+    d_hist = buf[:hist] if hist else None
+    steps = max(1, min(args.steps, 5))
+
+    def max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # (1) one stream, one part per rank
+    ip, iplan = S.inflate_sharded(res.out, part_bytes, n, B.WRAP_ZLIB, d_hist, ctx=ctx)
+    ip, iplan = S.inflate_sharded(res.out, part_bytes, n, B.WRAP_ZLIB, d_hist, ctx=ctx, reuse=ip)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.profile(True); ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        ip, iplan = S.inflate_sharded(res.out, part_bytes, n, B.WRAP_ZLIB, d_hist, ctx=ctx, reuse=ip)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = 1e3 * (time.perf_counter() - t0)
+    prof = ctx.profile_read(); ctx.profile(False)
+    ms = max_ms(max(e0.elapsed_time(e1), wall) / steps)   # every step ends with a host read: wall == device
+    want = 1 if (rank == world - 1) else -5                # Z_STREAM_END on the last part, Z_BUF_ERROR (input ran dry) before
+    ok = (ip.status == want and ip.out_len == n and ip.in_used == part_bytes and bool(torch.equal(ip.out[:n], local))
+          and iplan.check == plan.check and iplan.total_len == total)
+    out["one_stream_sharded"] = {
+        "workload": "the zlib stream of the deflate line, every rank inflating the part it holds (raw deflate + the 32 KiB "
+                    "before its range as dictionary; rank 0 with the zlib header), adler32 folded across ranks",
+        "output_GBps": total / (ms / 1e3) / 1e9, "ms_per_step": ms, "steps": steps,
+        "bit_exact_and_adler32_ok": all_ok(ok), "adler32": "%08x" % iplan.check,
+        "per_kernel_ms_per_step_rank0": {k: v[1] / steps for k, v in sorted(prof.items())}}
+    del ip
+
+    # (2) configs[3]: independent 4 KiB gzip records
+    if not args.no_extra:
+        rec = 4096
+        nrec = n // rec
+        src = local[: nrec * rec]
+        z = B.deflate_batch_dev(src, rec, 6, B.WRAP_GZIP, B.MODE_INDEPENDENT, 0, ctx=ctx)
+        ooff = torch.arange(0, nrec + 1, dtype=torch.int64, device=dev) * rec
+        inf = B.inflate_batch_dev(z.out, z.out_off, ooff, 31, out_capacity=nrec * rec, ctx=ctx)
+        B.inflate_batch_dev(z.out, z.out_off, ooff, 31, ctx=ctx, reuse=inf)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            B.inflate_batch_dev(z.out, z.out_off, ooff, 31, ctx=ctx, reuse=inf)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_ms(e0.elapsed_time(e1) / steps)
+        crc = B.checksum_batch_dev(src, ooff, 1, ctx=ctx)
+        ok = (bool((inf.status == 1).all().item()) and bool((inf.out_len == rec).all().item())
+              and bool(torch.equal(inf.out[: nrec * rec], src)) and bool(torch.equal(inf.checks, crc)))
+        cnt = torch.tensor([nrec, int(z.read_result().total_out_bytes)], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        nrec_all, zbytes_all = int(cnt[0].item()), int(cnt[1].item())
+        out["configs3_gzip_records"] = {
+            "workload": "configs[3]: %d independent 4 KiB gzip records (the mixed corpus cut in records, deflated at level 6 "
+                        "by this engine), block-partitioned over the ranks, inflate + crc32 of every record" % nrec_all,
+            "records": nrec_all, "compressed_bytes": zbytes_all, "output_GBps": nrec_all * rec / (ms / 1e3) / 1e9,
+            "records_per_s": nrec_all / (ms / 1e3), "ms_per_step": ms, "steps": steps,
+            "roofline_frac_per_gpu": (zbytes_all + nrec_all * rec) / world / (ms / 1e3) / 1e9 / hbm_peak()[0],
+            "bit_exact_status_and_crc32_ok": all_ok(ok)}
+        del inf, z
     return out
 
 
@@ -786,6 +860,14 @@ def run_sharded(args, torch, dist, dev, rank, local_rank, world):
     flag = torch.tensor([1 if (verified or rank != 0) else 0], device=dev)
     dist.broadcast(flag, 0)
 
+    # ---- inflate, sharded the same way: every rank decodes the part it holds (sharded.inflate_sharded) ----
+    inflate = None
+    try:
+        inflate = sharded_inflate_legs(args, torch, dist, dev, rank, world, ctx, buf, hist, local, res, out_bytes, plan, total)
+    except Exception as e:   # the deflate line must not die with the inflate legs
+        inflate = {"error": repr(e)}
+    dist.barrier()
+
     # ---- e2e: every rank's shard from pinned host memory through zs_deflate_part + the exchange ----
     numa = bind_numa(torch, local_rank)
     h_buf = torch.empty(hist + n, dtype=torch.uint8, pin_memory=True)
@@ -863,6 +945,7 @@ def run_sharded(args, torch, dist, dev, rank, local_rank, world):
                     "copy_ceiling_note": "every rank's H2D and D2H bytes of one step copied concurrently with no kernels, max over ranks",
                     "numa_node_rank0": numa},
             "single_gpu_same_workload": single,
+            "inflate": inflate,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,
@@ -893,6 +976,8 @@ def main():
     ap.add_argument("--total-mib", type=int, default=4096, help="configs[2]: size of the one sharded corpus (MiB)")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--force-sharded", action="store_true", help="run the N > 1 code path with however many ranks there are "
+                    "(one rank: a check of that path on a single GPU, not a bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -907,7 +992,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 or args.force_sharded:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
         run_sharded(args, torch, dist, dev, rank, local_rank, world)
         dist.barrier()

@@ -144,3 +144,46 @@ def test_null_part_with_history_is_an_argument_error(gpu_ctx):
     torch.cuda.synchronize()
     nbytes = int.from_bytes(bytes(res[:8].cpu().numpy()), "little")
     assert zlib.decompress(bytes(out[:nbytes].cpu().numpy())) == b""
+
+
+def test_inflate_parts_round_trip(gpu_ctx, oracle):
+    """The inverse split (sharded.inflate_part / inflate_sharded): the parts of one stream, as deflate_sharded
+    leaves them on the ranks, are inflated one by one -- rank 0's with the wrapper's windowBits, the later ones
+    raw with the 32 KiB before their range as preset dictionary -- and their checksums folded with *_combine.
+    Ranks are emulated on one GPU: large parts (segment-parallel decoder, with and without flush points inside),
+    small ones (one warp), an empty range in the middle."""
+    import torch
+    S, B, capi = pkg("sharded"), pkg("batch"), pkg("capi")
+    data = make_mixed(6 << 20, 11)
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    chunk = 65536
+    cuts_list = ([0, 40, 40, 90, 96], [0, 1, 2, 96], [0, 96])      # chunk ranges per emulated rank
+    for wrap, kind, ref in ((1, capi.KIND_ADLER32, zlib.adler32(data)), (2, capi.KIND_CRC32, zlib.crc32(data)), (0, None, 0)):
+        for cuts in cuts_list:
+            for sync in (0, B.FLAG_SYNC):
+                world = len(cuts) - 1
+                check, total, pos = None, 0, 0
+                for r in range(world):
+                    b0, b1 = cuts[r] * chunk, cuts[r + 1] * chunk
+                    hist = min(b0, 32768)
+                    res = B.deflate_batch_dev(t[b0:b1], chunk, 6, wrap, B.MODE_STITCHED, S.part_flags(r, world) | sync, history=hist)
+                    rr = res.read_result()
+                    assert rr.total_out_bits == 8 * rr.total_out_bytes
+                    ip = S.inflate_part(res.out, int(rr.total_out_bytes), b1 - b0, wrap, r == 0, t[b0 - hist: b0] if hist else None)
+                    last = r == world - 1
+                    # a lone part is a whole stream with its trailer; otherwise only the last part ends the stream
+                    assert ip.status == (capi.Z_STREAM_END if last else capi.Z_BUF_ERROR), (wrap, cuts, r, ip.status)
+                    assert ip.out_len == b1 - b0 and ip.in_used == rr.total_out_bytes, (wrap, cuts, r, ip.out_len, ip.in_used)
+                    assert torch.equal(ip.out[: ip.out_len], t[b0:b1]), (wrap, cuts, r)
+                    if kind is not None:
+                        assert ip.check == int(rr.check)
+                        check = ip.check if check is None else (B.adler32_combine if kind == capi.KIND_ADLER32 else B.crc32_combine)(check, ip.check, ip.out_len)
+                    total += ip.out_len
+                assert total == len(data)
+                if kind is not None:
+                    assert check == ref, (wrap, cuts)
+    # the collective form on one rank (no process group): plan = the part's own numbers
+    res, rr, plan = S.deflate_sharded(t, 262144, 6, 1)
+    ip, iplan = S.inflate_sharded(res.out, int(rr.total_out_bytes), len(data), 1)
+    assert ip.status == capi.Z_STREAM_END and torch.equal(ip.out[: ip.out_len], t)
+    assert iplan.check == plan.check == zlib.adler32(data) and iplan.total_len == len(data) and iplan.total_bits == 8 * rr.total_out_bytes

@@ -365,3 +365,49 @@ def test_window_bits_zero_is_a_zlib_stream(gpu_ctx):
     assert out == b"" and r != Z.Z_STREAM_END
     out, r, total_in = chunked_inflate(stream, 0, 7, 4096)
     assert r == Z.Z_STREAM_END and out == data and total_in == len(stream)
+
+
+def test_stream_loop_in_c(gpu_ctx):
+    """The driver loop of src/mod/streams.ts:78-93,139-170 in C (bindings/c/stream_pump.c: 32 KiB slices with
+    Z_NO_FLUSH, the last one with Z_FINISH, 64 KiB output buffers) -- what bench.py measures the stream API with.
+    Calls arrive within microseconds of each other here, so a long stream's decode attempts are paced by the shim
+    (zs_stream.cu): the results must not depend on when the attempts run."""
+    import ctypes as C
+    import numpy as np
+    from tools import streampump
+    capi = pkg("capi")
+    lib = capi.load()
+    data = np.frombuffer(make_text(5 << 20, 123), dtype=np.uint8)
+    big = np.empty(data.size + (1 << 20), dtype=np.uint8)
+    for level, wbits in ((1, 31), (6, 15), (6, -15)):
+        zs = capi.ZStream()
+        assert lib.zs_stream_deflate_init(gpu_ctx.handle, C.byref(zs), level, 8, wbits, 8, 0) == 0
+        rc, made, calls = streampump.pump(lib.zs_stream_deflate, zs, data, big)
+        assert rc == 1 and zs.total_in == data.size and zs.total_out == made and calls >= data.size // 32768
+        assert lib.zs_stream_deflate_end(C.byref(zs)) == 0
+        comp = big[:made].copy()
+        assert zlib.decompress(comp.tobytes(), wbits) == data.tobytes()
+        co = zlib.compressobj(6, zlib.DEFLATED, wbits)
+        czlib = np.frombuffer(co.compress(data.tobytes()) + co.flush(), dtype=np.uint8)   # no flush points inside
+        for src in (comp, czlib):
+            zs = capi.ZStream()
+            assert lib.zs_stream_inflate_init(gpu_ctx.handle, C.byref(zs), wbits) == 0
+            rc, made, calls = streampump.pump(lib.zs_stream_inflate, zs, src, big)
+            assert rc == 1, (rc, zs.msg)
+            assert made == data.size and zs.total_in == src.size and zs.total_out == made
+            assert np.array_equal(big[:made], data)
+            if wbits == 31:
+                assert zs.adler == zlib.crc32(data.tobytes())
+            if wbits == 15:
+                assert zs.adler == zlib.adler32(data.tobytes())
+            assert lib.zs_stream_inflate_end(C.byref(zs)) == 0
+    # a truncated stream: Z_BUF_ERROR under Z_FINISH, everything decodable delivered
+    co = zlib.compressobj(6)
+    whole = co.compress(data.tobytes()) + co.flush()
+    cut = np.frombuffer(whole[: len(whole) * 2 // 3], dtype=np.uint8)
+    zs = capi.ZStream()
+    assert lib.zs_stream_inflate_init(gpu_ctx.handle, C.byref(zs), 15) == 0
+    rc, made, calls = streampump.pump(lib.zs_stream_inflate, zs, cut, big)
+    assert rc == capi.Z_BUF_ERROR
+    assert big[:made].tobytes() == zlib.decompressobj().decompress(cut.tobytes())
+    assert lib.zs_stream_inflate_end(C.byref(zs)) == 0

@@ -186,33 +186,64 @@ __device__ bool spec_header_ok(const uint8_t* in, uint64_t in_len, uint64_t safe
     return true;
 }
 
+// The 17-bit test alone: BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29, room for a whole header (1 position in 9 passes).
+__device__ __forceinline__ bool spec_quick_ok(const uint8_t* in, uint64_t in_len, uint64_t safe_end, uint64_t p) {
+    if ((p >> 3) + 40 > in_len) return false;
+    const unsigned w = (unsigned)peek_bits57(in, safe_end, p);
+    return (w & 7u) == 4u && ((w >> 3) & 31u) <= 29u && ((w >> 8) & 31u) <= 29u;
+}
+
 constexpr unsigned kSpecWarpsPerTile = 4;
-__global__ void __launch_bounds__(128) par_spec_kernel(ParArgs a) {
+constexpr unsigned kSpecWarpsPerCta = 4;
+__global__ void __launch_bounds__(32 * kSpecWarpsPerCta) par_spec_kernel(ParArgs a) {
     // few markers for the size of the input?  (a stream with flush points needs no guessing)
     if (a.state[5] == ~0ull || a.marker_count[0] * (256ull << 10) >= a.in_len) return;
-    const unsigned lane = zs_lane();
-    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // Two stages, so that the expensive one runs on full warps: every lane puts its bit position through the 17-bit
+    // test and the survivors -- 3 or 4 of 32 -- are queued, in order; once 32 are waiting, each lane takes one
+    // through the rest of the header test.  (Run straight through, the code-length-code and run-length stages were
+    // executed for those 3 or 4 lanes in nearly every iteration: 40 ms per 420 MB of input, the largest kernel of
+    // the one-stream decode of a stream without flush points.)
+    __shared__ uint32_t s_queue[kSpecWarpsPerCta][64];
+    const unsigned lane = zs_lane(), wq = threadIdx.x >> 5;
+    const uint64_t w = (uint64_t)blockIdx.x * kSpecWarpsPerCta + wq;
     const uint64_t t = w / kSpecWarpsPerTile, part = w % kSpecWarpsPerTile;
     if (t + 1 >= a.n_slots || a.cand[t + 1] != ~0ull) return;   // (markers were found by par_scan_kernel, which ran before)
-    const uint64_t tile_bits = a.tile * 8, part_bits = tile_bits / kSpecWarpsPerTile;
+    const uint64_t tile_bits = a.tile * 8, part_bits = tile_bits / kSpecWarpsPerTile;   // < 2^32: a tile is in_len / 6144 bytes
     uint64_t lo = t * tile_bits + part * part_bits, hi = lo + part_bits;
     const uint64_t body = a.state[5];
     if (lo <= body) lo = body + 1;                            // slot 0 is the true start
     if (hi > a.in_len * 8) hi = a.in_len * 8;
     const uint64_t safe_end = (a.in_len + 7) & ~7ull;
-    for (uint64_t p0 = lo; p0 < hi; p0 += 32) {
+    uint32_t* queue = s_queue[wq];
+    unsigned qn = 0;                                          // queued positions (relative to lo, increasing), warp-uniform
+    uint64_t found = ~0ull;
+    for (uint64_t p0 = lo; p0 < hi && found == ~0ull; p0 += 32) {
         const uint64_t p = p0 + lane;
-        const bool ok = p < hi && spec_header_ok(a.in, a.in_len, safe_end, p);
-        const unsigned m = __ballot_sync(ZS_FULL_MASK, ok);
-        if (m) {
-            if (lane == 0) {
-                const unsigned long long found = p0 + (unsigned)(__ffs((int)m) - 1);
-                const unsigned long long old = atomicMin((unsigned long long*)&a.spec[t + 1], found);
-                (void)old;
+        const bool pass = p < hi && spec_quick_ok(a.in, a.in_len, safe_end, p);
+        const unsigned m = __ballot_sync(ZS_FULL_MASK, pass);
+        if (pass) queue[qn + __popc(m & zs_lanemask_lt())] = (uint32_t)(p - lo);
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32u) {
+            const bool ok = spec_header_ok(a.in, a.in_len, safe_end, lo + queue[lane]);
+            const unsigned mm = __ballot_sync(ZS_FULL_MASK, ok);
+            if (mm) {
+                found = lo + queue[__ffs((int)mm) - 1];       // the queue is in position order: the lowest lane is the first find
+            } else {
+                const uint32_t rest = lane + 32u < qn ? queue[lane + 32u] : 0u;
+                __syncwarp();
+                queue[lane] = rest;
+                qn -= 32u;
+                __syncwarp();
             }
-            break;
         }
     }
+    if (found == ~0ull && qn) {                               // what is left in the queue (< 32 positions)
+        const bool ok = lane < qn && spec_header_ok(a.in, a.in_len, safe_end, lo + queue[lane]);
+        const unsigned mm = __ballot_sync(ZS_FULL_MASK, ok);
+        if (mm) found = lo + queue[__ffs((int)mm) - 1];
+    }
+    if (found != ~0ull && lane == 0) atomicMin((unsigned long long*)&a.spec[t + 1], (unsigned long long)found);
 }
 // the speculative finds become candidates (kept apart until every part of a tile has reported its first)
 __global__ void par_spec_merge_kernel(ParArgs a) {
@@ -639,7 +670,8 @@ int zs_launch_inflate_parallel(zs_ctx* ctx, const uint8_t* d_in, uint64_t in_len
     if (p.n_slots > 1 && !getenv("ZS_INFLATE_NO_SPEC")) {
         ZS_CUDA_TRY(ctx, cudaMemsetAsync(p.spec, 0xff, (size_t)p.n_slots * 8, ctx->stream));
         const uint64_t warps = (uint64_t)(p.n_slots - 1) * kSpecWarpsPerTile;
-        ZS_KERNEL(ctx, "par_spec_kernel", par_spec_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(p));
+        ZS_KERNEL(ctx, "par_spec_kernel",
+                  par_spec_kernel<<<(unsigned)((warps + kSpecWarpsPerCta - 1) / kSpecWarpsPerCta), 32 * kSpecWarpsPerCta, 0, ctx->stream>>>(p));
         ZS_KERNEL(ctx, "par_spec_merge_kernel", par_spec_merge_kernel<<<(p.n_slots + 255) / 256, 256, 0, ctx->stream>>>(p));
     }
     unsigned ctas = (p.n_slots + kWarps - 1) / kWarps;

@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <mutex>
 #include <vector>
 
 #include "zs_common.cuh"
@@ -74,12 +76,109 @@ struct RawBuf {
     }
 };
 
+// Host byte buffer of the deflate shim: ordinary memory while it is small, page-locked once it holds a part's
+// worth of data -- a pageable cudaMemcpy is staged through the driver's bounce buffers at a few GB/s, which was
+// most of a CompressionStream's time (64 MiB of text: 47 ms, of which the kernels took 4.3).  Page-locking costs
+// about as much as one such copy, so the large buffers are handed from stream to stream through a small pool.
+constexpr size_t kPinAbove = 1u << 20;
+struct PinPool {
+    std::mutex mu;
+    struct Item { uint8_t* p; size_t cap; };
+    std::vector<Item> free_list;
+    uint8_t* take(size_t want, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].cap >= want) {
+                    Item it = free_list[i];
+                    free_list.erase(free_list.begin() + i);
+                    *cap = it.cap;
+                    return it.p;
+                }
+        }
+        void* q = nullptr;
+        if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *cap = want;
+        return (uint8_t*)q;
+    }
+    void give(uint8_t* p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (free_list.size() < 4) { free_list.push_back({p, cap}); return; }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinPool& pin_pool() { static PinPool* pool = new PinPool(); return *pool; }   // never destroyed: outlives the CUDA runtime's teardown
+
+struct HostBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { release(); }
+    void release() {
+        if (p) { if (pinned) pin_pool().give(p, cap); else free(p); }
+        p = nullptr; n = cap = 0; pinned = false;
+    }
+    uint8_t* data() { return p; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+    // `part_hint`: the size a large buffer is expected to reach (one part of input / its bound of output)
+    bool reserve(size_t want, size_t part_hint) {
+        if (want <= cap) return true;
+        size_t c = cap + (cap >> 1);
+        if (c < want) c = want;
+        if (c >= kPinAbove) {
+            if (c < part_hint) c = part_hint;
+            size_t got = 0;
+            uint8_t* q = pin_pool().take(c, &got);
+            if (q) {
+                if (n) memcpy(q, p, n);
+                if (p) { if (pinned) pin_pool().give(p, cap); else free(p); }
+                p = q; cap = got; pinned = true;
+                return true;
+            }
+        }
+        if (pinned) {   // no more page-locked memory: carry on in ordinary memory
+            uint8_t* q = (uint8_t*)malloc(c);
+            if (!q) return false;
+            if (n) memcpy(q, p, n);
+            pin_pool().give(p, cap);
+            p = q; cap = c; pinned = false;
+            return true;
+        }
+        uint8_t* q = (uint8_t*)realloc(p, c ? c : 1);
+        if (!q) return false;
+        p = q; cap = c;
+        return true;
+    }
+    bool append(const uint8_t* src, size_t k, size_t part_hint) {
+        if (!reserve(n + k, part_hint)) return false;
+        if (k) memcpy(p + n, src, k);
+        n += k;
+        return true;
+    }
+    bool push_back(uint8_t b) { return append(&b, 1, 0); }
+    bool grow(size_t k, size_t part_hint) {   // k more bytes, left uninitialised
+        if (!reserve(n + k, part_hint)) return false;
+        n += k;
+        return true;
+    }
+};
+
 enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
 constexpr size_t kPartThreshold = 16u << 20;
-// inflate: streams shorter than this are decoded on every call, so the call that brings the last byte of the
-// stream returns Z_STREAM_END and hands back what follows it through avail_in, exactly like the reference.
-// Longer streams are decoded in batches (see zs_stream_inflate): the end may be found in a later call, when
-// input that arrived earlier can only be accounted for in total_in ("Streaming inflate").
+constexpr size_t kPartOutHint = kPartThreshold + (kPartThreshold >> 6) + (64u << 10);   // a part's output: the stored-block bound and change
+// inflate: while a stream has brought less input than this it is decoded on EVERY call, so the call that brings the
+// last byte of a short stream returns Z_STREAM_END and hands back what follows it through avail_in, exactly like the
+// reference, however fast the calls arrive.  Longer streams are paced (see zs_stream_inflate): the end may be found in
+// a later call, when input that arrived earlier can only be accounted for in total_in ("Streaming inflate").
 constexpr size_t kEveryCallBelow = 256u << 10;
 
 struct DeflateState {
@@ -87,8 +186,8 @@ struct DeflateState {
     zs_ctx* ctx = nullptr;
     int level = 6, strategy = 0, wrap = 1, status = ST_INIT, last_flush = -2;
     std::vector<uint8_t> hist;      // last <= 32 KiB already compressed (or the preset dictionary)
-    std::vector<uint8_t> in;        // buffered, not yet compressed
-    std::vector<uint8_t> out;       // compressed, not yet delivered
+    HostBuf in;                     // buffered, not yet compressed: at most one part (kPartThreshold)
+    HostBuf out;                    // compressed, not yet delivered
     size_t out_pos = 0;
     bool header_done = false, any_part = false, trailer_done = false, have_dict = false;
     uint32_t check = 0, dict_id = 0;
@@ -119,6 +218,8 @@ struct InflateState {
     size_t out_pushed = 0;          // bytes of `out` already copied to `ready`
     size_t next_attempt = 0;
     bool fresh_input = false;       // input has arrived since the last attempt
+    double attempt_end = 0.0;       // monotonic clock at the end of the last attempt ...
+    double attempt_cost = 0.0;      // ... and how long it took (seconds): the pacing of a long stream's attempts
     size_t out_cap_hint = 1 << 20;
     bool body = false;              // the wrapper header is behind us: raw blocks from start_bit
     uint64_t start_bit = 0;         // of the next block header inside `in`
@@ -136,6 +237,16 @@ struct InflateState {
 
 int rank_of(int f) { return f * 2 - (f > 4 ? 9 : 0); }  // RANK, deflate.ts:105
 
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+// inflate: a long stream whose calls arrive faster than attempts complete waits kPaceFactor x the duration of its
+// last attempt before the next one, or until this much undecoded input is buffered
+constexpr double kPaceFactor = 2.0;
+constexpr size_t kAttemptAtLeastEvery = 64u << 20;
+
 DeflateState* dstate(zs_stream* s) {
     if (!s || !s->state) return nullptr;
     DeflateState* st = (DeflateState*)s->state;
@@ -152,6 +263,15 @@ void put_be32(std::vector<uint8_t>& v, uint32_t x) {
 }
 void put_le32(std::vector<uint8_t>& v, uint32_t x) {
     v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 24));
+}
+
+void put_be32(HostBuf& v, uint32_t x) {
+    const uint8_t b[4] = {(uint8_t)(x >> 24), (uint8_t)(x >> 16), (uint8_t)(x >> 8), (uint8_t)x};
+    v.append(b, 4, 0);
+}
+void put_le32(HostBuf& v, uint32_t x) {
+    const uint8_t b[4] = {(uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24)};
+    v.append(b, 4, 0);
 }
 
 // crc32 of a few header bytes on the host (framing only; payload checksums are computed on the GPU)
@@ -184,7 +304,7 @@ void put_gzip_header(DeflateState* st) {
         const uint32_t c = host_crc32(h.data(), h.size());
         h.push_back((uint8_t)c); h.push_back((uint8_t)(c >> 8));
     }
-    st->out.insert(st->out.end(), h.begin(), h.end());
+    st->out.append(h.data(), h.size(), 0);
 }
 
 // Compress everything buffered as one part.  `finish` makes it the last part of the stream.
@@ -230,8 +350,9 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (res.total_out_bytes > cap) return ZS_BUF_ERROR;
     const size_t old = st->out.size();
-    st->out.resize(old + res.total_out_bytes);
-    ZS_CUDA_TRY(ctx, cudaMemcpy(st->out.data() + old, st->d_out.p, res.total_out_bytes, cudaMemcpyDeviceToHost));
+    if (!st->out.grow(res.total_out_bytes, kPartOutHint)) return ZS_MEM_ERROR;
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(st->out.data() + old, st->d_out.p, res.total_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // running check over the uncompressed data (read_buf, deflate.ts:155-159)
     if (st->wrap == ZS_WRAP_ZLIB) st->check = st->total_in_len || st->any_part ? zs_host_adler32_combine(st->check, res.check, n) : res.check;
     else if (st->wrap == ZS_WRAP_GZIP) st->check = st->total_in_len || st->any_part ? zs_host_crc32_combine(st->check, res.check, n) : res.check;
@@ -262,7 +383,7 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     return ZS_OK;
 }
 
-void drain(zs_stream* strm, std::vector<uint8_t>& out, size_t& pos) {
+void drain(zs_stream* strm, HostBuf& out, size_t& pos) {
     size_t avail = out.size() - pos;
     size_t c = avail < strm->avail_out ? avail : (size_t)strm->avail_out;
     if (c) {
@@ -336,6 +457,7 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
         return ZS_STREAM_ERROR;
     }
     if (strm->avail_out == 0) { strm->msg = "buffer error"; return ZS_BUF_ERROR; }
+    cudaSetDevice(st->ctx->device);   // (the buffers below may be page-locked: on this context's device, not on device 0)
     const int old_flush = st->last_flush;
     st->last_flush = flush;
     if (st->out_pos < st->out.size()) {
@@ -350,11 +472,23 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
         if (st->wrap == 1 && !st->have_dict) strm->adler = 1u;
         st->status = ST_BUSY;
     }
-    if (strm->avail_in) {
-        st->in.insert(st->in.end(), strm->next_in, strm->next_in + strm->avail_in);
-        strm->next_in += strm->avail_in;
-        strm->total_in += strm->avail_in;
-        strm->avail_in = 0;
+    // Input is buffered one part at a time: a call that brings more than a part compresses full parts as it goes
+    // and comes back for output room when a part's output does not fit (Z_OK with avail_in > 0, as in the reference).
+    while (strm->avail_in) {
+        const size_t room = kPartThreshold > st->in.size() ? kPartThreshold - st->in.size() : 0;
+        const size_t take = strm->avail_in < room ? (size_t)strm->avail_in : room;
+        if (!st->in.append(strm->next_in, take, kPartThreshold)) { strm->msg = "insufficient memory"; return ZS_MEM_ERROR; }
+        strm->next_in += take;
+        strm->total_in += take;
+        strm->avail_in -= take;
+        if (strm->avail_in == 0 || st->status != ST_BUSY) break;
+        const int rc = run_part(strm, st, false, false);
+        if (rc != ZS_OK) {
+            strm->msg = zs_last_error(st->ctx);
+            return rc;
+        }
+        drain(strm, st->out, st->out_pos);
+        if (st->out_pos < st->out.size()) { st->last_flush = -1; return ZS_OK; }
     }
     if (st->status == ST_BUSY) {
         int rc = ZS_OK;
@@ -367,7 +501,7 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
             } else {
                 // nothing new since the last flush point: just the marker (deflate.ts:945-946)
                 static const uint8_t marker[5] = {0, 0, 0, 0xff, 0xff};
-                st->out.insert(st->out.end(), marker, marker + 5);
+                st->out.append(marker, 5, 0);
                 if (flush == ZS_FULL_FLUSH) st->hist.clear();
             }
         } else if (st->in.size() >= kPartThreshold) {
@@ -626,9 +760,11 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
     if (st->await_trailer) return finish_stream(st);
     const int raw_wb = st->window_bits == -16 ? -16 : -15;
     for (;;) {
-        const uint64_t in_off[2] = {0, st->in.size()}, out_off[2] = {0, st->out_cap_hint};
         // `out` is rebuilt by every attempt; what was queued from it stays in `ready`
         if (st->out_cap_hint < 4 * st->in.size()) st->out_cap_hint = 4 * st->in.size();   // a typical ratio: fewer re-decodes
+        // (the capacity handed to the decoder must be the one the "output full" test below compares with: taken before
+        // the line above, a large attempt stopped at the old capacity and was mistaken for "input ran dry")
+        const uint64_t in_off[2] = {0, st->in.size()}, out_off[2] = {0, st->out_cap_hint};
         if (!st->out.resize(st->out_cap_hint)) return ZS_MEM_ERROR;
         uint64_t out_len = 0, in_used = 0, rng[2] = {0, st->hist.size()};
         uint32_t check = 0;
@@ -709,28 +845,34 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         }
         if (st->need_dict) return ZS_NEED_DICT;
         fill_gz_header(st);
-        // `in` holds only what follows the last resume point, so an attempt costs the current block plus
-        // the new input: every call while that is short, then whenever it has grown by half (a single
-        // huge block is decoded from its start each time); any flush request decodes now
-        // ... and so does a call that brings no new input while some of what is buffered has not been through an
-        // attempt yet (a caller that never sends Z_FINISH must still reach Z_STREAM_END)
+        // `in` holds only what follows the last resume point, so an attempt costs the current block plus the new
+        // input (a single huge block is decoded from its start each time).  When is one due?
+        //  * on every call while the stream is short (kEveryCallBelow), on any flush request, and on a call that
+        //    brings no new input while some of what is buffered has not been through an attempt yet (a caller that
+        //    never sends Z_FINISH must still reach Z_STREAM_END);
+        //  * otherwise attempts are PACED by what they cost: the next one runs once kPaceFactor x the duration of
+        //    the last one has passed since it ended (or 64 MiB of undecoded input have piled up).  An attempt costs
+        //    the latency of one warp decoding one segment twice (count pass, decode pass: ~13 ms) plus the serial
+        //    decoder on what follows the last flush point however little input it holds, while a large one goes
+        //    through the segment-parallel decoder (zs_inflate_par.cu) at GB/s.  A caller that is slower than the
+        //    decoder -- a socket, an interactive protocol, anything that waits for output -- therefore gets an
+        //    attempt on EVERY call, exactly like the reference: progress, Z_STREAM_END and the hand-back of trailing
+        //    bytes through avail_in happen in the call that brings the bytes.  A caller that feeds from memory, calls
+        //    microseconds apart, gets a few large attempts; between them inflate(Z_NO_FLUSH) consumes input without
+        //    producing output, which the zlib contract allows.
+        //    (Round 2 first doubled the batches of a long stream -- an attempt when as much input as had been seen had
+        //    arrived again: 0.22-0.26 GB/s for a 64 MiB stream fed in 32 KiB slices, nine attempts of ~20 ms.)
         if (in0) st->fresh_input = true;
-        const bool due = flush != ZS_NO_FLUSH || st->in.size() >= st->next_attempt || (in0 == 0 && st->fresh_input);
+        bool due = flush != ZS_NO_FLUSH || st->in.size() >= st->next_attempt || (in0 == 0 && st->fresh_input);
+        if (!due && st->fresh_input && now_s() - st->attempt_end >= kPaceFactor * st->attempt_cost) due = true;
         if (due && !st->in.empty()) {
+            const double t_begin = now_s();
             int rc = inflate_attempt(strm, st);
             if (rc != ZS_OK) return rc;
             st->fresh_input = false;
-            // Short streams are decoded on every call.  A long stream is decoded in batches that double (the input seen
-            // so far, at most 64 MiB, must arrive again before the next attempt): an attempt costs the latency of one
-            // warp decoding one flush-point segment twice (count pass, decode pass: ~13 ms) plus the serial decoder on
-            // what follows the last flush point (~7 ms) however little input it holds, and a large one goes through
-            // the segment-parallel decoder (zs_inflate_par.cu) at GB/s.  Measured on a 64 MiB text stream fed in
-            // 32 KiB slices: every call below 1 MiB and +25 % batches up to 8 MiB gave 0.05-0.09 GB/s.
-            const size_t seen = (size_t)strm->total_in;
-            size_t grain = seen;
-            if (grain > (64u << 20)) grain = 64u << 20;
-            if (seen < kEveryCallBelow) st->next_attempt = st->in.size() + 1;
-            else st->next_attempt = st->in.size() + (grain > st->in.size() / 2 ? grain : st->in.size() / 2);
+            st->attempt_end = now_s();
+            st->attempt_cost = st->attempt_end - t_begin;
+            st->next_attempt = st->in.size() + ((size_t)strm->total_in < kEveryCallBelow ? 1 : kAttemptAtLeastEvery);
             if (st->need_dict) {
                 strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
                 return ZS_NEED_DICT;
@@ -801,6 +943,7 @@ int zs_stream_inflate_reset(zs_stream* strm) {
     st->ready_pos = st->out_pushed = 0;
     st->next_attempt = 0;
     st->fresh_input = false;
+    st->attempt_end = st->attempt_cost = 0.0;
     st->body = st->await_trailer = false;
     st->start_bit = 0;
     st->trailer = 0;

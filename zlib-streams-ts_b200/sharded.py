@@ -161,6 +161,80 @@ def deflate_sharded_host(h_buf: torch.Tensor, history: int, chunk_size: int, lev
     return res, plan
 
 
+@dataclass
+class InflatePart:
+    out: torch.Tensor         # uint8: this rank's range of the stream's output (capacity >= out_len)
+    result: torch.Tensor      # int64 [4] on the device: out_len, in_used, check (unused), status
+    out_len: int
+    in_used: int
+    status: int               # Z_STREAM_END on the rank that holds the final block, Z_BUF_ERROR (input ran dry) before it
+    check: int                # adler32 / crc32 of this rank's output (0 for raw streams)
+
+
+def inflate_part(part: torch.Tensor, part_bytes: int, out_cap: int, wrap: int, first: bool,
+                 d_hist: torch.Tensor | None = None, ctx=None, reuse: InflatePart | None = None) -> InflatePart:
+    """Inflate ONE part of a sharded stream on this GPU (no communication): see inflate_sharded.  `first`: the
+    part begins with the wrapper header (rank 0's part)."""
+    import ctypes as C
+
+    from . import batch as B
+    assert part.is_cuda and part.dtype == torch.uint8 and part.data_ptr() % 8 == 0
+    dev = part.device
+    ctx = ctx or B.default_context(dev.index)
+    if reuse is not None:
+        out, result = reuse.out, reuse.result
+    else:
+        out = torch.empty(out_cap + 64, dtype=torch.uint8, device=dev)
+        result = torch.zeros(4, dtype=torch.int64, device=dev)
+    window_bits = -15
+    if first:
+        window_bits = -15 if wrap == capi.WRAP_RAW else 15 if wrap == capi.WRAP_ZLIB else 31
+        d_hist = None
+    p = result.data_ptr()
+    hist_len = d_hist.numel() if d_hist is not None else 0
+    rc = capi.load().zs_inflate_stream_dev(ctx.handle, C.c_void_p(part.data_ptr()), part_bytes, window_bits,
+                                           C.c_void_p(out.data_ptr()), out_cap, C.c_void_p(p), C.c_void_p(p + 8),
+                                           C.c_void_p(p + 16), C.c_void_p(p + 24),
+                                           C.c_void_p(d_hist.data_ptr()) if hist_len else None, hist_len)
+    ctx.check(rc, "zs_inflate_stream_dev")
+    out_len, in_used, _, status = (int(x) for x in result.cpu())
+    status &= 0xFFFFFFFF
+    if status & 0x80000000:
+        status -= 1 << 32
+    kind = None if wrap == capi.WRAP_RAW else (capi.KIND_ADLER32 if wrap == capi.WRAP_ZLIB else capi.KIND_CRC32)
+    check = 0
+    if kind is not None:   # (an empty range: the checksum of nothing is its initial value)
+        check = B.checksum_dev(out[:out_len], kind, ctx=ctx) if out_len else (1 if kind == capi.KIND_ADLER32 else 0)
+    return InflatePart(out, result, out_len, in_used, status, check)
+
+
+def inflate_sharded(part: torch.Tensor, part_bytes: int, out_cap: int, wrap: int, d_hist: torch.Tensor | None = None,
+                    group=None, ctx=None, reuse: InflatePart | None = None):
+    """The inverse of deflate_sharded: every rank inflates the part of the stream it holds (GPU), then the ranks
+    fold their checksums and lengths with the same exchange step.
+
+    `part` is what deflate_sharded left on this rank (bit 0 of the part = byte 0 of the tensor: parts of one
+    stream are byte aligned, every non-last part ends with the Z_SYNC_FLUSH marker of deflate.ts:945-946), 8-byte
+    aligned, `part_bytes` long.  Rank 0's part begins with the wrapper header and is decoded with the wrapper's
+    windowBits; every later part is raw deflate whose back references reach into the previous rank's output, so
+    it is given `d_hist`, the <= 32 KiB of the stream that precede its range (what deflate_sharded primed it with),
+    as a preset dictionary (inflateSetDictionary, inflate.ts:1220).  A part is ONE stream for the decoder: it goes
+    through the segment-parallel path of zs_inflate_stream_dev (cut at flush points, else at located block
+    headers).  Only the last rank's part holds the final block, so it alone ends with Z_STREAM_END; the others run
+    out of input at their marker (Z_BUF_ERROR under Z_FINISH, inflate.ts:1092-1098) with all of their output written.
+    The wrapper trailer is not part of any part (wrapper_trailer() makes it from the folded checksum): the caller
+    compares plan.check with the trailer it holds.
+
+    Returns (InflatePart, StitchPlan): plan.check = checksum of the whole output, plan.total_len its length,
+    plan.bit_offset[r] = 8 x the compressed bytes the ranks before r consumed.
+    """
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ip = inflate_part(part, part_bytes, out_cap, wrap, rank == 0, d_hist, ctx=ctx, reuse=reuse)
+    kind = None if wrap == capi.WRAP_RAW else (capi.KIND_ADLER32 if wrap == capi.WRAP_ZLIB else capi.KIND_CRC32)
+    plan = exchange_meta(ip.in_used * 8, ip.check, ip.out_len, kind, 0, device=part.device, group=group)
+    return ip, plan
+
+
 def gather_stream(res, rr, plan: StitchPlan, wrap: int, dst: int = 0, group=None):
     """One contiguous stream on rank `dst`: byte gather of the parts + bit-shift stitch (K9)."""
     import ctypes as C
@@ -189,4 +263,6 @@ def gather_stream(res, rr, plan: StitchPlan, wrap: int, dst: int = 0, group=None
                                         C.c_void_p(part.data_ptr()), nbits), "zs_bit_concat_dev")
     torch.cuda.synchronize(dev)
     body = out[:total_bytes].cpu().numpy().tobytes()
+    if world == 1:
+        return body   # a lone part is a whole stream: the engine framed it, trailer included
     return body + wrapper_trailer(wrap, plan.check, plan.total_len)
