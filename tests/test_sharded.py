@@ -63,6 +63,18 @@ def _worker(rank, world, port, wrap, q):
         if wrap == 2:
             ok &= plan.check == zlib.crc32(data)
         ok &= plan.total_len == len(data)
+    # The inverse split (sharded.inflate_sharded's contract, with the oracle standing in for the GPU decoder): every
+    # rank inflates the part it holds -- rank 0 with the wrapper's windowBits, the others raw with the 32 KiB before
+    # their range as preset dictionary -- only the last part ends with Z_STREAM_END, the others run out of input
+    # behind their Z_SYNC_FLUSH marker (Z_BUF_ERROR under Z_FINISH) with all of their output written; the same
+    # exchange step folds the checksums and lengths.
+    wb = {0: -15, 1: 15, 2: 31}[wrap] if rank == 0 else -15
+    ret, out, used, _ = O.inflate(part, wb, len(local) + 64, None if rank == 0 else (data[max(0, b0 - 32768): b0] or None))
+    ok &= ret == (O.Z_STREAM_END if last else O.Z_BUF_ERROR) and out == local and used == len(part)
+    out_check = 0 if wrap == 0 else (zlib.adler32(out) if wrap == 1 else zlib.crc32(out))
+    iplan = S.exchange_meta(used * 8, out_check, len(out), kind)
+    ok &= iplan.check == plan.check and iplan.total_len == len(data) and iplan.total_bits == plan.total_bits
+    ok &= iplan.bit_offset == plan.bit_offset
     q.put((rank, bool(ok), plan.my_bit_offset))
     dist.barrier()
     dist.destroy_process_group()

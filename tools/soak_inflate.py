@@ -109,10 +109,10 @@ def api_child(budget, seed):
             pos += len(piece) - t.avail_in
             assert pos <= len(z)
         # total_in is always exact; the bytes behind the end come back through avail_in when the stream is shorter than
-        # the shim's every-call threshold (256 KiB of input) or the caller flushes -- a longer stream is decoded in
+        # the shim's every-call threshold (64 KiB of input) or the caller flushes -- a longer stream is decoded in
         # batches and may find its end one call after the input arrived ("Streaming inflate")
         assert bytes(got) == data and t.total_in == len(z) - 3, ("inflate stream", seed, it, n, wbits, t.total_in, len(z))
-        assert pos == len(z) - 3 or (len(z) >= (256 << 10) and pos <= len(z)), ("inflate stream hand-back", seed, it, n, wbits, pos, len(z))
+        assert pos == len(z) - 3 or (len(z) >= (64 << 10) and pos <= len(z)), ("inflate stream hand-back", seed, it, n, wbits, pos, len(z))
         assert Z.inflateEnd(t) == Z.Z_OK
     print(f"api soak ok: {it} streams each way, seed {seed}")
 

@@ -186,24 +186,40 @@ __device__ bool spec_header_ok(const uint8_t* in, uint64_t in_len, uint64_t safe
     return true;
 }
 
-// The 17-bit test alone: BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29, room for a whole header (1 position in 9 passes).
-__device__ __forceinline__ bool spec_quick_ok(const uint8_t* in, uint64_t in_len, uint64_t safe_end, uint64_t p) {
-    if ((p >> 3) + 40 > in_len) return false;
-    const unsigned w = (unsigned)peek_bits57(in, safe_end, p);
-    return (w & 7u) == 4u && ((w >> 3) & 31u) <= 29u && ((w >> 8) & 31u) <= 29u;
+// The 17-bit test -- BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29 -- for 32 consecutive bit positions at once:
+// bit i of the result is position i of the window `w` (>= 45 valid bits).  1 position in 9 passes.
+__device__ __forceinline__ uint32_t spec_quick_mask(uint64_t w) {
+    uint64_t m = ~w & ~(w >> 1) & (w >> 2);                            // 0, 0, 1: not final, dynamic
+    m &= ~((w >> 4) & (w >> 5) & (w >> 6) & (w >> 7));                 // HLIT (bits 3..7) is not 30 or 31
+    m &= ~((w >> 9) & (w >> 10) & (w >> 11) & (w >> 12));              // HDIST (bits 8..12) is not 30 or 31
+    return (uint32_t)m;
+}
+// The code-length code of the header at p is complete (Kraft sum of its HCLEN + 4 three-bit lengths = 1): what the
+// 17-bit test lets through fails here 99 times in 100, so this runs before anything that needs arrays.
+__device__ __forceinline__ bool spec_clcode_complete(const uint8_t* in, uint64_t safe_end, uint64_t p) {
+    const unsigned ncode = ((unsigned)(peek_bits57(in, safe_end, p + 13) & 15u)) + 4u;
+    uint64_t c = peek_bits57(in, safe_end, p + 17);                    // 57 bits = 19 lengths
+    if (ncode < 19u) c &= (1ull << (3u * ncode)) - 1ull;
+    const uint64_t weights = 0x0102040810204000ull;                    // byte l: 128 >> l (0 for an unused symbol)
+    unsigned kraft = 0;
+#pragma unroll
+    for (int i = 0; i < 19; i++) kraft += (unsigned)(weights >> (8u * ((unsigned)(c >> (3 * i)) & 7u))) & 0xffu;
+    return kraft == 128u;
 }
 
 constexpr unsigned kSpecWarpsPerTile = 4;
 constexpr unsigned kSpecWarpsPerCta = 4;
+constexpr unsigned kSpecQueue = 32 + 32 * 11;   // fewer than 32 waiting + at most 11 finds per lane (the pattern is 3 bits long)
 __global__ void __launch_bounds__(32 * kSpecWarpsPerCta) par_spec_kernel(ParArgs a) {
     // few markers for the size of the input?  (a stream with flush points needs no guessing)
     if (a.state[5] == ~0ull || a.marker_count[0] * (256ull << 10) >= a.in_len) return;
-    // Two stages, so that the expensive one runs on full warps: every lane puts its bit position through the 17-bit
-    // test and the survivors -- 3 or 4 of 32 -- are queued, in order; once 32 are waiting, each lane takes one
-    // through the rest of the header test.  (Run straight through, the code-length-code and run-length stages were
-    // executed for those 3 or 4 lanes in nearly every iteration: 40 ms per 420 MB of input, the largest kernel of
-    // the one-stream decode of a stream without flush points.)
-    __shared__ uint32_t s_queue[kSpecWarpsPerCta][64];
+    // Two stages, so that the expensive one runs on full warps.  Stage 1: a lane takes 32 consecutive bit positions
+    // through the 17-bit test with a dozen 64-bit operations (a warp: 128 bytes of input per iteration) and queues
+    // the survivors -- 1 in 9 -- in position order.  Stage 2: once 32 are waiting, each lane takes one through the
+    // rest of the header test, the Kraft sum of the code-length code first.  (Run straight through with a lane per
+    // position, the later stages were executed for 3 or 4 lanes in nearly every iteration: 40 ms per 420 MB of
+    // input, the largest kernel of the one-stream decode of a stream without flush points; queued: 18.8 ms.)
+    __shared__ uint32_t s_queue[kSpecWarpsPerCta][kSpecQueue];
     const unsigned lane = zs_lane(), wq = threadIdx.x >> 5;
     const uint64_t w = (uint64_t)blockIdx.x * kSpecWarpsPerCta + wq;
     const uint64_t t = w / kSpecWarpsPerTile, part = w % kSpecWarpsPerTile;
@@ -212,34 +228,58 @@ __global__ void __launch_bounds__(32 * kSpecWarpsPerCta) par_spec_kernel(ParArgs
     uint64_t lo = t * tile_bits + part * part_bits, hi = lo + part_bits;
     const uint64_t body = a.state[5];
     if (lo <= body) lo = body + 1;                            // slot 0 is the true start
-    if (hi > a.in_len * 8) hi = a.in_len * 8;
+    if (a.in_len < 40) return;
+    if (hi > (a.in_len - 39) * 8) hi = (a.in_len - 39) * 8;   // a whole header needs 40 bytes from the byte that holds p
     const uint64_t safe_end = (a.in_len + 7) & ~7ull;
     uint32_t* queue = s_queue[wq];
     unsigned qn = 0;                                          // queued positions (relative to lo, increasing), warp-uniform
     uint64_t found = ~0ull;
-    for (uint64_t p0 = lo; p0 < hi && found == ~0ull; p0 += 32) {
-        const uint64_t p = p0 + lane;
-        const bool pass = p < hi && spec_quick_ok(a.in, a.in_len, safe_end, p);
-        const unsigned m = __ballot_sync(ZS_FULL_MASK, pass);
-        if (pass) queue[qn + __popc(m & zs_lanemask_lt())] = (uint32_t)(p - lo);
-        qn += __popc(m);
+    for (uint64_t p0 = lo; p0 < hi && found == ~0ull; p0 += 1024) {
+        // stage 1
+        const uint64_t base = p0 + 32u * lane;
+        uint32_t m = 0;
+        if (base < hi) {
+            m = spec_quick_mask(peek_bits57(a.in, safe_end, base));
+            if (hi - base < 32) m &= (1u << (unsigned)(hi - base)) - 1u;
+        }
+        unsigned cnt = __popc(m), off = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(ZS_FULL_MASK, off, d);
+            if ((int)lane >= d) off += v;
+        }
+        const unsigned total = __shfl_sync(ZS_FULL_MASK, off, 31);
+        off = qn + off - cnt;
+        const uint32_t rel = (uint32_t)(base - lo);
+        while (m) {
+            queue[off++] = rel + (unsigned)(__ffs((int)m) - 1);
+            m &= m - 1u;
+        }
+        qn += total;
         __syncwarp();
-        if (qn >= 32u) {
-            const bool ok = spec_header_ok(a.in, a.in_len, safe_end, lo + queue[lane]);
+        // stage 2
+        unsigned head = 0;
+        while (qn - head >= 32u) {
+            const uint64_t p = lo + queue[head + lane];
+            const bool ok = spec_clcode_complete(a.in, safe_end, p) && spec_header_ok(a.in, a.in_len, safe_end, p);
             const unsigned mm = __ballot_sync(ZS_FULL_MASK, ok);
-            if (mm) {
-                found = lo + queue[__ffs((int)mm) - 1];       // the queue is in position order: the lowest lane is the first find
-            } else {
-                const uint32_t rest = lane + 32u < qn ? queue[lane + 32u] : 0u;
-                __syncwarp();
-                queue[lane] = rest;
-                qn -= 32u;
-                __syncwarp();
-            }
+            if (mm) { found = lo + queue[head + (unsigned)(__ffs((int)mm) - 1)]; break; }   // position order: the lowest lane is the first find
+            head += 32u;
+        }
+        if (found == ~0ull && head) {   // the remainder (< 32) moves to the front
+            const uint32_t rest = head + lane < qn ? queue[head + lane] : 0u;
+            __syncwarp();
+            queue[lane] = rest;
+            qn -= head;
+            __syncwarp();
         }
     }
     if (found == ~0ull && qn) {                               // what is left in the queue (< 32 positions)
-        const bool ok = lane < qn && spec_header_ok(a.in, a.in_len, safe_end, lo + queue[lane]);
+        bool ok = false;
+        if (lane < qn) {
+            const uint64_t p = lo + queue[lane];
+            ok = spec_clcode_complete(a.in, safe_end, p) && spec_header_ok(a.in, a.in_len, safe_end, p);
+        }
         const unsigned mm = __ballot_sync(ZS_FULL_MASK, ok);
         if (mm) found = lo + queue[__ffs((int)mm) - 1];
     }

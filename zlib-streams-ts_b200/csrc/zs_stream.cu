@@ -44,42 +44,12 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
-// Host byte buffer that grows without initialising what it grows by (std::vector::resize zero-fills: the
-// inflate shim asks for four times its input as output room on every attempt).
-struct RawBuf {
-    uint8_t* p = nullptr;
-    size_t n = 0, cap = 0;
-    RawBuf() = default;
-    RawBuf(const RawBuf&) = delete;
-    RawBuf& operator=(const RawBuf&) = delete;
-    ~RawBuf() { free(p); }
-    uint8_t* data() { return p; }
-    const uint8_t* data() const { return p; }
-    size_t size() const { return n; }
-    bool resize(size_t want) {
-        if (want > cap) {
-            size_t c = cap + (cap >> 1);
-            if (c < want) c = want;
-            uint8_t* q = (uint8_t*)realloc(p, c ? c : 1);
-            if (!q) return false;
-            p = q;
-            cap = c;
-        }
-        n = want;
-        return true;
-    }
-    void clear() { n = 0; }
-    void erase_front(size_t k) {
-        if (k >= n) { n = 0; return; }
-        memmove(p, p + k, n - k);
-        n -= k;
-    }
-};
-
-// Host byte buffer of the deflate shim: ordinary memory while it is small, page-locked once it holds a part's
-// worth of data -- a pageable cudaMemcpy is staged through the driver's bounce buffers at a few GB/s, which was
-// most of a CompressionStream's time (64 MiB of text: 47 ms, of which the kernels took 4.3).  Page-locking costs
-// about as much as one such copy, so the large buffers are handed from stream to stream through a small pool.
+// Host byte buffer of the shim (grows without initialising what it grows by): ordinary memory while it is small,
+// page-locked once it holds more than kPinAbove.  A pageable cudaMemcpy is staged through the driver's bounce
+// buffers at a few GB/s, and a fresh 64 MiB of ordinary memory costs 16 384 page faults on first touch: together
+// most of a stream's time (CompressionStream, 64 MiB of text: 47 ms, of which the kernels took 4.3).  Page-locking
+// costs about as much as one such copy, so the large buffers are handed from stream to stream through a small
+// pool: the first long stream of a process pays for them, the following ones do not.
 constexpr size_t kPinAbove = 1u << 20;
 struct PinPool {
     std::mutex mu;
@@ -88,13 +58,15 @@ struct PinPool {
     uint8_t* take(size_t want, size_t* cap) {
         {
             std::lock_guard<std::mutex> g(mu);
+            size_t best = free_list.size();
             for (size_t i = 0; i < free_list.size(); i++)
-                if (free_list[i].cap >= want) {
-                    Item it = free_list[i];
-                    free_list.erase(free_list.begin() + i);
-                    *cap = it.cap;
-                    return it.p;
-                }
+                if (free_list[i].cap >= want && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best < free_list.size()) {
+                Item it = free_list[best];
+                free_list.erase(free_list.begin() + best);
+                *cap = it.cap;
+                return it.p;
+            }
         }
         void* q = nullptr;
         if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -104,10 +76,13 @@ struct PinPool {
     void give(uint8_t* p, size_t cap) {
         {
             std::lock_guard<std::mutex> g(mu);
-            if (free_list.size() < 4) { free_list.push_back({p, cap}); return; }
+            size_t held = 0;
+            for (const Item& it : free_list) held += it.cap;
+            if (free_list.size() < kMaxItems && held + cap <= kMaxBytes) { free_list.push_back({p, cap}); return; }
         }
         cudaFreeHost(p);
     }
+    static constexpr size_t kMaxItems = 8, kMaxBytes = 768u << 20;   // what the pool keeps page-locked between streams
 };
 PinPool& pin_pool() { static PinPool* pool = new PinPool(); return *pool; }   // never destroyed: outlives the CUDA runtime's teardown
 
@@ -134,7 +109,7 @@ struct HostBuf {
         if (want <= cap) return true;
         size_t c = cap + (cap >> 1);
         if (c < want) c = want;
-        if (c >= kPinAbove) {
+        if (c > kPinAbove) {
             if (c < part_hint) c = part_hint;
             size_t got = 0;
             uint8_t* q = pin_pool().take(c, &got);
@@ -165,6 +140,16 @@ struct HostBuf {
         return true;
     }
     bool push_back(uint8_t b) { return append(&b, 1, 0); }
+    bool resize(size_t want) {   // grows without initialising what it grows by
+        if (!reserve(want, 0)) return false;
+        n = want;
+        return true;
+    }
+    void erase_front(size_t k) {
+        if (k >= n) { n = 0; return; }
+        memmove(p, p + k, n - k);
+        n -= k;
+    }
     bool grow(size_t k, size_t part_hint) {   // k more bytes, left uninitialised
         if (!reserve(n + k, part_hint)) return false;
         n += k;
@@ -179,7 +164,9 @@ constexpr size_t kPartOutHint = kPartThreshold + (kPartThreshold >> 6) + (64u <<
 // last byte of a short stream returns Z_STREAM_END and hands back what follows it through avail_in, exactly like the
 // reference, however fast the calls arrive.  Longer streams are paced (see zs_stream_inflate): the end may be found in
 // a later call, when input that arrived earlier can only be accounted for in total_in ("Streaming inflate").
-constexpr size_t kEveryCallBelow = 256u << 10;
+// (An attempt on a 32 KiB slice is ~5 ms of one warp decoding serially: with the limit at 256 KiB the first eight
+// calls of EVERY stream cost 43 ms -- a third of a 64 MiB DecompressionStream -- so the limit is two slices.)
+constexpr size_t kEveryCallBelow = 64u << 10;
 
 struct DeflateState {
     uint32_t magic = 0x44464c54;  // 'DFLT'
@@ -208,10 +195,10 @@ struct InflateState {
     // starts; the blocks before that point are final, their input is dropped and the next attempt
     // resumes there in raw mode with the last 64 KiB of output as its window.
     std::vector<uint8_t> in;        // input not yet consumed: from the byte that holds the next block header on
-    RawBuf out;                     // output of the latest attempt (from the resume point)
+    HostBuf out;                    // output of the latest attempt (from the resume point); page-locked once it is large
     bool out_on_device = false;     // `out` is byte for byte what the last attempt left on the device ...
     uint64_t out_gen = 0;           // ... as long as the context has not handed that scratch out again (h_out_gen)
-    std::vector<uint8_t> ready;     // decoded, not yet delivered
+    HostBuf ready;                  // decoded, not yet delivered
     std::vector<uint8_t> hist;      // window: the last <= 64 KiB of final output, or the preset dictionary
     std::vector<uint8_t> leftover;  // input after the end of the stream that could not be handed back
     size_t ready_pos = 0;           // delivered part of `ready`
@@ -693,7 +680,7 @@ static void fill_gz_header(InflateState* st) {
 // Everything of `out` below `upto` that has not been queued for delivery yet goes to `ready`.
 static void push_ready(InflateState* st, size_t upto) {
     if (upto > st->out_pushed) {
-        st->ready.insert(st->ready.end(), st->out.data() + st->out_pushed, st->out.data() + upto);
+        st->ready.append(st->out.data() + st->out_pushed, upto - st->out_pushed, 0);
         st->out_pushed = upto;
     }
 }
@@ -714,8 +701,13 @@ static int advance_to_mark(InflateState* st, uint64_t mark_bit, uint64_t mark_ou
         int rc = out_checksum(st, (size_t)mark_out, &st->run_check);
         if (rc != ZS_OK) return rc;
         st->run_len += mark_out;
-        st->hist.insert(st->hist.end(), st->out.data(), st->out.data() + (size_t)mark_out);
-        if (st->hist.size() > 65536) st->hist.erase(st->hist.begin(), st->hist.end() - 65536);
+        // the window: the last 64 KiB of final output (only those are copied: mark_out is the whole batch of a paced stream)
+        if (mark_out >= 65536) {
+            st->hist.assign(st->out.data() + (size_t)mark_out - 65536, st->out.data() + (size_t)mark_out);
+        } else {
+            st->hist.insert(st->hist.end(), st->out.data(), st->out.data() + (size_t)mark_out);
+            if (st->hist.size() > 65536) st->hist.erase(st->hist.begin(), st->hist.end() - 65536);
+        }
         st->out.erase_front((size_t)mark_out);
         st->out_on_device = false;
         st->out_pushed -= (size_t)mark_out;
@@ -826,6 +818,7 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
     InflateState* st = istate(strm);
     if (!st || !strm->next_out || (!strm->next_in && strm->avail_in != 0)) return ZS_STREAM_ERROR;
     const uint64_t in0 = strm->avail_in, out0 = strm->avail_out;
+    cudaSetDevice(st->ctx->device);   // (large buffers are page-locked: on this context's device, not on device 0)
     // Like inflate(), which stops consuming input when the output buffer is full: while more decoded bytes
     // are waiting than this call can deliver, no new input is taken (the reference's driver loop,
     // streams.ts:86 `while (strm.avail_in > 0)`, then keeps calling with fresh output buffers).
@@ -901,7 +894,10 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         strm->total_out += c;
         st->ready_pos += c;
         if (st->ready_pos == st->ready.size()) { st->ready.clear(); st->ready_pos = 0; }
-        else if (st->ready_pos > (8u << 20)) { st->ready.erase(st->ready.begin(), st->ready.begin() + st->ready_pos); st->ready_pos = 0; }
+        else if (st->ready_pos > (8u << 20) && st->ready_pos >= st->ready.size() / 2) {   // (amortised: the delivered half goes, the rest moves once)
+            st->ready.erase_front(st->ready_pos);
+            st->ready_pos = 0;
+        }
     }
     const bool all_out = st->ready_pos >= st->ready.size();
     if (st->failed && all_out) {
