@@ -13,6 +13,7 @@ enum {
     SCR_D_SYM = 3, SCR_D_NBLK = 4, SCR_D_DESC = 5, SCR_D_FREQ = 6, SCR_D_CODE = 7, SCR_D_HDR = 8, SCR_D_BITS = 9,
     SCR_D_PR = 10, SCR_D_OFF = 11, SCR_D_CHECKS = 12,
     SCR_I_MISC = 13,
+    // (SCR_H_IN, SCR_H_OUT and SCR_H_RES are named by number in zs_stream.cu: run_part)
     SCR_H_IN = 14, SCR_H_OUT = 15, SCR_H_OFF = 16, SCR_H_OFF2 = 17, SCR_H_RES = 18, SCR_H_DICT = 19, SCR_H_RNG = 20,
     SCR_D_OUTOFF = 21, SCR_D_OUTBITS = 22, SCR_H_CHECKS = 23, SCR_I_RESUME = 24,
     // 25..29: zs_inflate_par.cu

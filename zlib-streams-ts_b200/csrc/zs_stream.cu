@@ -28,22 +28,6 @@
 
 namespace {
 
-struct DevBuf {
-    uint8_t* p = nullptr;
-    size_t cap = 0;
-    bool ensure(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = (n + (n >> 2) + 4095) & ~(size_t)255;
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
-        cap = want;
-        return true;
-    }
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-
 // Host byte buffer of the shim (grows without initialising what it grows by): ordinary memory while it is small,
 // page-locked once it holds more than kPinAbove.  A pageable cudaMemcpy is staged through the driver's bounce
 // buffers at a few GB/s, and a fresh 64 MiB of ordinary memory costs 16 384 page faults on first touch: together
@@ -90,6 +74,7 @@ struct HostBuf {
     uint8_t* p = nullptr;
     size_t n = 0, cap = 0;
     bool pinned = false;
+    bool may_pin = true;            // false: stays in ordinary memory whatever its size
     HostBuf() = default;
     HostBuf(const HostBuf&) = delete;
     HostBuf& operator=(const HostBuf&) = delete;
@@ -109,7 +94,7 @@ struct HostBuf {
         if (want <= cap) return true;
         size_t c = cap + (cap >> 1);
         if (c < want) c = want;
-        if (c > kPinAbove) {
+        if (may_pin && c > kPinAbove) {
             if (c < part_hint) c = part_hint;
             size_t got = 0;
             uint8_t* q = pin_pool().take(c, &got);
@@ -157,7 +142,14 @@ struct HostBuf {
     }
 };
 
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
+enum { kScrHostIn = 14, kScrHostOut = 15, kScrHostRes = 18 };   // SCR_H_IN / SCR_H_OUT / SCR_H_RES of zs_api.cu
 constexpr size_t kPartThreshold = 16u << 20;
 constexpr size_t kPartOutHint = kPartThreshold + (kPartThreshold >> 6) + (64u << 10);   // a part's output: the stored-block bound and change
 // inflate: while a stream has brought less input than this it is decoded on EVERY call, so the call that brings the
@@ -184,7 +176,9 @@ struct DeflateState {
     int gz_text = 0, gz_os = 0, gz_hcrc = 0;
     uint32_t gz_time = 0;
     std::vector<uint8_t> gz_extra, gz_name, gz_comment;
-    DevBuf d_in, d_out, d_res;
+    // ZS_STREAM_PROF=1: where a stream's time went (seconds), printed by deflateEnd
+    double t_append = 0, t_part = 0, t_drain = 0, t_alloc = 0, t_d2h = 0, t_created = 0;
+    unsigned n_parts = 0, n_calls = 0;
 };
 
 struct InflateState {
@@ -220,15 +214,18 @@ struct InflateState {
     const char* fail_msg = "";
     uint32_t check = 0;
     zs_gz_header* gzhead = nullptr;   // inflateGetHeader
+    // The inflate buffers stay in ordinary memory: their sizes follow the stream (four times the buffered input, what
+    // is waiting for delivery), so page-locked ones would rarely be reusable from stream to stream, and page-locking
+    // 100 MiB anew costs more than the pageable copy it replaces (measured through the stream API: 0.39-0.91 GB/s,
+    // erratic, and the pool's churn slowed the deflate streams between them from 3 to 0.5-1.2 GB/s).
+    InflateState() { out.may_pin = false; ready.may_pin = false; t_created = now_s(); }
+    // ZS_STREAM_PROF=1: where a stream's time went (seconds), printed by inflateEnd
+    double t_created = 0, t_insert = 0, t_attempts = 0, t_engine = 0, t_deliver = 0;
+    unsigned n_attempts = 0, n_calls = 0;
 };
 
 int rank_of(int f) { return f * 2 - (f > 4 ? 9 : 0); }  // RANK, deflate.ts:105
 
-double now_s() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
-}
 // inflate: a long stream whose calls arrive faster than attempts complete waits kPaceFactor x the duration of its
 // last attempt before the next one, or until this much undecoded input is buffered
 constexpr double kPaceFactor = 2.0;
@@ -298,6 +295,8 @@ void put_gzip_header(DeflateState* st) {
 int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     zs_ctx* ctx = st->ctx;
     cudaSetDevice(ctx->device);
+    const double t_part0 = now_s();
+    struct PartTimer { DeflateState* s; double t0; ~PartTimer() { s->t_part += now_s() - t0; s->n_parts++; } } part_timer{st, t_part0};
     const size_t hist_len = st->hist.size(), n = st->in.size();
     // zlib header with a preset dictionary carries FDICT + DICTID: host framing (deflate.ts:754-777)
     if (!st->header_done && st->wrap == ZS_WRAP_ZLIB && st->have_dict) {
@@ -322,24 +321,35 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     const uint32_t chunk = n >= (148u * 4u * 262144u) ? 262144u : 65536u;
     const uint32_t n_chunks = n ? (uint32_t)((n + chunk - 1) / chunk) : 1u;
     const uint64_t cap = zs_deflate_batch_bound(n, n_chunks, chunk, st->wrap, ZS_MODE_STITCHED);
-    if (!st->d_in.ensure(hist_len + n + 64) || !st->d_out.ensure(cap + 64) || !st->d_res.ensure(256)) return ZS_MEM_ERROR;
+    // Device buffers of a part: the context's grow-only scratch (the slots of the host-buffer batch calls, which are
+    // free while a part runs: zs_deflate_batch_dev uses the SCR_D_* slots only).  They used to belong to the stream --
+    // cudaMalloc at its first part, cudaFree at deflateEnd -- and the driver took up to 19 ms for the one and 17 ms for
+    // the other: as much as the whole 64 MiB stream (ZS_STREAM_PROF).
+    const double t_alloc0 = now_s();
+    uint8_t* d_in_buf = (uint8_t*)zs_scratch_get(ctx, kScrHostIn, hist_len + n + 64 + 16);
+    uint8_t* d_out_buf = (uint8_t*)zs_scratch_get(ctx, kScrHostOut, cap + 64);
+    uint8_t* d_res_buf = (uint8_t*)zs_scratch_get(ctx, kScrHostRes, 256);
+    st->t_alloc += now_s() - t_alloc0;
+    if (!d_in_buf || !d_out_buf || !d_res_buf) return ZS_MEM_ERROR;
     // history and input are contiguous on the device; keep the input 16-byte aligned
     const size_t pad = (16 - (hist_len & 15)) & 15;
-    uint8_t* d_hist = st->d_in.p + pad;
+    uint8_t* d_hist = d_in_buf + pad;
     if (hist_len) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_hist, st->hist.data(), hist_len, cudaMemcpyHostToDevice, ctx->stream));
     if (n) ZS_CUDA_TRY(ctx, cudaMemcpyAsync(d_hist + hist_len, st->in.data(), n, cudaMemcpyHostToDevice, ctx->stream));
-    zs_deflate_result* d_result = (zs_deflate_result*)st->d_res.p;
+    zs_deflate_result* d_result = (zs_deflate_result*)d_res_buf;
     int rc = zs_deflate_batch_dev(ctx, d_hist + hist_len, n, nullptr, n_chunks, chunk, chunk, (uint32_t)hist_len, st->level,
-                                  st->wrap, ZS_MODE_STITCHED, flags, st->d_out.p, cap, nullptr, nullptr, nullptr, d_result);
+                                  st->wrap, ZS_MODE_STITCHED, flags, d_out_buf, cap, nullptr, nullptr, nullptr, d_result);
     if (rc != ZS_OK) return rc;
     zs_deflate_result res;
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(&res, d_result, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (res.total_out_bytes > cap) return ZS_BUF_ERROR;
     const size_t old = st->out.size();
+    const double t_d2h0 = now_s();
     if (!st->out.grow(res.total_out_bytes, kPartOutHint)) return ZS_MEM_ERROR;
-    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(st->out.data() + old, st->d_out.p, res.total_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZS_CUDA_TRY(ctx, cudaMemcpyAsync(st->out.data() + old, d_out_buf, res.total_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    st->t_d2h += now_s() - t_d2h0;
     // running check over the uncompressed data (read_buf, deflate.ts:155-159)
     if (st->wrap == ZS_WRAP_ZLIB) st->check = st->total_in_len || st->any_part ? zs_host_adler32_combine(st->check, res.check, n) : res.check;
     else if (st->wrap == ZS_WRAP_GZIP) st->check = st->total_in_len || st->any_part ? zs_host_crc32_combine(st->check, res.check, n) : res.check;
@@ -411,6 +421,7 @@ int zs_stream_deflate_init(zs_ctx* ctx, zs_stream* strm, int level, int method, 
     st->strategy = strategy;
     st->wrap = wrap;
     st->status = ST_INIT;
+    st->t_created = now_s();
     strm->state = st;
     strm->total_in = strm->total_out = 0;
     strm->adler = wrap == 2 ? 0u : 1u;
@@ -445,6 +456,7 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
     }
     if (strm->avail_out == 0) { strm->msg = "buffer error"; return ZS_BUF_ERROR; }
     cudaSetDevice(st->ctx->device);   // (the buffers below may be page-locked: on this context's device, not on device 0)
+    st->n_calls++;
     const int old_flush = st->last_flush;
     st->last_flush = flush;
     if (st->out_pos < st->out.size()) {
@@ -464,7 +476,9 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
     while (strm->avail_in) {
         const size_t room = kPartThreshold > st->in.size() ? kPartThreshold - st->in.size() : 0;
         const size_t take = strm->avail_in < room ? (size_t)strm->avail_in : room;
+        const double t_app0 = now_s();
         if (!st->in.append(strm->next_in, take, kPartThreshold)) { strm->msg = "insufficient memory"; return ZS_MEM_ERROR; }
+        st->t_append += now_s() - t_app0;
         strm->next_in += take;
         strm->total_in += take;
         strm->avail_in -= take;
@@ -499,7 +513,11 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
             return rc;
         }
     }
-    drain(strm, st->out, st->out_pos);
+    {
+        const double t0 = now_s();
+        drain(strm, st->out, st->out_pos);
+        st->t_drain += now_s() - t0;
+    }
     if (flush == ZS_FINISH && st->status == ST_FINISH && st->out_pos >= st->out.size()) return ZS_STREAM_END;
     return ZS_OK;
 }
@@ -577,7 +595,17 @@ int zs_stream_deflate_end(zs_stream* strm) {
     DeflateState* st = dstate(strm);
     if (!st) return ZS_STREAM_ERROR;
     const int status = st->status;
-    delete st;
+    if (getenv("ZS_STREAM_PROF")) {
+        const double t0 = now_s();
+        const unsigned long long tin = strm->total_in;
+        const double life = t0 - st->t_created, app = st->t_append, part = st->t_part, alloc = st->t_alloc, d2h = st->t_d2h, dr = st->t_drain;
+        const unsigned np = st->n_parts, nc = st->n_calls;
+        delete st;
+        fprintf(stderr, "[stream prof] deflate: %llu bytes in %.1f ms: %u calls, append %.1f ms, %u parts %.1f ms (device alloc %.1f, copy out %.1f), drain %.1f, end %.1f\n",
+                tin, 1e3 * life, nc, 1e3 * app, np, 1e3 * part, 1e3 * alloc, 1e3 * d2h, 1e3 * dr, 1e3 * (now_s() - t0));
+    } else {
+        delete st;
+    }
     strm->state = nullptr;
     return status == ST_BUSY ? ZS_DATA_ERROR : ZS_OK;  // deflate.ts:1012
 }
@@ -763,10 +791,12 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
         int32_t status = 0, detail = 0;
         ctx->inflate_resume = true;
         ctx->inflate_start_bit = st->body ? st->start_bit : ~0ull;
+        const double t_eng0 = now_s();
         int rc = zs_inflate_batch(ctx, st->in.data(), in_off, 1, st->body ? raw_wb : st->window_bits, st->out.data(), out_off,
                                   &out_len, &in_used, &check, &status, st->hist.empty() ? nullptr : st->hist.data(),
                                   st->hist.empty() ? nullptr : rng, st->hist.size());
         ctx->inflate_resume = false;
+        st->t_engine += now_s() - t_eng0;
         if (rc != ZS_OK) { strm->msg = zs_last_error(ctx); return rc; }
         if (status == ZS_BUF_ERROR && out_len == st->out_cap_hint) {  // output full: grow and decode again
             st->out_cap_hint *= 4;
@@ -831,7 +861,9 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
             st->next_attempt = 0;
         }
         if (strm->avail_in) {
+            const double t_ins0 = now_s();
             st->in.insert(st->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+            st->t_insert += now_s() - t_ins0;
             strm->next_in += strm->avail_in;
             strm->total_in += strm->avail_in;
             strm->avail_in = 0;
@@ -865,6 +897,8 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
             st->fresh_input = false;
             st->attempt_end = now_s();
             st->attempt_cost = st->attempt_end - t_begin;
+            st->t_attempts += st->attempt_cost;
+            st->n_attempts++;
             st->next_attempt = st->in.size() + ((size_t)strm->total_in < kEveryCallBelow ? 1 : kAttemptAtLeastEvery);
             if (st->need_dict) {
                 strm->adler = st->in.size() >= 6 ? ((uint32_t)st->in[2] << 24 | (uint32_t)st->in[3] << 16 | (uint32_t)st->in[4] << 8 | st->in[5]) : 0u;
@@ -885,6 +919,9 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
         }
     }
     // deliver what has been decoded
+    st->n_calls++;
+    const double t_del0 = now_s();
+    struct DeliverTimer { InflateState* s; double t0; ~DeliverTimer() { s->t_deliver += now_s() - t0; } } deliver_timer{st, t_del0};
     if (st->ready_pos < st->ready.size()) {
         size_t c = st->ready.size() - st->ready_pos;
         if (c > strm->avail_out) c = (size_t)strm->avail_out;
@@ -976,6 +1013,10 @@ int zs_stream_inflate_reset2(zs_stream* strm, int window_bits) {
 int zs_stream_inflate_end(zs_stream* strm) {
     InflateState* st = istate(strm);
     if (!st) return ZS_STREAM_ERROR;
+    if (getenv("ZS_STREAM_PROF"))
+        fprintf(stderr, "[stream prof] inflate: %llu bytes out in %.1f ms: %u calls, buffering input %.1f ms, %u attempts %.1f ms (engine incl. copies %.1f), "
+                "delivery %.1f ms\n", (unsigned long long)strm->total_out, 1e3 * (now_s() - st->t_created), st->n_calls, 1e3 * st->t_insert,
+                st->n_attempts, 1e3 * st->t_attempts, 1e3 * st->t_engine, 1e3 * st->t_deliver);
     delete st;
     strm->state = nullptr;
     return ZS_OK;
