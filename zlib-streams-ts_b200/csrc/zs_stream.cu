@@ -70,6 +70,42 @@ struct PinPool {
 };
 PinPool& pin_pool() { static PinPool* pool = new PinPool(); return *pool; }   // never destroyed: outlives the CUDA runtime's teardown
 
+// The same for large buffers in ORDINARY memory (the inflate side): what is expensive about them is the first touch --
+// a device-to-host copy of 64 MiB into freshly mapped pages takes 41 ms on the B200 box, 3.7 ms into pages that have
+// been touched (profiles/pincost_r2.txt) -- so a stream's large buffers go to the next stream instead of back to the
+// allocator.  take() hands out the best fit, or the largest buffer there is (the caller grows it with realloc, which
+// keeps the touched pages).
+struct PagePool {
+    std::mutex mu;
+    struct Item { uint8_t* p; size_t cap; };
+    std::vector<Item> free_list;
+    static constexpr size_t kMaxItems = 4, kMaxBytes = 512u << 20;
+    uint8_t* take(size_t want, size_t* cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.empty()) return nullptr;
+        size_t best = free_list.size(), largest = 0;
+        for (size_t i = 0; i < free_list.size(); i++) {
+            if (free_list[i].cap >= want && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+            if (free_list[i].cap > free_list[largest].cap) largest = i;
+        }
+        if (best == free_list.size()) best = largest;
+        Item it = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        *cap = it.cap;
+        return it.p;
+    }
+    void give(uint8_t* p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t held = 0;
+            for (const Item& it : free_list) held += it.cap;
+            if (free_list.size() < kMaxItems && held + cap <= kMaxBytes) { free_list.push_back({p, cap}); return; }
+        }
+        free(p);
+    }
+};
+PagePool& page_pool() { static PagePool* pool = new PagePool(); return *pool; }
+
 struct HostBuf {
     uint8_t* p = nullptr;
     size_t n = 0, cap = 0;
@@ -80,7 +116,11 @@ struct HostBuf {
     HostBuf& operator=(const HostBuf&) = delete;
     ~HostBuf() { release(); }
     void release() {
-        if (p) { if (pinned) pin_pool().give(p, cap); else free(p); }
+        if (p) {
+            if (pinned) pin_pool().give(p, cap);
+            else if (cap > kPinAbove) page_pool().give(p, cap);
+            else free(p);
+        }
         p = nullptr; n = cap = 0; pinned = false;
     }
     uint8_t* data() { return p; }
@@ -112,6 +152,16 @@ struct HostBuf {
             pin_pool().give(p, cap);
             p = q; cap = c; pinned = false;
             return true;
+        }
+        if (cap <= kPinAbove && c > kPinAbove) {   // becoming large: a buffer whose pages have been touched, if there is one
+            size_t got = 0;
+            uint8_t* q = page_pool().take(c, &got);
+            if (q) {
+                if (n) memcpy(q, p, n);
+                free(p);
+                p = q; cap = got;
+                if (cap >= want) return true;
+            }
         }
         uint8_t* q = (uint8_t*)realloc(p, c ? c : 1);
         if (!q) return false;
