@@ -238,7 +238,7 @@ struct InflateState {
     // Decoding is incremental at block granularity: every attempt reports where the last block it began
     // starts; the blocks before that point are final, their input is dropped and the next attempt
     // resumes there in raw mode with the last 64 KiB of output as its window.
-    std::vector<uint8_t> in;        // input not yet consumed: from the byte that holds the next block header on
+    HostBuf in;                     // input not yet consumed: from the byte that holds the next block header on
     HostBuf out;                    // output of the latest attempt (from the resume point); page-locked once it is large
     bool out_on_device = false;     // `out` is byte for byte what the last attempt left on the device ...
     uint64_t out_gen = 0;           // ... as long as the context has not handed that scratch out again (h_out_gen)
@@ -268,7 +268,7 @@ struct InflateState {
     // is waiting for delivery), so page-locked ones would rarely be reusable from stream to stream, and page-locking
     // 100 MiB anew costs more than the pageable copy it replaces (measured through the stream API: 0.39-0.91 GB/s,
     // erratic, and the pool's churn slowed the deflate streams between them from 3 to 0.5-1.2 GB/s).
-    InflateState() { out.may_pin = false; ready.may_pin = false; t_created = now_s(); }
+    InflateState() { in.may_pin = false; out.may_pin = false; ready.may_pin = false; t_created = now_s(); }
     // ZS_STREAM_PROF=1: where a stream's time went (seconds), printed by inflateEnd
     double t_created = 0, t_insert = 0, t_attempts = 0, t_engine = 0, t_deliver = 0;
     unsigned n_attempts = 0, n_calls = 0;
@@ -716,7 +716,7 @@ int zs_stream_inflate_set_dictionary(zs_stream* strm, const uint8_t* dict, uint3
 static void fill_gz_header(InflateState* st) {
     zs_gz_header* g = st->gzhead;
     if (!g || g->done != 0 || st->body) return;   // `in` starts at the stream start only until the first resume
-    const std::vector<uint8_t>& b = st->in;
+    const HostBuf& b = st->in;
     if (b.size() < 2) return;
     if (!(b[0] == 0x1f && b[1] == 0x8b)) { g->done = -1; return; }   // a zlib stream (windowBits 32+), inflate.ts:404
     if (b.size() < 10) return;
@@ -791,7 +791,7 @@ static int advance_to_mark(InflateState* st, uint64_t mark_bit, uint64_t mark_ou
         st->out_pushed -= (size_t)mark_out;
     }
     const size_t bytes = (size_t)(mark_bit >> 3);
-    st->in.erase(st->in.begin(), st->in.begin() + bytes);
+    st->in.erase_front(bytes);
     st->start_bit = mark_bit & 7u;
     st->body = true;
     return ZS_OK;
@@ -820,7 +820,7 @@ static int finish_stream(InflateState* st) {
     st->check = total;
     st->done = true;
     const size_t used = st->trailer_pos + T;
-    if (st->in.size() > used) st->leftover.assign(st->in.begin() + used, st->in.end());
+    if (st->in.size() > used) st->leftover.assign(st->in.data() + used, st->in.data() + st->in.size());
     st->in.clear();
     return ZS_OK;
 }
@@ -862,7 +862,7 @@ static int inflate_attempt(zs_stream* strm, InflateState* st) {
                 push_ready(st, out_len);
                 st->check = check;
                 st->done = true;
-                if (st->in.size() > (size_t)in_used) st->leftover.assign(st->in.begin() + (size_t)in_used, st->in.end());
+                if (st->in.size() > (size_t)in_used) st->leftover.assign(st->in.data() + (size_t)in_used, st->in.data() + st->in.size());
                 st->in.clear();
                 return ZS_OK;
             }
@@ -906,13 +906,14 @@ int zs_stream_inflate(zs_stream* strm, int flush) {
     if (!st->done && !st->failed && !backlog) {
         // input left over from the previous member is consumed first (inflateReset flow)
         if (!st->leftover.empty() && st->in.empty()) {
-            st->in.swap(st->leftover);
+            st->in.clear();
+            st->in.append(st->leftover.data(), st->leftover.size(), 0);
             st->leftover.clear();
             st->next_attempt = 0;
         }
         if (strm->avail_in) {
             const double t_ins0 = now_s();
-            st->in.insert(st->in.end(), strm->next_in, strm->next_in + strm->avail_in);
+            if (!st->in.append(strm->next_in, (size_t)strm->avail_in, 0)) { strm->msg = "insufficient memory"; return ZS_MEM_ERROR; }
             st->t_insert += now_s() - t_ins0;
             strm->next_in += strm->avail_in;
             strm->total_in += strm->avail_in;
