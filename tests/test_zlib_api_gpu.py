@@ -401,6 +401,33 @@ def test_stream_loop_in_c(gpu_ctx):
             if wbits == 15:
                 assert zs.adler == zlib.adler32(data.tobytes())
             assert lib.zs_stream_inflate_end(C.byref(zs)) == 0
+    # parts that run in the background: 40 MiB is two full parts (16 MiB each, started when their input is complete and
+    # compressed while the next one is buffered) and a final one; fed in 32 KiB slices, in one giant call (the call
+    # compresses part by part and comes back for output room: Z_OK with avail_in > 0), and through a 1000-byte output buffer
+    long_data = np.frombuffer(make_text(40 << 20, 321), dtype=np.uint8)
+    big2 = np.empty(long_data.size + (1 << 20), dtype=np.uint8)
+    outs = []
+    for in_slice, out_slice, level, wbits in ((32768, 65536, 1, 31), (48 << 20, 65536, 6, 15), (1 << 20, 1000, 1, -15)):
+        zs = capi.ZStream()
+        assert lib.zs_stream_deflate_init(gpu_ctx.handle, C.byref(zs), level, 8, wbits, 8, 0) == 0
+        rc, made, calls = streampump.pump(lib.zs_stream_deflate, zs, long_data, big2, in_slice, out_slice)
+        assert rc == 1 and zs.total_in == long_data.size and zs.total_out == made, (rc, in_slice, out_slice)
+        if wbits == 31:
+            assert zs.adler == zlib.crc32(long_data.tobytes())
+        if wbits == 15:
+            assert zs.adler == zlib.adler32(long_data.tobytes())
+        assert lib.zs_stream_deflate_end(C.byref(zs)) == 0
+        d = zlib.decompressobj(wbits)
+        assert d.decompress(big2[:made].tobytes()) + d.flush() == long_data.tobytes() and d.eof and d.unused_data == b""
+        outs.append(made)
+    # a stream abandoned with a part in flight: deflateEnd waits for it (Z_DATA_ERROR: mid-stream, deflate.ts:1012)
+    zs = capi.ZStream()
+    assert lib.zs_stream_deflate_init(gpu_ctx.handle, C.byref(zs), 1, 8, 15, 8, 0) == 0
+    obuf = np.empty(65536, dtype=np.uint8)
+    zs.next_in, zs.avail_in = long_data.ctypes.data, 17 << 20
+    zs.next_out, zs.avail_out = obuf.ctypes.data, obuf.size
+    assert lib.zs_stream_deflate(C.byref(zs), 0) == 0 and zs.avail_in == 0
+    assert lib.zs_stream_deflate_end(C.byref(zs)) == capi.Z_DATA_ERROR
     # a truncated stream: Z_BUF_ERROR under Z_FINISH, everything decodable delivered
     co = zlib.compressobj(6)
     whole = co.compress(data.tobytes()) + co.flush()

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "zs_common.cuh"
@@ -185,6 +186,9 @@ struct HostBuf {
         memmove(p, p + k, n - k);
         n -= k;
     }
+    void swap(HostBuf& o) {
+        std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); std::swap(pinned, o.pinned); std::swap(may_pin, o.may_pin);
+    }
     bool grow(size_t k, size_t part_hint) {   // k more bytes, left uninitialised
         if (!reserve(n + k, part_hint)) return false;
         n += k;
@@ -201,7 +205,7 @@ double now_s() {
 enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
 enum { kScrHostIn = 14, kScrHostOut = 15, kScrHostRes = 18 };   // SCR_H_IN / SCR_H_OUT / SCR_H_RES of zs_api.cu
 constexpr size_t kPartThreshold = 16u << 20;
-constexpr size_t kPartOutHint = kPartThreshold + (kPartThreshold >> 6) + (64u << 10);   // a part's output: the stored-block bound and change
+constexpr size_t kPartOutHint = 2 * kPartThreshold;   // a part's output (the stored-block bound and change) behind what is still waiting
 // inflate: while a stream has brought less input than this it is decoded on EVERY call, so the call that brings the
 // last byte of a short stream returns Z_STREAM_END and hands back what follows it through avail_in, exactly like the
 // reference, however fast the calls arrive.  Longer streams are paced (see zs_stream_inflate): the end may be found in
@@ -218,6 +222,14 @@ struct DeflateState {
     HostBuf in;                     // buffered, not yet compressed: at most one part (kPartThreshold)
     HostBuf out;                    // compressed, not yet delivered
     size_t out_pos = 0;
+    // A part that was started because a whole part of input had piled up runs in the BACKGROUND: its copies and
+    // kernels are queued on the context's stream and the call returns, so the caller buffers the next part while the
+    // GPU compresses this one (the zlib contract lets deflate(Z_NO_FLUSH) hold output back).  Its input stays in
+    // `in_flight`, its output lands in `out` behind the bytes that are waiting there, followed by the result record;
+    // harvest() -- before the next part, on any flush, on a call without input, at deflateEnd -- waits for it.
+    HostBuf in_flight;
+    bool pending = false, p_first = false;
+    size_t p_old = 0, p_cap = 0, p_cap_al = 0, p_n = 0;
     bool header_done = false, any_part = false, trailer_done = false, have_dict = false;
     uint32_t check = 0, dict_id = 0;
     uint64_t total_in_len = 0;
@@ -341,10 +353,34 @@ void put_gzip_header(DeflateState* st) {
     st->out.append(h.data(), h.size(), 0);
 }
 
-// Compress everything buffered as one part.  `finish` makes it the last part of the stream.
-int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
+// Wait for the part in flight (if any) and take its output and checksum.
+int harvest(zs_stream* strm, DeflateState* st) {
+    if (!st->pending) return ZS_OK;
+    zs_ctx* ctx = st->ctx;
+    st->pending = false;
+    const double t0 = now_s();
+    ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    st->t_part += now_s() - t0;
+    zs_deflate_result res;
+    memcpy(&res, st->out.data() + st->p_old + st->p_cap_al, sizeof(res));
+    if (res.total_out_bytes > st->p_cap) return ZS_BUF_ERROR;
+    st->out.n = st->p_old + (size_t)res.total_out_bytes;
+    if (st->wrap == ZS_WRAP_ZLIB) st->check = st->p_first ? res.check : zs_host_adler32_combine(st->check, res.check, st->p_n);
+    else if (st->wrap == ZS_WRAP_GZIP) st->check = st->p_first ? res.check : zs_host_crc32_combine(st->check, res.check, st->p_n);
+    if (st->wrap != ZS_WRAP_RAW) strm->adler = st->check;
+    st->in_flight.clear();
+    return ZS_OK;
+}
+
+// Compress everything buffered as one part.  `finish` makes it the last part of the stream; `background`: queue it
+// and return (see DeflateState::pending).
+int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush, bool background = false) {
     zs_ctx* ctx = st->ctx;
     cudaSetDevice(ctx->device);
+    {
+        const int rc = harvest(strm, st);
+        if (rc != ZS_OK) return rc;
+    }
     const double t_part0 = now_s();
     struct PartTimer { DeflateState* s; double t0; ~PartTimer() { s->t_part += now_s() - t0; s->n_parts++; } } part_timer{st, t_part0};
     const size_t hist_len = st->hist.size(), n = st->in.size();
@@ -390,6 +426,36 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     int rc = zs_deflate_batch_dev(ctx, d_hist + hist_len, n, nullptr, n_chunks, chunk, chunk, (uint32_t)hist_len, st->level,
                                   st->wrap, ZS_MODE_STITCHED, flags, d_out_buf, cap, nullptr, nullptr, nullptr, d_result);
     if (rc != ZS_OK) return rc;
+    if (background && !finish && !full_flush) {
+        // what is still waiting in `out` moves to its front, the part's output (as much as it can be: its size is
+        // known only when the kernels are done) and the result record are copied behind it
+        if (st->out_pos == st->out.size()) st->out.clear();
+        else if (st->out_pos) st->out.erase_front(st->out_pos);
+        st->out_pos = 0;
+        const size_t old = st->out.size(), cap_al = ((size_t)cap + 15) & ~(size_t)15;
+        if (!st->out.reserve(old + cap_al + 64, kPartOutHint)) return ZS_MEM_ERROR;
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(st->out.data() + old + cap_al, d_result, sizeof(zs_deflate_result), cudaMemcpyDeviceToHost, ctx->stream));
+        ZS_CUDA_TRY(ctx, cudaMemcpyAsync(st->out.data() + old, d_out_buf, cap, cudaMemcpyDeviceToHost, ctx->stream));
+        st->pending = true;
+        st->p_old = old; st->p_cap = (size_t)cap; st->p_cap_al = cap_al; st->p_n = n;
+        st->p_first = !(st->total_in_len || st->any_part);
+        st->total_in_len += n;
+        st->header_done = true;
+        st->any_part = true;
+        {   // history for the next part: the last 32 KiB of (history + input)
+            std::vector<uint8_t> h;
+            const size_t total = hist_len + n, keep = total < 32768 ? total : 32768;
+            h.resize(keep);
+            for (size_t i = 0; i < keep; i++) {
+                size_t idx = total - keep + i;
+                h[i] = idx < hist_len ? st->hist[idx] : st->in[idx - hist_len];
+            }
+            st->hist.swap(h);
+        }
+        st->in.swap(st->in_flight);   // the copy engine is still reading it
+        st->in.clear();
+        return ZS_OK;
+    }
     zs_deflate_result res;
     ZS_CUDA_TRY(ctx, cudaMemcpyAsync(&res, d_result, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
     ZS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -430,7 +496,7 @@ int run_part(zs_stream* strm, DeflateState* st, bool finish, bool full_flush) {
     return ZS_OK;
 }
 
-void drain(zs_stream* strm, HostBuf& out, size_t& pos) {
+void drain(zs_stream* strm, HostBuf& out, size_t& pos, bool pending = false) {
     size_t avail = out.size() - pos;
     size_t c = avail < strm->avail_out ? avail : (size_t)strm->avail_out;
     if (c) {
@@ -440,7 +506,7 @@ void drain(zs_stream* strm, HostBuf& out, size_t& pos) {
         strm->total_out += c;
         pos += c;
     }
-    if (pos == out.size()) { out.clear(); pos = 0; }
+    if (pos == out.size() && !pending) { out.clear(); pos = 0; }   // (a part in flight is writing behind out.size())
 }
 
 }  // namespace
@@ -507,10 +573,15 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
     if (strm->avail_out == 0) { strm->msg = "buffer error"; return ZS_BUF_ERROR; }
     cudaSetDevice(st->ctx->device);   // (the buffers below may be page-locked: on this context's device, not on device 0)
     st->n_calls++;
+    // a part in flight is waited for when the caller asks for output (a call without input, any flush request)
+    if (st->pending && (strm->avail_in == 0 || flush != ZS_NO_FLUSH)) {
+        const int rc = harvest(strm, st);
+        if (rc != ZS_OK) { strm->msg = zs_last_error(st->ctx); return rc; }
+    }
     const int old_flush = st->last_flush;
     st->last_flush = flush;
     if (st->out_pos < st->out.size()) {
-        drain(strm, st->out, st->out_pos);
+        drain(strm, st->out, st->out_pos, st->pending);
         if (strm->avail_out == 0) { st->last_flush = -1; return ZS_OK; }
     } else if (strm->avail_in == 0 && rank_of(flush) <= rank_of(old_flush) && flush != ZS_FINISH) {
         strm->msg = "buffer error";
@@ -533,12 +604,12 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
         strm->total_in += take;
         strm->avail_in -= take;
         if (strm->avail_in == 0 || st->status != ST_BUSY) break;
-        const int rc = run_part(strm, st, false, false);
+        const int rc = run_part(strm, st, false, false, true);
         if (rc != ZS_OK) {
             strm->msg = zs_last_error(st->ctx);
             return rc;
         }
-        drain(strm, st->out, st->out_pos);
+        drain(strm, st->out, st->out_pos, st->pending);
         if (st->out_pos < st->out.size()) { st->last_flush = -1; return ZS_OK; }
     }
     if (st->status == ST_BUSY) {
@@ -556,7 +627,7 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
                 if (flush == ZS_FULL_FLUSH) st->hist.clear();
             }
         } else if (st->in.size() >= kPartThreshold) {
-            rc = run_part(strm, st, false, false);
+            rc = run_part(strm, st, false, false, true);
         }
         if (rc != ZS_OK) {
             strm->msg = zs_last_error(st->ctx);
@@ -565,7 +636,7 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
     }
     {
         const double t0 = now_s();
-        drain(strm, st->out, st->out_pos);
+        drain(strm, st->out, st->out_pos, st->pending);
         st->t_drain += now_s() - t0;
     }
     if (flush == ZS_FINISH && st->status == ST_FINISH && st->out_pos >= st->out.size()) return ZS_STREAM_END;
@@ -576,7 +647,8 @@ int zs_stream_deflate(zs_stream* strm, int flush) {
 int zs_stream_deflate_reset(zs_stream* strm) {
     DeflateState* st = dstate(strm);
     if (!st) return ZS_STREAM_ERROR;
-    st->hist.clear(); st->in.clear(); st->out.clear();
+    if (st->pending) { cudaSetDevice(st->ctx->device); cudaStreamSynchronize(st->ctx->stream); st->pending = false; }   // (nobody writes the buffers any more)
+    st->hist.clear(); st->in.clear(); st->in_flight.clear(); st->out.clear();
     st->out_pos = 0;
     st->header_done = st->any_part = st->trailer_done = st->have_dict = false;
     st->check = st->dict_id = 0;
@@ -645,6 +717,7 @@ int zs_stream_deflate_end(zs_stream* strm) {
     DeflateState* st = dstate(strm);
     if (!st) return ZS_STREAM_ERROR;
     const int status = st->status;
+    if (st->pending) { cudaSetDevice(st->ctx->device); cudaStreamSynchronize(st->ctx->stream); st->pending = false; }   // before the buffers go back to the pool
     if (getenv("ZS_STREAM_PROF")) {
         const double t0 = now_s();
         const unsigned long long tin = strm->total_in;
