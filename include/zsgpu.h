@@ -229,7 +229,13 @@ ZS_API int zs_inflate_last_details(zs_ctx* ctx, int32_t* detail, uint32_t n);
  * Mirrors createDeflateStream/deflateInit2_/deflate/deflateEnd (deflate.ts:80,253,716,991),
  * deflateSetDictionary (:367) and createInflateStream/inflateInit2_/inflate/inflateEnd/
  * inflateSetDictionary/inflateReset (inflate.ts:68,174,332,1187,1220,124).  The counters are the
- * Stream fields of src/mod/common/types.ts:1-15. */
+ * Stream fields of src/mod/common/types.ts:1-15.
+ * Scheduling: deflate buffers one part (16 MiB) of input; a part that is complete under
+ * Z_NO_FLUSH is compressed in the background while the caller feeds the next one, and its output is handed out by
+ * later calls, by any flush request or by a call without input.  inflate decodes on every call while a stream has
+ * brought less than 64 KiB, on any flush request and on a call without new input; beyond that its decode attempts
+ * are paced by what they cost, so a caller that is slower than the decoder still gets one per call and a caller that
+ * feeds from memory gets a few large ones.  Both are what the zlib contract allows a Z_NO_FLUSH call to do. */
 typedef struct zs_stream {
     const uint8_t* next_in;
     uint64_t avail_in;
