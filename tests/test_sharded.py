@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, wrap, q):
+def _worker(rank, world, port, wrap, q, size=700000):
     import sys
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -32,7 +32,7 @@ def _worker(rank, world, port, wrap, q):
     from oracle import oracle as O
     S = pkg("sharded")
     capi = pkg("capi")
-    data = make_text(700000, 77)
+    data = make_text(size, 77)
     chunk = 65536
     n_chunks = -(-len(data) // chunk)
     lo, hi = S.shard_range(n_chunks, rank, world)
@@ -80,11 +80,11 @@ def _worker(rank, world, port, wrap, q):
     dist.destroy_process_group()
 
 
-def _run(wrap):
+def _run(wrap, world=2, size=700000):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, wrap, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, wrap, q, size)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -103,6 +103,15 @@ def test_two_ranks_zlib_stream():
 def test_two_ranks_gzip_and_raw():
     assert all(ok for _, ok, _ in _run(2))
     assert all(ok for _, ok, _ in _run(0))
+
+
+def test_three_ranks_with_an_empty_range():
+    """Fewer chunks than ranks (2 chunks of 64 KiB over 3 ranks: rank 0's range is empty and it still writes the
+    wrapper header, an empty block and the marker): the plan, the stitched stream and the inverse exchange need no
+    special case."""
+    res = _run(1, world=3, size=100000)
+    assert len(res) == 3 and all(ok for _, ok, _ in res)
+    assert res[0][2] == 0 and 0 < res[1][2] < res[2][2]
 
 
 def test_shard_range_and_bit_concat():
