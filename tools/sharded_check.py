@@ -1,5 +1,7 @@
 """torchrun --nproc-per-node N tools/sharded_check.py : N-rank stitched deflate of one replicated
-input, gathered on rank 0 and decoded with C zlib + the oracle (run on the GPU box)."""
+input, gathered on rank 0 and decoded with C zlib + the oracle, and inflated again where it lies (every rank the
+part it holds, sharded.inflate_sharded; added after the last multi-GPU run of round 2: the 2-rank bench line and
+the one-GPU emulation in tests/test_sharded_gpu.py are its evidence so far).  Run on the GPU box."""
 import importlib, os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,10 +13,34 @@ S = importlib.import_module("zlib-streams-ts_b200.sharded")
 B = importlib.import_module("zlib-streams-ts_b200.batch")
 corpus = importlib.import_module("zlib-streams-ts_b200.corpus")
 ok = True
+
+
+def inverse_ok(data, res, rr, plan, chunk, wrap):
+    """The inverse split: every rank inflates the part it holds (sharded.inflate_sharded); all ranks get the verdict."""
+    n = data.numel()
+    lo, hi = S.shard_range(B.n_chunks_for(n, chunk), rank, world)
+    b0, b1 = lo * chunk, min(hi * chunk, n)
+    hist = min(b0, 32768)
+    good = True
+    try:
+        ip, iplan = S.inflate_sharded(res.out, int(rr.total_out_bytes), b1 - b0, wrap, data[b0 - hist: b0] if hist else None)
+        want = 1 if rank == world - 1 else -5
+        good = (ip.status == want and ip.out_len == b1 - b0 and ip.in_used == int(rr.total_out_bytes)
+                and bool(torch.equal(ip.out[: ip.out_len], data[b0:b1])) and iplan.total_len == n
+                and (wrap == 0 or iplan.check == plan.check))
+    except Exception as e:   # (the exchange inside inflate_sharded ran or did not run on every rank alike: it follows the GPU call)
+        print("inflate_sharded raised on rank", rank, repr(e))
+        good = False
+    t = torch.tensor([1 if good else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 for wrap, level, chunk, n in ((1, 6, 262144, 24 << 20), (2, 1, 65536, 10 << 20), (0, 6, 65536, (5 << 20) + 12345)):
     data = torch.from_numpy(corpus.mixed_numpy(n, 0xB200)).cuda()     # same bytes on every rank
     res, rr, plan = S.deflate_sharded(data, chunk, level, wrap)
     stream = S.gather_stream(res, rr, plan, wrap, dst=0)
+    inv = inverse_ok(data, res, rr, plan, chunk, wrap)
     if rank == 0:
         host = data.cpu().numpy().tobytes()
         wb = {0: -15, 1: 15, 2: 31}[wrap]
@@ -23,8 +49,8 @@ for wrap, level, chunk, n in ((1, 6, 262144, 24 << 20), (2, 1, 65536, 10 << 20),
         if wrap == 1: good &= plan.check == zlib.adler32(host)
         if wrap == 2: good &= plan.check == zlib.crc32(host)
         ref = len(zlib.compress(host, level))
-        print(f"wrap {wrap} level {level} world {world}: ok={good} size {len(stream)} vs zlib {ref} ({len(stream)/ref:.4f}) bit offsets {plan.bit_offset}")
-        ok &= good
+        print(f"wrap {wrap} level {level} world {world}: ok={good} inflate_sharded={inv} size {len(stream)} vs zlib {ref} ({len(stream)/ref:.4f}) bit offsets {plan.bit_offset}")
+        ok &= good and inv
     dist.barrier()
 # randomised part (argument: seconds): sizes down to fewer chunks than ranks, every level, both chunk sizes
 import numpy as np, time
@@ -44,10 +70,11 @@ while True:
     data = torch.from_numpy(corpus.mixed_numpy(n, seed)).cuda()
     res, rr, plan = S.deflate_sharded(data, chunk, level, wrap)
     stream = S.gather_stream(res, rr, plan, wrap, dst=0)
+    inv = inverse_ok(data, res, rr, plan, chunk, wrap)
     if rank == 0:
         host = data.cpu().numpy().tobytes()
         d = zlib.decompressobj({0: -15, 1: 15, 2: 31}[wrap])
-        good = d.decompress(stream) + d.flush() == host and d.eof
+        good = d.decompress(stream) + d.flush() == host and d.eof and inv
         if not good:
             print("random case FAILED", it, n, wrap, level, chunk, seed)
         ok &= good
