@@ -16,21 +16,25 @@ ok = True
 
 
 def inverse_ok(data, res, rr, plan, chunk, wrap):
-    """The inverse split: every rank inflates the part it holds (sharded.inflate_sharded); all ranks get the verdict."""
+    """The inverse split, sharded.inflate_sharded spelled out: every rank inflates the part it holds, the ranks fold
+    checksums and lengths; all ranks get the verdict."""
     n = data.numel()
     lo, hi = S.shard_range(B.n_chunks_for(n, chunk), rank, world)
     b0, b1 = lo * chunk, min(hi * chunk, n)
     hist = min(b0, 32768)
-    good = True
-    try:
-        ip, iplan = S.inflate_sharded(res.out, int(rr.total_out_bytes), b1 - b0, wrap, data[b0 - hist: b0] if hist else None)
-        want = 1 if rank == world - 1 else -5
-        good = (ip.status == want and ip.out_len == b1 - b0 and ip.in_used == int(rr.total_out_bytes)
-                and bool(torch.equal(ip.out[: ip.out_len], data[b0:b1])) and iplan.total_len == n
-                and (wrap == 0 or iplan.check == plan.check))
-    except Exception as e:   # (the exchange inside inflate_sharded ran or did not run on every rank alike: it follows the GPU call)
-        print("inflate_sharded raised on rank", rank, repr(e))
-        good = False
+    capi = importlib.import_module("zlib-streams-ts_b200.capi")
+    kind = None if wrap == 0 else (capi.KIND_ADLER32 if wrap == 1 else capi.KIND_CRC32)
+    ip = None
+    try:   # the GPU call alone may fail on one rank: the exchange below runs on every rank whatever happened
+        ip = S.inflate_part(res.out, int(rr.total_out_bytes), b1 - b0, wrap, rank == 0, data[b0 - hist: b0] if hist else None)
+    except Exception as e:
+        print("inflate_part raised on rank", rank, repr(e))
+    meta = (ip.in_used * 8, ip.check, ip.out_len) if ip is not None else (0, 0, 0)
+    iplan = S.exchange_meta(meta[0], meta[1], meta[2], kind, 0, device=data.device)
+    want = 1 if rank == world - 1 else -5
+    good = (ip is not None and ip.status == want and ip.out_len == b1 - b0 and ip.in_used == int(rr.total_out_bytes)
+            and bool(torch.equal(ip.out[: ip.out_len], data[b0:b1])) and iplan.total_len == n
+            and (wrap == 0 or iplan.check == plan.check))
     t = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return bool(t.item())
