@@ -304,12 +304,6 @@ InflateState* istate(zs_stream* s) {
     return st->magic == 0x494e464c ? st : nullptr;
 }
 
-void put_be32(std::vector<uint8_t>& v, uint32_t x) {
-    v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
-}
-void put_le32(std::vector<uint8_t>& v, uint32_t x) {
-    v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 24));
-}
 
 void put_be32(HostBuf& v, uint32_t x) {
     const uint8_t b[4] = {(uint8_t)(x >> 24), (uint8_t)(x >> 16), (uint8_t)(x >> 8), (uint8_t)x};
