@@ -20,6 +20,12 @@
  *                                deflate.ts:1310-1322) is passed over without using up the chain budget; at most N per position
  *   too_far=D too_far4=D         greedy levels: 3-byte (4-byte) matches at a distance above D become literals
  *   chain=N nice=N               override the level's max_chain / nice_length
+ *   probe=K                      greedy levels, "parse before search": every position is PROBED with K candidates only, a
+ *                                greedy parse over the probe results marks the positions it visits, only those get the full
+ *                                chain walk, and the final parse uses the full result where there is one and the probe
+ *                                result elsewhere (a longer match moves the parse onto positions that were only probed).
+ *                                Reports the share of positions that are searched in full and the walk of the COMPACTED
+ *                                batches (32 visited positions per warp).
  *   dump=path                    write the symbols (lit<<24 | len<<15 | dist) as little-endian u32
  */
 #include <stdint.h>
@@ -39,6 +45,7 @@ static uint16_t head[1 << kHashBits], prev16[32768];
 static int dense_hop = 8, interior_chain = 16, stop_active = 0, stop_after = 0, work_shift = -1;
 static int too_far_greedy = 4096, too_far4 = 0;   /* greedy levels: a 3-byte (4-byte) match further back than this becomes a literal */
 static int chain_override = 0, nice_override = 0;   /* chain= / nice=: replace the level's max_chain / nice_length */
+static int probe_k = 0;                   /* probe=K: two-phase search of the greedy levels */
 static int skip_lag = 0, skip_cap = 16;   /* greedy levels: candidates the reference would not have inserted are passed over */
 static uint8_t* mark;                     /* 1 = deflate_fast would have put this position into its hash chains */
 
@@ -270,6 +277,7 @@ int main(int argc, char** argv) {
         else if (!strncmp(argv[i], "too_far4=", 9)) too_far4 = atoi(argv[i] + 9);
         else if (!strncmp(argv[i], "chain=", 6)) chain_override = atoi(argv[i] + 6);
         else if (!strncmp(argv[i], "nice=", 5)) nice_override = atoi(argv[i] + 5);
+        else if (!strncmp(argv[i], "probe=", 6)) probe_k = atoi(argv[i] + 6);
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
     level_cfg cfg_copy = LEVELS[level];
@@ -284,6 +292,9 @@ int main(int argc, char** argv) {
     if (skip_lag) mark = (uint8_t*)calloc(total + 300, 1);
     uint64_t bits = 0, nsym_total = 0, cand_total = 0, simt_total = 0, batches = 0, nblocks = 0, stopped = 0, rounds_total = 0, simt_heavy = 0, step_heavy_total = 0, steps = 0;
     uint64_t hist[16] = {0};   /* longest walk of a batch, log2 buckets */
+    uint64_t probe_cand = 0, full_positions = 0, full_cand = 0, full_batches = 0, full_simt = 0, data_positions = 0;
+    unsigned cw[32], ncw = 0;   /* walks of the visited positions waiting to fill a compacted batch */
+    if (probe_k && lazy) { fprintf(stderr, "probe= applies to the greedy levels\n"); return 2; }
 
     for (size_t seg_start = 0; seg_start < total; seg_start += seg_chunks * chunk) {
         size_t seg_end = seg_start + seg_chunks * chunk;
@@ -321,6 +332,7 @@ int main(int argc, char** argv) {
                 if (pcs >= seg_end) break;                                                                               \
             }                                                                                                            \
         }
+        size_t pp1 = seg_start;   /* probe=: the parse over the probe results */
         for (size_t q0 = 0; q0 < n; q0 += 32) {
             if (skip_lag && prime0 + q0 > seg_start + (size_t)skip_lag) PARSE_UNTIL(prime0 + q0 - (size_t)skip_lag);
             unsigned walk[32], rnd[32];
@@ -332,10 +344,30 @@ int main(int argc, char** argv) {
                 if (q < q_data || q >= n) continue;
                 const size_t abs = prime0 + q, cs = seg_start + ((abs - seg_start) / chunk) * chunk;
                 size_t ce = cs + chunk; if (ce > seg_end) ce = seg_end;
-                res[q - q_data] = search_pos(cfg, lazy, abs, prime0, pre, cs, ce, cross, 0, &walk[l], &rnd[l]);
+                res[q - q_data] = search_pos(cfg, lazy, abs, prime0, pre, cs, ce, cross, probe_k > 0 ? (unsigned)probe_k : 0, &walk[l], &rnd[l]);
                 if (walk[l] > longest) longest = walk[l];
+                data_positions++;
             }
             if (q0 + 32 <= q_data) continue;
+            if (probe_k > 0) {
+                /* the greedy parse over the probe results visits some positions of this batch: those are searched in full */
+                const size_t batch_end = prime0 + q0 + 32 < seg_end ? prime0 + q0 + 32 : seg_end;
+                for (unsigned l = 0; l < 32; l++) probe_cand += walk[l];
+                while (pp1 < batch_end) {
+                    const size_t cs = seg_start + ((pp1 - seg_start) / chunk) * chunk;
+                    size_t ce = cs + chunk; if (ce > seg_end) ce = seg_end;
+                    const unsigned L1 = (res[pp1 - seg_start] >> 15) & 0x1ffu;
+                    unsigned w = 0, r8 = 0;
+                    res[pp1 - seg_start] = search_pos(cfg, lazy, pp1, prime0, pre, cs, ce, cross, 0, &w, &r8);
+                    full_positions++; full_cand += w;
+                    cw[ncw++] = w;
+                    if (ncw == 32) { unsigned m = 0; for (unsigned i = 0; i < 32; i++) if (cw[i] > m) m = cw[i]; full_simt += m; full_batches++; ncw = 0; }
+                    pp1 += L1 >= 3 ? L1 : 1;           /* the probe's parse moves on by the PROBE's match */
+                    if (pp1 > ce) pp1 = ce;
+                }
+                for (unsigned l = 0; l < 32; l++) walk[l] = rnd[l] = 0;   /* the probe walks are accounted separately */
+                longest = 0;
+            }
             if (stop_active && longest > (unsigned)stop_after) {
                 /* the iteration at which at most stop_active lanes are still walking */
                 unsigned cap = (unsigned)stop_after;
@@ -378,6 +410,11 @@ int main(int argc, char** argv) {
            (unsigned long long)rounds_total, (double)rounds_total / (double)total, (double)simt_heavy / (double)batches);
     printf("steps %llu  heaviest batch of a 960-position step (what the CTA's barrier waits for): %.2f\n", (unsigned long long)steps,
            (double)step_heavy_total / (double)steps);
+    if (probe_k > 0)
+        printf("probe=%d: probe candidates %.2f per position; searched in full %.1f %% of the positions, %.2f candidates each, "
+               "compacted batches: longest walk %.2f\n", probe_k, (double)probe_cand / (double)data_positions,
+               100.0 * (double)full_positions / (double)data_positions, full_positions ? (double)full_cand / (double)full_positions : 0.0,
+               full_batches ? (double)full_simt / (double)full_batches : 0.0);
     printf("longest walk per batch, buckets [0] [1] [2-3] [4-7] ...:");
     for (int i = 0; i < 16; i++) printf(" %llu", (unsigned long long)hist[i]);
     printf("\n");
